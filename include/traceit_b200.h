@@ -1,0 +1,179 @@
+/* traceit_b200.h - C ABI of the B200-native TraceIt physics step.
+ *
+ * The reference (zxcfghjkl/TraceIt, one C++17 translation unit) has no plugin or FFI
+ * layer.  Its de-facto boundary for the physics path is
+ *     void updatePhysics(world& w, ofstream& coords)     reference src/main.cpp:748
+ *         called once per frame at                       reference src/main.cpp:1589
+ *     w.objects.push_back(newObj)  (body creation)       reference src/main.cpp:1242,1491
+ *     world{atmDensity,g,...} plain fields               reference src/main.cpp:118-126
+ * Every entry point below names the reference interface it replaces.  All functions
+ * return 0 (TR_OK) or a TR_ERR_* code, never throw, and take only plain pointers and
+ * sizes.  The C++ shim that restores the reference signature on top of this ABI is
+ * traceit_b200/host/traceit_host.hpp; the binding a maintainer adds is in INTEGRATION.md.
+ *
+ * There is NO CPU fallback: every compute entry point fails with TR_ERR_NO_DEVICE /
+ * TR_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef TRACEIT_B200_H
+#define TRACEIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TR_ABI_VERSION 1
+
+/* status codes */
+#define TR_OK 0
+#define TR_ERR_INVALID_ARG 1
+#define TR_ERR_NO_DEVICE 2   /* no CUDA device / not an sm_100 part                      */
+#define TR_ERR_CUDA 3        /* a CUDA runtime call or kernel failed; see tr_last_error  */
+#define TR_ERR_NCCL 4        /* NCCL could not be loaded or a collective failed          */
+#define TR_ERR_CAPACITY 5    /* contact buffer overflow: raise tr_world_params.max_contacts */
+#define TR_ERR_DOMAIN 6      /* reserved (out-of-domain bodies are handled by the side list) */
+#define TR_ERR_STATE 7       /* call not valid in the world's current state              */
+#define TR_ERR_NOMEM 8
+
+/* tr_world_params.flags */
+#define TR_PAIR_GRAVITY 1u   /* Newtonian all-pairs term, reference src/main.cpp:679-693
+                                (dead code there, hence OFF by default)                 */
+#define TR_COLLISIONS 2u     /* resolveCollisions sweep, reference src/main.cpp:673-745  */
+
+typedef struct tr_world tr_world; /* opaque; owns all device buffers, streams, comms */
+
+/* World parameters.  Defaults (tr_default_params) equal the reference's constants:
+ *   g = {0,(float)-9.8,0}   hard-coded local, src/main.cpp:749  (world::g is never read)
+ *   G = 6.6743e-11f         src/main.cpp:685
+ *   dt = 0.01666f           src/main.cpp:750
+ *   atm_density = 1.2f      world::atmDensity, UI default src/main.cpp:1141
+ *   flags = TR_COLLISIONS   (what the live reference step does)                        */
+typedef struct tr_world_params {
+    float g[3];
+    float G;
+    float dt;
+    float atm_density;
+    uint32_t flags;
+    /* Uniform-grid broad phase (no reference counterpart; the reference is brute force).
+     * 0 / zeros = automatic.  cell edge defaults to 2*rmax*(1+2^-7) where rmax is the
+     * largest radius among grid bodies; grid_bits is bits per axis of the wrapped key
+     * (2..10).  Bodies that cannot live in the grid (boxes, oversize or out-of-domain
+     * spheres) go to a side list that is tested against every body.                    */
+    float grid_origin[3];
+    float grid_cell;
+    int32_t grid_bits;
+    uint64_t max_contacts;       /* 0 = 8*N + 4096 */
+    /* Largest radius admitted to the grid; 0 = automatic.              */
+    float grid_max_radius;
+    uint32_t reserved[3];
+} tr_world_params;
+
+/* Body descriptor = hot fields of the reference's `object` + `collider`
+ * (src/main.cpp:79-105), same names and meaning.  The UI-side parameter contract
+ * (mass [1,1000], Cd [0,2] default 0.42, size [1,10], rest 0.5; src/main.cpp:1216-1224,
+ * 1302-1307) is NOT enforced here, exactly as push_back does not enforce it.          */
+typedef struct tr_body_desc {
+    float pos[3];
+    float vel[3];
+    float force[3];     /* external force, consumed and zeroed by each step (main.cpp:782,811) */
+    float mass;
+    float Cd;
+    float area;
+    int32_t stationary; /* object::stationary: skipped by the integrator (main.cpp:764)  */
+    float center[3];    /* collider::center (refreshed from pos only when !stationary)   */
+    float size[3];      /* collider::size, AABB half-extents as used (main.cpp:648-652)  */
+    float radius;       /* collider::radius                                              */
+    int32_t isSphere;
+    int32_t isStatic;   /* collider::isStatic: immune to impulses/nudges (main.cpp:725-741) */
+    float rest;         /* collider::rest                                                */
+} tr_body_desc;         /* 92 bytes */
+
+typedef struct tr_stats {
+    uint64_t steps;              /* steps executed since creation / last reset           */
+    uint64_t kernel_launches;    /* launches of THIS library's kernels                   */
+    uint64_t last_contacts;      /* contacts found by the last step                      */
+    uint64_t last_candidates;    /* candidate pairs tested by the last step (debug mode) */
+    uint32_t last_response_rounds; /* wavefront depth of the last ordered response      */
+    uint32_t side_list_size;     /* bodies outside the grid at the last step             */
+    double gravity_ms;           /* accumulated device time of the gravity kernel        */
+    uint64_t gravity_launches;
+    double broadphase_ms;        /* keys + sort + ranges (K2-K4)                         */
+    uint64_t broadphase_launches;/* number of timed broad-phase passes (one per step)    */
+    double narrowphase_ms;       /* K5                                                   */
+    double response_ms;          /* contact sort + dependency build + K6                 */
+    double integrate_ms;         /* standalone integrator (pair gravity off)             */
+    double allgather_ms;         /* NCCL all-gather (sharded worlds)                     */
+    uint64_t interactions;       /* ordered pair interactions evaluated (N_targets * N)  */
+} tr_stats;
+
+/* ---- library --------------------------------------------------------------------- */
+int tr_abi_version(void);
+const char* tr_last_error(void);                 /* thread-local message of the last failure */
+int tr_device_count(int* count);
+int tr_default_params(tr_world_params* p);
+
+/* ---- world lifetime: replaces `world w;` (src/main.cpp:1479-1481) ----------------- */
+int tr_world_create(const tr_world_params* p, int device, tr_world** out);
+/* Sharded world, one process per GPU: rank owns a contiguous block of target bodies,
+ * holds every source position, and all-gathers float4(x,y,z,m) each step over NCCL.
+ * unique_id: 128 bytes from tr_comm_unique_id on rank 0, distributed by the caller.    */
+int tr_comm_unique_id(void* out128);
+int tr_world_create_sharded(const tr_world_params* p, int device, int rank, int nranks,
+                            const void* unique_id128, tr_world** out);
+int tr_world_destroy(tr_world* w);
+int tr_world_set_params(tr_world* w, const tr_world_params* p);   /* world field writes  */
+int tr_world_get_params(tr_world* w, tr_world_params* p);
+/* Run on the caller's CUDA stream (cudaStream_t) instead of the world's own.           */
+int tr_world_set_stream(tr_world* w, void* cuda_stream);
+
+/* ---- body creation: replaces w.objects.push_back(obj) (src/main.cpp:1242,1491) ----- */
+int tr_body_add(tr_world* w, const tr_body_desc* b, uint32_t* id);
+int tr_bodies_add(tr_world* w, uint64_t n, const tr_body_desc* b, uint32_t* first_id);
+int tr_world_size(tr_world* w, uint64_t* n);
+int tr_world_owned_range(tr_world* w, uint64_t* first, uint64_t* count); /* sharded worlds */
+/* Creation helpers of the reference UI path, in its own mixed double/float arithmetic:
+ * toSpherical (src/main.cpp:1080-1089) and area = M_PI*size*size (src/main.cpp:1295).  */
+int tr_to_spherical(float elev_deg, float azim_deg, float magnitude, float out_vel[3]);
+float tr_area_from_size(float size);
+
+/* ---- the step: replaces updatePhysics(w, coords) (src/main.cpp:748, call site 1589) - */
+int tr_step(tr_world* w, int nsteps);            /* asynchronous on the world's stream    */
+int tr_sync(tr_world* w);                        /* wait; reports deferred device errors  */
+/* Host-buffer round trip used by the C++ shim: upload bodies[0..n) (AoS), run nsteps,
+ * read them back.  n must equal the world size (bodies are created on first use).      */
+int tr_step_host(tr_world* w, uint64_t n, tr_body_desc* bodies_inout, int nsteps);
+
+/* ---- state access: replaces direct reads/writes of w.objects[i] -------------------- */
+int tr_read_state(tr_world* w, uint64_t first, uint64_t count, float* pos_xyz, float* vel_xyz);
+int tr_read_bodies(tr_world* w, uint64_t first, uint64_t count, tr_body_desc* out);
+int tr_write_bodies(tr_world* w, uint64_t first, uint64_t count, const tr_body_desc* in);
+int tr_set_force(tr_world* w, uint32_t id, float fx, float fy, float fz); /* obj.force = */
+
+/* ---- parity / observability --------------------------------------------------------- */
+/* Contact set of the last step in lexicographic (i,j) order, i<j: the pairs for which
+ * the reference's guards + predicate (src/main.cpp:695-707) hold.  pairs may be NULL.  */
+int tr_read_contacts(tr_world* w, int32_t* pairs_ij, uint64_t cap, uint64_t* n);
+/* Broad-phase internals of the last step (each pointer may be NULL):
+ *   keys[N]        wrapped cell key per body id (0xFFFFFFFF for side-list bodies)
+ *   sorted_ids[M]  grid body ids in (key,id) order;  *m receives M
+ *   cell, inv_cell, bits: the grid actually used.                                       */
+int tr_debug_grid(tr_world* w, uint32_t* keys, uint32_t* sorted_ids, uint64_t* m,
+                  float* cell, float* inv_cell, int32_t* bits);
+/* Re-run the last step's broad phase emitting every candidate pair (i<j) of the grid
+ * (not the side list), lexicographically sorted.  pairs may be NULL to only count.     */
+int tr_debug_candidates(tr_world* w, int32_t* pairs_ij, uint64_t cap, uint64_t* n);
+/* Pair-gravity force per body for the CURRENT positions (3 floats each, owned range).  */
+int tr_debug_gravity(tr_world* w, float* force_xyz);
+int tr_get_stats(tr_world* w, tr_stats* s);
+int tr_reset_stats(tr_world* w);
+int tr_enable_timing(tr_world* w, int on);       /* per-kernel CUDA-event timing          */
+
+/* FP32 FMA-pipe peak of `device`, measured with an FFMA-only kernel (lane-ops/s where a
+ * lane-op is one fp32 FMA-pipe operation on one lane) plus the SM clock it ran at.      */
+int tr_measure_fma_peak(int device, double* lane_ops_per_s, double* sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRACEIT_B200_H */
