@@ -91,6 +91,7 @@ def lib():
         L.orc_resolve_list.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
         L.orc_pair_gravity_f32.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p]
         L.orc_pair_gravity_f64.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+        L.orc_pair_gravity_f64_subset.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p]
         L.orc_contacts.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong]
         L.orc_contacts.restype = C.c_longlong
         L.orc_grid_cells.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p]
@@ -165,6 +166,13 @@ def pair_gravity_f32(bodies: np.ndarray, G: float) -> np.ndarray:
 def pair_gravity_f64(bodies: np.ndarray, G: float) -> np.ndarray:
     out = np.empty((len(bodies), 3), dtype=np.float64)
     lib().orc_pair_gravity_f64(_ptr(bodies), len(bodies), C.c_double(G), _ptr(out))
+    return out
+
+
+def pair_gravity_f64_subset(bodies: np.ndarray, G: float, idx) -> np.ndarray:
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    out = np.empty((len(idx), 3), dtype=np.float64)
+    lib().orc_pair_gravity_f64_subset(_ptr(bodies), len(bodies), C.c_double(G), _ptr(idx), len(idx), _ptr(out))
     return out
 
 

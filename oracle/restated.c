@@ -151,6 +151,30 @@ void orc_pair_gravity_f64(const orc_body* b, int n, double G, double* out) {
     }
 }
 
+/* fp64 force on a SUBSET of targets against all n sources: lets the 1M-body tests check
+ * sampled targets without the O(N^2) cost.  out: 3 doubles per listed target. */
+void orc_pair_gravity_f64_subset(const orc_body* b, int n, double G, const int32_t* idx, int m, double* out) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int t = 0; t < m; ++t) {
+        int k = idx[t];
+        double f[3] = {0.0, 0.0, 0.0};
+        double xk = b[k].pos[0], yk = b[k].pos[1], zk = b[k].pos[2], mk = b[k].mass;
+        for (int j = 0; j < n; ++j) {
+            if (j == k) continue;
+            double dx = (double)b[j].pos[0] - xk, dy = (double)b[j].pos[1] - yk, dz = (double)b[j].pos[2] - zk;
+            double d2 = dx * dx + dy * dy + dz * dz;
+            double inv = 1.0 / sqrt(d2);
+            double s = G * mk * (double)b[j].mass * inv * inv * inv;
+            f[0] += dx * s;
+            f[1] += dy * s;
+            f[2] += dz * s;
+        }
+        out[3 * t + 0] = f[0];
+        out[3 * t + 1] = f[1];
+        out[3 * t + 2] = f[2];
+    }
+}
+
 /* Drag + uniform gravity + force sum + semi-implicit Euler for one body
  * (main.cpp:763-791, 811).  fgrav may be NULL (pair gravity off). */
 static void integrate_body(orc_body* o, const orc_params* p, const float* fgrav) {

@@ -1,0 +1,59 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+def bits(a):
+    """Bit pattern view of a float32 array (for exact comparisons incl. signed zeros / NaNs)."""
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def assert_bits_equal(a, b, what=""):
+    a, b = bits(a), bits(b)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    bad = np.nonzero(a != b)
+    assert len(bad[0]) == 0, f"{what}: {len(bad[0])} of {a.size} words differ, first at {tuple(x[0] for x in bad)}"
+
+
+def mixed_cloud():
+    """Same construction as tests/golden/make_golden.py::mixed_cloud."""
+    from traceit_b200 import scenes
+    m = scenes.random_cloud(1024, 77, spheres=True, density_l=0.5)
+    m["isSphere"][::3] = 0
+    m["size"][::3] = (0.6, 0.4, 0.5)
+    m["isStatic"][::7] = 1
+    m["stationary"][::11] = 1
+    m["mass"][::13] = 0
+    m["rest"][::5] = 0.9
+    return m
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import pyoracle as po
+    po.lib()
+    return po
+
+
+@pytest.fixture(scope="session")
+def tr():
+    """The product binding; gpu tests fail (not skip) when the extension is missing."""
+    import traceit_b200
+    traceit_b200.lib()
+    return traceit_b200
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name))

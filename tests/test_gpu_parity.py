@@ -1,0 +1,323 @@
+"""GPU parity tests (run on a B200 with `-m gpu`): every call goes through the C ABI of
+libtraceit_b200.so and is compared with the CPU oracle on the same seeded inputs.
+
+Bars (SURVEY.md 8d / north_star):
+  * integrator, collision detection, contact set, collision response: BIT-EXACT;
+  * cell keys, sort order, candidate-pair set: BIT-EXACT against the CPU grid restatement;
+  * pair gravity (dead code in the reference, restated): force rel. L2 <= 1e-5 against the
+    fp64 restatement; positions/velocities after K steps: max error <= 1e-4 relative to the
+    cloud extent / rms speed against the fp32 restated oracle.
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_bits_equal, load_golden, mixed_cloud
+from traceit_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("pos", "vel", "force", "center")
+FORCE_REL_L2_TOL = 1e-5      # GPU pair-gravity force vs fp64 restatement
+TRAJ_REL_TOL = 1e-4          # pos/vel after K steps vs fp32 restated oracle
+
+
+def gpu_run(tr, bodies, steps, **pover):
+    p = tr.default_params(**pover)
+    with tr.World(p) as w:
+        w.add(bodies)
+        w.step(steps)
+        out = w.read_bodies()
+        contacts = w.contacts() if (p.flags & tr.COLLISIONS) else None
+        stats = w.stats()
+    return out, contacts, stats
+
+
+def check_state(got, want, what):
+    for f in FIELDS:
+        assert_bits_equal(got[f], want[f], f"{what}:{f}")
+
+
+# ---------------------------------------------------------------- O(N) integrator
+def test_integrator_bit_exact(tr, oracle):
+    rs = np.random.RandomState(42)
+    n = 10007
+    b = scenes.random_cloud(n, 5, spheres=True)
+    b["stationary"][rs.rand(n) < 0.1] = 1
+    b["force"] = rs.uniform(-20, 20, size=(n, 3)).astype(np.float32)
+    b["vel"][rs.rand(n) < 0.05] = 0          # exercises the speedSq <= 1e-4 branch
+    b["vel"][7] = (0.005, 0.0, 0.0)
+    b["Cd"] = rs.uniform(0, 2, n).astype(np.float32)
+    got, _, st = gpu_run(tr, b, 25, flags=0, atm_density=np.float32(0.9))
+    want = b.copy()
+    oracle.step(want, oracle.default_params(flags=0, atm_density=np.float32(0.9)), 25)
+    check_state(got, want, "integrator")
+    assert st.kernel_launches >= 25
+
+
+def test_step_host_round_trip_equals_step(tr, oracle):
+    b = scenes.random_cloud(3000, 8, spheres=True, density_l=0.6)
+    want = b.copy()
+    oracle.step(want, oracle.default_params(), 3)
+    p = tr.default_params()
+    with tr.World(p) as w:
+        cur = b.copy()
+        for _ in range(3):
+            w.step_host(cur, 1)      # upload AoS -> step -> read back, the shim's per-frame path
+    check_state(cur, want, "step_host")
+
+
+# ---------------------------------------------------------------- goldens from the verbatim reference
+def test_default_scene_golden_gpu(tr):
+    """Config 1 on the GPU: boxes + the 10000x5x10000 slab (side list), 1000 steps."""
+    g = load_golden("default_scene.npz")
+    got, contacts, st = gpu_run(tr, g["initial"].copy(), 1000)
+    check_state(got, g["final"], "default scene")
+    assert np.array_equal(contacts, g["contacts"])
+    assert st.side_list_size == 3
+
+
+@pytest.mark.parametrize("name,steps", [("sphere_cloud_2048_s1.npz", 1), ("sphere_cloud_2048_s50.npz", 50),
+                                        ("mixed_cloud_1024_s40.npz", 40), ("dense_lattice_12_s20.npz", 20)])
+def test_cloud_goldens_gpu(tr, name, steps):
+    g = load_golden(name)
+    got, contacts, st = gpu_run(tr, g["initial"].copy(), steps)
+    check_state(got, g["final"], name)
+    assert np.array_equal(contacts, g["contacts"]), name
+
+
+# ---------------------------------------------------------------- broad phase: keys, order, candidates
+@pytest.mark.parametrize("n,dens,bits", [(20000, 0.7, 0), (20000, 0.7, 3), (5000, 3.0, 2), (4096, 0.5, 6)])
+def test_grid_keys_sort_candidates_bit_exact(tr, oracle, n, dens, bits):
+    b = scenes.random_cloud(n, 100 + bits, spheres=True, density_l=dens)
+    b["radius"] = np.random.RandomState(bits).uniform(0.2, 0.5, n).astype(np.float32)
+    b["mass"][::17] = 0          # dropped from the grid
+    b["isSphere"][::29] = 0      # boxes -> side list
+    p = tr.default_params(flags=tr.COLLISIONS, grid_bits=bits)
+    with tr.World(p) as w:
+        w.add(b)
+        g = w.debug_grid()
+        ncand, cand = w.debug_candidates()
+    gb = g["bits"]
+    in_grid = (b["isSphere"] != 0) & ~(b["mass"] <= 0)
+    keys = oracle.grid_keys(b, (0, 0, 0), g["inv_cell"], gb)
+    assert np.array_equal(g["keys"][in_grid], keys[in_grid])
+    assert (g["keys"][~in_grid] == 0xFFFFFFFF).all()
+    order, _ = oracle.grid_sort(keys, np.nonzero(in_grid)[0].astype(np.int32), gb)
+    assert np.array_equal(g["sorted_ids"].astype(np.int32), order)
+    ocand, _, nc, _ = oracle.grid_pairs(b, in_grid.astype(np.uint8), (0, 0, 0), g["inv_cell"], gb, want_contacts=False)
+    assert ncand == nc
+    assert np.array_equal(cand, ocand)
+    # the grid actually used is the documented one
+    rmax = float(b["radius"][in_grid].max())
+    assert g["cell"] == np.float32(np.float32(2.0 * rmax) * np.float32(1.0078125))
+
+
+@pytest.mark.parametrize("n,dens", [(30000, 0.6), (30000, 4.0)])
+def test_contact_set_equals_brute_force(tr, oracle, n, dens):
+    b = scenes.random_cloud(n, 321, spheres=True, density_l=dens)
+    b["isStatic"][::5] = 1
+    b["isSphere"][::1000] = 0
+    b["size"][::1000] = (3.0, 0.2, 3.0)
+    b["radius"][5] = 40.0          # oversize sphere -> side list
+    want = b.copy()
+    oracle.integrate(want, oracle.default_params())
+    brute = oracle.contacts(want)
+    p = tr.default_params()
+    with tr.World(p) as w:
+        w.add(b)
+        w.step(1)
+        got = w.contacts()
+        st = w.stats()
+    assert np.array_equal(got, brute)
+    assert st.side_list_size == len(range(0, n, 1000)) + (0 if 5 % 1000 == 0 else 1)
+    assert st.last_contacts == len(brute)
+
+
+def test_out_of_domain_bodies_use_side_list(tr, oracle):
+    b = scenes.random_cloud(4000, 77, spheres=True, density_l=0.6)
+    b["pos"][10] = (1e6, 0, 0)
+    b["pos"][11] = (1e6 + 0.25, 0, 0)   # touches body 10, far outside the grid domain
+    b["pos"][12] = (np.nan, 0, 0)
+    b["center"] = b["pos"]
+    want = b.copy()
+    oracle.step(want, oracle.default_params(), 2)
+    got, contacts, st = gpu_run(tr, b, 2)
+    assert st.side_list_size >= 3
+    for f in FIELDS:
+        assert_bits_equal(got[f], want[f], f"domain:{f}")
+    assert np.array_equal(contacts, oracle.contacts(want))
+
+
+# ---------------------------------------------------------------- response order
+def test_dense_lattice_response_bit_exact(tr, oracle):
+    """Config 5 (small): ~3 contacts per body, lattice-ordered ids = long Gauss-Seidel chains."""
+    b = scenes.dense_lattice(20)           # 8000 bodies
+    p = oracle.default_params(g=(0, 0, 0))
+    want = b.copy()
+    for _ in range(10):
+        oracle.integrate(want, p)
+        oracle.resolve_list(want, oracle.contacts(want))
+    got, contacts, st = gpu_run(tr, b, 10, g=(0, 0, 0))
+    check_state(got, want, "dense lattice")
+    assert np.array_equal(contacts, oracle.contacts(want))
+    assert st.last_response_rounds >= 1
+
+
+def test_shuffled_ids_response_bit_exact(tr, oracle):
+    b = scenes.dense_lattice(16, shuffle_ids=True)
+    p = oracle.default_params(g=(0, 0, 0))
+    want = b.copy()
+    for _ in range(6):
+        oracle.integrate(want, p)
+        oracle.resolve_list(want, oracle.contacts(want))
+    got, _, _ = gpu_run(tr, b, 6, g=(0, 0, 0))
+    check_state(got, want, "shuffled lattice")
+
+
+def test_contact_capacity_overflow_is_loud(tr):
+    b = scenes.dense_lattice(10)
+    p = tr.default_params(max_contacts=16)
+    with tr.World(p) as w:
+        w.add(b)
+        with pytest.raises(tr.TraceItError) as e:
+            w.step(1)
+        assert e.value.code == 5
+
+
+# ---------------------------------------------------------------- pair gravity
+@pytest.mark.parametrize("n", [1, 2, 300, 2048, 5000, 16384, 20001])
+def test_gravity_force_vs_f64(tr, oracle, n):
+    b = scenes.random_cloud(n, 1000 + n, spheres=True)
+    p = tr.default_params(flags=tr.PAIR_GRAVITY, G=np.float32(1.0), g=(0, 0, 0))
+    with tr.World(p) as w:
+        w.add(b)
+        f = w.debug_gravity().astype(np.float64)
+    if n == 1:
+        assert (f == 0).all()
+        return
+    f64 = oracle.pair_gravity_f64(b, 1.0)
+    rel = np.linalg.norm(f - f64) / np.linalg.norm(f64)
+    f32 = oracle.pair_gravity_f32(b, 1.0).astype(np.float64)
+    rel_cpu = np.linalg.norm(f32 - f64) / np.linalg.norm(f64)
+    print(f"n={n}: GPU rel L2 {rel:.3e}  (CPU fp32 restatement {rel_cpu:.3e})")
+    assert rel <= FORCE_REL_L2_TOL
+
+
+def test_gravity_coincident_and_zero_mass(tr, oracle):
+    """Edge semantics of the restated formula: coincident DISTINCT bodies -> NaN (G*m*m/0 *
+    normalize(0)), exactly like the CPU restatement; zero-mass bodies feel nothing but the
+    self pair never contributes."""
+    b = scenes.random_cloud(600, 3, spheres=True)
+    b["pos"][1] = b["pos"][0]
+    b["mass"][5] = 0
+    p = tr.default_params(flags=tr.PAIR_GRAVITY, G=np.float32(1.0), g=(0, 0, 0))
+    with tr.World(p) as w:
+        w.add(b)
+        f = w.debug_gravity()
+    cpu = oracle.pair_gravity_f32(b, 1.0)
+    assert np.array_equal(np.isnan(f), np.isnan(cpu))
+    assert np.isnan(f[0]).all() and np.isnan(f[1]).all()
+    assert (f[5] == 0).all()
+    ok = ~np.isnan(cpu).any(axis=1)
+    f64 = oracle.pair_gravity_f64(b, 1.0)
+    assert np.linalg.norm(f[ok] - f64[ok]) / np.linalg.norm(f64[ok]) <= FORCE_REL_L2_TOL
+
+
+def _traj_errors(got, want):
+    extent = np.abs(want["pos"]).max()
+    vrms = np.sqrt((want["vel"].astype(np.float64) ** 2).sum(axis=1).mean())
+    epos = np.abs(got["pos"].astype(np.float64) - want["pos"]).max() / extent
+    evel = np.abs(got["vel"].astype(np.float64) - want["vel"]).max() / vrms
+    return epos, evel
+
+
+@pytest.mark.parametrize("n,steps", [(8192, 100), (65536, 4)])
+def test_gravity_trajectory_vs_restated_oracle(tr, oracle, n, steps):
+    """Config 2 shape: gravity + drag + integration, collisions off, K steps."""
+    b = scenes.random_cloud(n, scenes.SEED_CFG2, spheres=True)
+    flags = tr.PAIR_GRAVITY
+    got, _, st = gpu_run(tr, b, steps, flags=flags, G=np.float32(1.0), g=(0, 0, 0))
+    want = b.copy()
+    oracle.step(want, oracle.default_params(flags=oracle.PAIR_GRAVITY, G=np.float32(1.0), g=(0, 0, 0)), steps)
+    epos, evel = _traj_errors(got, want)
+    print(f"n={n} K={steps}: max pos err / extent = {epos:.3e}, max vel err / vrms = {evel:.3e}")
+    assert epos <= TRAJ_REL_TOL and evel <= TRAJ_REL_TOL
+    assert st.interactions == n * n * steps
+
+
+def test_gravity_plus_collisions_small(tr, oracle):
+    """Full step (gravity + drag + integrate + collisions) on a dense small cloud: the contact
+    sets must agree exactly whenever positions do, and trajectories within tolerance."""
+    b = scenes.random_cloud(3000, 17, spheres=True, density_l=0.6)
+    flags = tr.PAIR_GRAVITY | tr.COLLISIONS
+    got, contacts, _ = gpu_run(tr, b, 5, flags=flags, G=np.float32(1e-3), g=(0, 0, 0))
+    want = b.copy()
+    oracle.step(want, oracle.default_params(flags=oracle.PAIR_GRAVITY | oracle.COLLISIONS, G=np.float32(1e-3),
+                                           g=(0, 0, 0)), 5)
+    epos, evel = _traj_errors(got, want)
+    assert epos <= TRAJ_REL_TOL and evel <= TRAJ_REL_TOL
+    # the GPU's own contact set equals brute force on the GPU's own centres
+    assert np.array_equal(contacts, oracle.contacts(got))
+
+
+def test_sharded_world_of_one_rank_is_bit_identical(tr):
+    b = scenes.random_cloud(9000, 4, spheres=True)
+    p = tr.default_params(flags=tr.PAIR_GRAVITY, G=np.float32(1.0), g=(0, 0, 0))
+    a, _, _ = gpu_run(tr, b, 3, flags=tr.PAIR_GRAVITY, G=np.float32(1.0), g=(0, 0, 0))
+    with tr.World(p, rank=0, nranks=1) as w:
+        w.add(b)
+        assert w.owned_range() == (0, 9000)
+        w.step(3)
+        c = w.read_bodies()
+    check_state(a, c, "sharded(1)")
+
+
+def test_empty_world_and_errors(tr):
+    with tr.World() as w:
+        w.step(3)
+        assert len(w) == 0
+        assert len(w.contacts()) == 0
+        with pytest.raises(tr.TraceItError):
+            w.read_state(0, 5)
+    with pytest.raises(tr.TraceItError):
+        tr.World(tr.default_params(grid_bits=1))
+    with pytest.raises(tr.TraceItError):
+        tr.World(device=99)
+
+
+# ---------------------------------------------------------------- full-size properties (BASELINE sizes)
+def test_full_size_1m_properties(tr, oracle):
+    """Config 3 at N = 1,048,576: (a) sampled targets' force vs fp64; (b) total momentum change
+    ~ 0 (Newton's third law over the fp32 sums); (c) contact set equals the CPU grid
+    restatement and, for sampled rows, brute force."""
+    n = 1 << 20
+    b = scenes.cfg3_cloud(n)
+    p = tr.default_params(flags=tr.PAIR_GRAVITY | tr.COLLISIONS, G=np.float32(1.0), g=(0, 0, 0))
+    with tr.World(p) as w:
+        w.add(b)
+        f = w.debug_gravity().astype(np.float64)
+        idx = np.random.RandomState(0).choice(n, 128, replace=False).astype(np.int32)
+        f64 = oracle.pair_gravity_f64_subset(b, 1.0, idx)
+        rel = np.linalg.norm(f[idx] - f64) / np.linalg.norm(f64)
+        print(f"1M sampled-force rel L2 vs fp64: {rel:.3e}")
+        assert rel <= FORCE_REL_L2_TOL
+        tot = np.abs(f.sum(axis=0)).max() / np.abs(f).sum(axis=0).max()
+        print(f"1M |sum F| / sum |F| = {tot:.3e}")
+        assert tot < 1e-5
+        w.step(1)
+        got = w.read_bodies()
+        contacts = w.contacts()
+        g = w.debug_grid()
+    # contact set through the CPU grid on the GPU's own post-step centres
+    _, cont, _, nk = oracle.grid_pairs(got, np.ones(n, np.uint8), (0, 0, 0), g["inv_cell"], g["bits"], want_candidates=False)
+    assert np.array_equal(contacts, cont)
+    # brute-force rows for a few sampled bodies (numpy fp32, same op order as the predicate)
+    c = got["center"]
+    for i in np.random.RandomState(1).choice(n, 8, replace=False):
+        d = c[i] - c
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        rs = got["radius"][i] + got["radius"]
+        hit = np.nonzero((d2 <= rs * rs))[0]
+        hit = hit[hit != i]
+        mine = set(map(tuple, contacts[(contacts[:, 0] == i) | (contacts[:, 1] == i)].tolist()))
+        assert mine == {(min(i, j), max(i, j)) for j in hit.tolist()}

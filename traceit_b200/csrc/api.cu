@@ -1,0 +1,736 @@
+// C ABI of libtraceit_b200.so: world lifetime, body creation, AoS<->SoA transfer, the
+// step sequencer.  See include/traceit_b200.h for the reference interface each entry
+// point replaces.  No CPU fallback exists: without a usable CUDA device every compute
+// entry point returns an error.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "world.cuh"
+
+namespace tr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error '%s' in %s (%s:%d)", cudaGetErrorString(e), what, file, line);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return TR_ERR_NO_DEVICE;
+    if (e == cudaErrorMemoryAllocation) return TR_ERR_NOMEM;
+    return TR_ERR_CUDA;
+}
+
+// ---- timing -----------------------------------------------------------------------------
+static cudaEvent_t get_event(tr_world* w) {
+    if (!w->event_pool.empty()) {
+        cudaEvent_t e = w->event_pool.back();
+        w->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void timer_begin(tr_world* w, int cat, PendingTimer* t) {
+    t->cat = cat;
+    t->a = t->b = nullptr;
+    if (!w->timing) return;
+    t->a = get_event(w);
+    t->b = get_event(w);
+    cudaEventRecord(t->a, w->stream);
+}
+
+void timer_end(tr_world* w, PendingTimer* t) {
+    if (!w->timing || !t->a) return;
+    cudaEventRecord(t->b, w->stream);
+    w->pending.push_back(*t);
+}
+
+void timers_collect(tr_world* w) {
+    for (const PendingTimer& t : w->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+            switch (t.cat) {
+                case T_GRAVITY: w->stats.gravity_ms += ms; break;
+                case T_BROAD: w->stats.broadphase_ms += ms; w->stats.broadphase_launches += 1; break;
+                case T_NARROW: w->stats.narrowphase_ms += ms; break;
+                case T_RESPONSE: w->stats.response_ms += ms; break;
+                case T_INTEGRATE: w->stats.integrate_ms += ms; break;
+                case T_ALLGATHER: w->stats.allgather_ms += ms; break;
+            }
+        }
+        w->event_pool.push_back(t.a);
+        w->event_pool.push_back(t.b);
+    }
+    w->pending.clear();
+}
+
+// ---- AoS <-> SoA ------------------------------------------------------------------------
+struct SoA {
+    float4* pos_m;
+    float4* vel_rest;
+    float4* force;
+    float2* drag;
+    float4* center_r;
+    float4* half_ext;
+    uint8_t* flags;
+};
+
+__global__ void __launch_bounds__(256) unpack_kernel(const tr_body_desc* __restrict__ in, uint32_t first,
+                                                     uint32_t count, SoA s) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const tr_body_desc b = in[t];
+    uint32_t i = first + t;
+    s.pos_m[i] = make_float4(b.pos[0], b.pos[1], b.pos[2], b.mass);
+    s.vel_rest[i] = make_float4(b.vel[0], b.vel[1], b.vel[2], b.rest);
+    s.force[i] = make_float4(b.force[0], b.force[1], b.force[2], 0.f);
+    s.drag[i] = make_float2(b.Cd, b.area);
+    s.center_r[i] = make_float4(b.center[0], b.center[1], b.center[2], b.radius);
+    s.half_ext[i] = make_float4(b.size[0], b.size[1], b.size[2], 0.f);
+    uint8_t f = 0;
+    if (b.stationary) f |= F_STATIONARY;
+    if (b.isStatic) f |= F_STATIC;
+    if (b.isSphere) f |= F_SPHERE;
+    s.flags[i] = f;
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(tr_body_desc* __restrict__ out, uint32_t first, uint32_t count,
+                                                   SoA s) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    uint32_t i = first + t;
+    tr_body_desc b;
+    float4 p = s.pos_m[i], v = s.vel_rest[i], f = s.force[i], c = s.center_r[i], h = s.half_ext[i];
+    float2 d = s.drag[i];
+    uint8_t fl = s.flags[i];
+    b.pos[0] = p.x; b.pos[1] = p.y; b.pos[2] = p.z;
+    b.vel[0] = v.x; b.vel[1] = v.y; b.vel[2] = v.z;
+    b.force[0] = f.x; b.force[1] = f.y; b.force[2] = f.z;
+    b.mass = p.w; b.Cd = d.x; b.area = d.y;
+    b.stationary = (fl & F_STATIONARY) ? 1 : 0;
+    b.center[0] = c.x; b.center[1] = c.y; b.center[2] = c.z;
+    b.size[0] = h.x; b.size[1] = h.y; b.size[2] = h.z;
+    b.radius = c.w;
+    b.isSphere = (fl & F_SPHERE) ? 1 : 0;
+    b.isStatic = (fl & F_STATIC) ? 1 : 0;
+    b.rest = v.w;
+    out[t] = b;
+}
+
+__global__ void __launch_bounds__(256) read_state_kernel(const float4* __restrict__ pos_m,
+                                                         const float4* __restrict__ vel_rest, uint32_t first,
+                                                         uint32_t count, float* pos_xyz, float* vel_xyz) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    float4 p = pos_m[first + t];
+    pos_xyz[3 * t + 0] = p.x; pos_xyz[3 * t + 1] = p.y; pos_xyz[3 * t + 2] = p.z;
+    if (vel_xyz) {
+        float4 v = vel_rest[first + t];
+        vel_xyz[3 * t + 0] = v.x; vel_xyz[3 * t + 1] = v.y; vel_xyz[3 * t + 2] = v.z;
+    }
+}
+
+__global__ void copy_pos_kernel(const float4* __restrict__ a, float4* __restrict__ b, uint32_t n) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) b[t] = a[t];
+}
+
+static SoA soa_of(tr_world* w) {
+    SoA s;
+    s.pos_m = w->pos_m[w->cur];
+    s.vel_rest = w->vel_rest;
+    s.force = w->force;
+    s.drag = w->drag;
+    s.center_r = w->center_r;
+    s.half_ext = w->half_ext;
+    s.flags = w->flags;
+    return s;
+}
+
+template <typename T>
+static int grow(T** p, uint64_t old_n, uint64_t new_cap, cudaStream_t st) {
+    T* q = nullptr;
+    TR_CUDA(cudaMalloc(&q, new_cap * sizeof(T)));
+    if (*p && old_n) TR_CUDA(cudaMemcpyAsync(q, *p, old_n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    if (*p) {
+        TR_CUDA(cudaStreamSynchronize(st));
+        cudaFree(*p);
+    }
+    *p = q;
+    return TR_OK;
+}
+
+static int ensure_capacity(tr_world* w, uint64_t need) {
+    if (need <= w->cap) return TR_OK;
+    uint64_t nc = w->cap ? w->cap : 1024;
+    while (nc < need) nc *= 2;
+    if (need > (1ull << 31)) {
+        set_error("world too large: %llu bodies (limit 2^31)", (unsigned long long)need);
+        return TR_ERR_INVALID_ARG;
+    }
+    TR_TRY(grow(&w->pos_m[0], w->n, nc, w->stream));
+    TR_TRY(grow(&w->pos_m[1], w->n, nc, w->stream));
+    TR_TRY(grow(&w->vel_rest, w->n, nc, w->stream));
+    TR_TRY(grow(&w->force, w->n, nc, w->stream));
+    TR_TRY(grow(&w->drag, w->n, nc, w->stream));
+    TR_TRY(grow(&w->center_r, w->n, nc, w->stream));
+    TR_TRY(grow(&w->half_ext, w->n, nc, w->stream));
+    TR_TRY(grow(&w->flags, w->n, nc, w->stream));
+    w->cap = nc;
+    return TR_OK;
+}
+
+static int ensure_staging(tr_world* w, uint64_t count) {
+    if (count > w->aos_cap) {
+        if (w->aos) cudaFree(w->aos);
+        w->aos = nullptr;
+        w->aos_cap = 0;
+        TR_CUDA(cudaMalloc(&w->aos, count * sizeof(tr_body_desc)));
+        w->aos_cap = count;
+    }
+    if (count > w->pinned_cap) {
+        if (w->pinned) cudaFreeHost(w->pinned);
+        w->pinned = nullptr;
+        w->pinned_cap = 0;
+        TR_CUDA(cudaMallocHost(&w->pinned, count * sizeof(tr_body_desc)));
+        w->pinned_cap = count;
+    }
+    return TR_OK;
+}
+
+static void set_owned_range(tr_world* w) {
+    // contiguous blocks of ceil(N/R) targets in creation order (ids stay stable)
+    uint64_t per = (w->n + w->nranks - 1) / w->nranks;
+    uint64_t lo = per * (uint64_t)w->rank;
+    if (lo > w->n) lo = w->n;
+    uint64_t hi = lo + per;
+    if (hi > w->n) hi = w->n;
+    w->own_first = lo;
+    w->own_count = hi - lo;
+}
+
+// device <- bodies[first .. first+count) given as host AoS
+static int upload_range(tr_world* w, uint64_t first, uint64_t count, const tr_body_desc* host) {
+    if (count == 0) return TR_OK;
+    TR_TRY(ensure_capacity(w, first + count));
+    TR_TRY(ensure_staging(w, count));
+    memcpy(w->pinned, host, count * sizeof(tr_body_desc));
+    TR_CUDA(cudaMemcpyAsync(w->aos, w->pinned, count * sizeof(tr_body_desc), cudaMemcpyHostToDevice, w->stream));
+    unsigned blocks = (unsigned)((count + 255) / 256);
+    unpack_kernel<<<blocks, 256, 0, w->stream>>>(w->aos, (uint32_t)first, (uint32_t)count, soa_of(w));
+    TR_CUDA(cudaGetLastError());
+    w->stats.kernel_launches += 1;
+    // the pinned buffer is reused by the next call: wait for the copy
+    TR_CUDA(cudaStreamSynchronize(w->stream));
+    return TR_OK;
+}
+
+static int flush_created(tr_world* w) {
+    if (!w->dirty_upload) return TR_OK;
+    uint64_t total = w->host_bodies.size();
+    if (total > w->n) {
+        TR_TRY(upload_range(w, w->n, total - w->n, w->host_bodies.data() + w->n));
+        w->n = total;
+    }
+    w->dirty_upload = false;
+    w->classified = false;
+    set_owned_range(w);
+    return TR_OK;
+}
+
+static int download_range(tr_world* w, uint64_t first, uint64_t count, tr_body_desc* host) {
+    if (count == 0) return TR_OK;
+    TR_TRY(ensure_staging(w, count));
+    unsigned blocks = (unsigned)((count + 255) / 256);
+    pack_kernel<<<blocks, 256, 0, w->stream>>>(w->aos, (uint32_t)first, (uint32_t)count, soa_of(w));
+    TR_CUDA(cudaGetLastError());
+    w->stats.kernel_launches += 1;
+    TR_CUDA(cudaMemcpyAsync(w->pinned, w->aos, count * sizeof(tr_body_desc), cudaMemcpyDeviceToHost, w->stream));
+    TR_CUDA(cudaStreamSynchronize(w->stream));
+    memcpy(host, w->pinned, count * sizeof(tr_body_desc));
+    return TR_OK;
+}
+
+static int check_world(tr_world* w) {
+    if (!w) {
+        set_error("null world");
+        return TR_ERR_INVALID_ARG;
+    }
+    cudaError_t e = cudaSetDevice(w->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__);
+    return TR_OK;
+}
+
+static int validate_params(const tr_world_params* p) {
+    if (!p) {
+        set_error("null params");
+        return TR_ERR_INVALID_ARG;
+    }
+    if (p->grid_bits != 0 && (p->grid_bits < 2 || p->grid_bits > 10)) {
+        set_error("grid_bits must be 0 (auto) or 2..10, got %d", p->grid_bits);
+        return TR_ERR_INVALID_ARG;
+    }
+    if (p->grid_cell < 0.f || p->grid_max_radius < 0.f) {
+        set_error("grid_cell / grid_max_radius must be >= 0");
+        return TR_ERR_INVALID_ARG;
+    }
+    return TR_OK;
+}
+
+static int create_common(const tr_world_params* p, int device, int rank, int nranks, tr_world** out) {
+    if (!out) {
+        set_error("null out pointer");
+        return TR_ERR_INVALID_ARG;
+    }
+    *out = nullptr;
+    tr_world_params def;
+    if (!p) {
+        tr_default_params(&def);
+        p = &def;
+    }
+    TR_TRY(validate_params(p));
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no CUDA device available (%s); this library has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return TR_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) {
+        set_error("device %d out of range (0..%d)", device, count - 1);
+        return TR_ERR_INVALID_ARG;
+    }
+    cudaDeviceProp prop;
+    TR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return TR_ERR_NO_DEVICE;
+    }
+    TR_CUDA(cudaSetDevice(device));
+    tr_world* w = new (std::nothrow) tr_world();
+    if (!w) return TR_ERR_NOMEM;
+    w->device = device;
+    w->num_sms = prop.multiProcessorCount;
+    w->params = *p;
+    w->rank = rank;
+    w->nranks = nranks;
+    cudaError_t se = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess) {
+        delete w;
+        return cuda_fail(se, "cudaStreamCreate", __FILE__, __LINE__);
+    }
+    *out = w;
+    return TR_OK;
+}
+
+static StepConsts consts_of(const tr_world* w) {
+    StepConsts c;
+    c.gx = w->params.g[0];
+    c.gy = w->params.g[1];
+    c.gz = w->params.g[2];
+    c.dt = w->params.dt;
+    c.rho = w->params.atm_density;
+    c.G = w->params.G;
+    return c;
+}
+
+static int step_once(tr_world* w) {
+    const StepConsts c = consts_of(w);
+    const bool grav = (w->params.flags & TR_PAIR_GRAVITY) != 0;
+    const bool coll = (w->params.flags & TR_COLLISIONS) != 0;
+    if (coll && w->nranks > 1) {
+        set_error("sharded worlds run gravity + drag + integration only; collisions under sharding are not "
+                  "implemented (SURVEY.md 8f row 4)");
+        return TR_ERR_STATE;
+    }
+    if (grav) {
+        TR_TRY(gravity_step(w, c, true, nullptr));
+        w->cur ^= 1;
+        if (w->nranks > 1) {
+            TR_TRY(nccl_allgather_pos(w, w->pos_m[w->cur]));
+        }
+    } else {
+        TR_TRY(integrate_only(w, c));
+        if (w->nranks > 1) TR_TRY(nccl_allgather_pos(w, w->pos_m[w->cur]));
+    }
+    if (coll) TR_TRY(collide_step(w, false));
+    w->stats.steps += 1;
+    return TR_OK;
+}
+
+}  // namespace tr
+
+using namespace tr;
+
+extern "C" {
+
+int tr_abi_version(void) { return TR_ABI_VERSION; }
+
+const char* tr_last_error(void) { return g_err; }
+
+int tr_device_count(int* count) {
+    if (!count) return TR_ERR_INVALID_ARG;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
+    }
+    return TR_OK;
+}
+
+int tr_default_params(tr_world_params* p) {
+    if (!p) return TR_ERR_INVALID_ARG;
+    memset(p, 0, sizeof(*p));
+    p->g[0] = 0.0f;
+    p->g[1] = (float)-9.8;   // reference src/main.cpp:749
+    p->g[2] = 0.0f;
+    p->G = 6.6743e-11f;      // reference src/main.cpp:685
+    p->dt = 0.01666f;        // reference src/main.cpp:750
+    p->atm_density = 1.2f;   // reference src/main.cpp:1141
+    p->flags = TR_COLLISIONS;
+    return TR_OK;
+}
+
+int tr_world_create(const tr_world_params* p, int device, tr_world** out) {
+    return create_common(p, device, 0, 1, out);
+}
+
+int tr_comm_unique_id(void* out128) { return nccl_unique_id(out128); }
+
+int tr_world_create_sharded(const tr_world_params* p, int device, int rank, int nranks, const void* unique_id128,
+                            tr_world** out) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || !unique_id128) {
+        set_error("bad rank/nranks/unique id");
+        return TR_ERR_INVALID_ARG;
+    }
+    TR_TRY(create_common(p, device, rank, nranks, out));
+    if (nranks > 1) {
+        int rc = nccl_init(*out, unique_id128);
+        if (rc != TR_OK) {
+            tr_world_destroy(*out);
+            *out = nullptr;
+            return rc;
+        }
+    }
+    return TR_OK;
+}
+
+int tr_world_destroy(tr_world* w) {
+    if (!w) return TR_OK;
+    cudaSetDevice(w->device);
+    cudaStreamSynchronize(w->stream);
+    timers_collect(w);
+    nccl_destroy(w);
+    collide_free(w);
+    for (cudaEvent_t e : w->event_pool) cudaEventDestroy(e);
+    cudaFree(w->pos_m[0]);
+    cudaFree(w->pos_m[1]);
+    cudaFree(w->vel_rest);
+    cudaFree(w->force);
+    cudaFree(w->drag);
+    cudaFree(w->center_r);
+    cudaFree(w->half_ext);
+    cudaFree(w->flags);
+    cudaFree(w->aos);
+    if (w->pinned) cudaFreeHost(w->pinned);
+    cudaFree(w->grav_partial);
+    cudaFree(w->grav_ctrl);
+    cudaFree(w->grav_force_dbg);
+    if (w->own_stream && w->stream) cudaStreamDestroy(w->stream);
+    delete w;
+    return TR_OK;
+}
+
+int tr_world_set_params(tr_world* w, const tr_world_params* p) {
+    TR_TRY(check_world(w));
+    TR_TRY(validate_params(p));
+    bool grid_changed = p->grid_cell != w->params.grid_cell || p->grid_bits != w->params.grid_bits ||
+                        p->grid_max_radius != w->params.grid_max_radius ||
+                        memcmp(p->grid_origin, w->params.grid_origin, sizeof(p->grid_origin)) != 0;
+    w->params = *p;
+    if (grid_changed) w->classified = false;
+    return TR_OK;
+}
+
+int tr_world_get_params(tr_world* w, tr_world_params* p) {
+    if (!w || !p) return TR_ERR_INVALID_ARG;
+    *p = w->params;
+    return TR_OK;
+}
+
+int tr_world_set_stream(tr_world* w, void* cuda_stream) {
+    TR_TRY(check_world(w));
+    TR_CUDA(cudaStreamSynchronize(w->stream));
+    timers_collect(w);
+    if (w->own_stream && w->stream) cudaStreamDestroy(w->stream);
+    if (cuda_stream) {
+        w->stream = (cudaStream_t)cuda_stream;
+        w->own_stream = false;
+    } else {
+        TR_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+        w->own_stream = true;
+    }
+    return TR_OK;
+}
+
+int tr_bodies_add(tr_world* w, uint64_t n, const tr_body_desc* b, uint32_t* first_id) {
+    if (!w || (n && !b)) {
+        set_error("null argument");
+        return TR_ERR_INVALID_ARG;
+    }
+    if (w->host_bodies.size() + n > (1ull << 31)) {
+        set_error("too many bodies");
+        return TR_ERR_INVALID_ARG;
+    }
+    if (first_id) *first_id = (uint32_t)w->host_bodies.size();
+    try {
+        w->host_bodies.insert(w->host_bodies.end(), b, b + n);
+    } catch (...) {
+        set_error("out of host memory staging %llu bodies", (unsigned long long)n);
+        return TR_ERR_NOMEM;
+    }
+    if (n) w->dirty_upload = true;
+    return TR_OK;
+}
+
+int tr_body_add(tr_world* w, const tr_body_desc* b, uint32_t* id) { return tr_bodies_add(w, 1, b, id); }
+
+int tr_world_size(tr_world* w, uint64_t* n) {
+    if (!w || !n) return TR_ERR_INVALID_ARG;
+    *n = w->host_bodies.size();
+    return TR_OK;
+}
+
+int tr_world_owned_range(tr_world* w, uint64_t* first, uint64_t* count) {
+    TR_TRY(check_world(w));
+    TR_TRY(flush_created(w));
+    if (first) *first = w->own_first;
+    if (count) *count = w->own_count;
+    return TR_OK;
+}
+
+// toSpherical, reference src/main.cpp:1080-1089: the degree->radian factor is a double
+// (M_PI / 180), the product is narrowed to float, trig runs on floats.
+int tr_to_spherical(float elev_deg, float azim_deg, float magnitude, float out_vel[3]) {
+    if (!out_vel) return TR_ERR_INVALID_ARG;
+    float radE = (float)((double)elev_deg * (M_PI / 180));
+    float radA = (float)((double)azim_deg * (M_PI / 180));
+    out_vel[0] = magnitude * cosf(radE) * cosf(radA);
+    out_vel[1] = magnitude * sinf(radE);
+    out_vel[2] = magnitude * cosf(radE) * sinf(radA);
+    return TR_OK;
+}
+
+// area = M_PI * size * size evaluated in double, narrowed to float (src/main.cpp:1295).
+float tr_area_from_size(float size) { return (float)(M_PI * (double)size * (double)size); }
+
+int tr_step(tr_world* w, int nsteps) {
+    TR_TRY(check_world(w));
+    if (nsteps < 0) {
+        set_error("nsteps < 0");
+        return TR_ERR_INVALID_ARG;
+    }
+    TR_TRY(flush_created(w));
+    if (w->n == 0) return TR_OK;
+    for (int s = 0; s < nsteps; ++s) TR_TRY(step_once(w));
+    return TR_OK;
+}
+
+int tr_sync(tr_world* w) {
+    TR_TRY(check_world(w));
+    TR_CUDA(cudaStreamSynchronize(w->stream));
+    timers_collect(w);
+    if (w->deferred_error != TR_OK) {
+        int rc = w->deferred_error;
+        set_error("%s", w->deferred_msg.c_str());
+        w->deferred_error = TR_OK;
+        w->deferred_msg.clear();
+        return rc;
+    }
+    return TR_OK;
+}
+
+int tr_step_host(tr_world* w, uint64_t n, tr_body_desc* bodies, int nsteps) {
+    TR_TRY(check_world(w));
+    if (!bodies && n) return TR_ERR_INVALID_ARG;
+    if (w->nranks > 1) {
+        set_error("tr_step_host is for unsharded worlds");
+        return TR_ERR_STATE;
+    }
+    if (w->host_bodies.empty() && w->n == 0) {
+        TR_TRY(tr_bodies_add(w, n, bodies, nullptr));
+        TR_TRY(flush_created(w));
+    } else {
+        TR_TRY(flush_created(w));
+        if (n != w->n) {
+            set_error("tr_step_host: %llu bodies passed, world holds %llu", (unsigned long long)n,
+                      (unsigned long long)w->n);
+            return TR_ERR_INVALID_ARG;
+        }
+        TR_TRY(upload_range(w, 0, n, bodies));
+        w->classified = false;
+    }
+    TR_TRY(tr_step(w, nsteps));
+    TR_TRY(download_range(w, 0, n, bodies));
+    return tr_sync(w);
+}
+
+int tr_read_state(tr_world* w, uint64_t first, uint64_t count, float* pos_xyz, float* vel_xyz) {
+    TR_TRY(check_world(w));
+    TR_TRY(flush_created(w));
+    if (first + count > w->n || !pos_xyz) {
+        set_error("tr_read_state: range [%llu,+%llu) outside world of %llu", (unsigned long long)first,
+                  (unsigned long long)count, (unsigned long long)w->n);
+        return TR_ERR_INVALID_ARG;
+    }
+    if (w->nranks > 1 && vel_xyz && (first < w->own_first || first + count > w->own_first + w->own_count)) {
+        set_error("tr_read_state: velocities exist only for this rank's owned range");
+        return TR_ERR_INVALID_ARG;
+    }
+    if (count == 0) return TR_OK;
+    float* d = nullptr;
+    size_t bytes = (size_t)count * 3 * sizeof(float);
+    TR_CUDA(cudaMalloc(&d, bytes * (vel_xyz ? 2 : 1)));
+    float* dv = vel_xyz ? d + count * 3 : nullptr;
+    unsigned blocks = (unsigned)((count + 255) / 256);
+    read_state_kernel<<<blocks, 256, 0, w->stream>>>(w->pos_m[w->cur], w->vel_rest, (uint32_t)first, (uint32_t)count,
+                                                     d, dv);
+    w->stats.kernel_launches += 1;
+    cudaError_t e = cudaMemcpyAsync(pos_xyz, d, bytes, cudaMemcpyDeviceToHost, w->stream);
+    if (e == cudaSuccess && vel_xyz) e = cudaMemcpyAsync(vel_xyz, dv, bytes, cudaMemcpyDeviceToHost, w->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "tr_read_state copy", __FILE__, __LINE__);
+    return TR_OK;
+}
+
+int tr_read_bodies(tr_world* w, uint64_t first, uint64_t count, tr_body_desc* out) {
+    TR_TRY(check_world(w));
+    TR_TRY(flush_created(w));
+    if (first + count > w->n || (!out && count)) {
+        set_error("tr_read_bodies: bad range");
+        return TR_ERR_INVALID_ARG;
+    }
+    if (w->nranks > 1 && (first < w->own_first || first + count > w->own_first + w->own_count)) {
+        set_error("tr_read_bodies: only this rank's owned range is complete on a sharded world");
+        return TR_ERR_INVALID_ARG;
+    }
+    return download_range(w, first, count, out);
+}
+
+int tr_write_bodies(tr_world* w, uint64_t first, uint64_t count, const tr_body_desc* in) {
+    TR_TRY(check_world(w));
+    TR_TRY(flush_created(w));
+    if (first + count > w->n || (!in && count)) {
+        set_error("tr_write_bodies: bad range");
+        return TR_ERR_INVALID_ARG;
+    }
+    TR_TRY(upload_range(w, first, count, in));
+    for (uint64_t i = 0; i < count; ++i) w->host_bodies[first + i] = in[i];
+    w->classified = false;
+    return TR_OK;
+}
+
+int tr_set_force(tr_world* w, uint32_t id, float fx, float fy, float fz) {
+    TR_TRY(check_world(w));
+    TR_TRY(flush_created(w));
+    if (id >= w->n) {
+        set_error("tr_set_force: id %u out of range", id);
+        return TR_ERR_INVALID_ARG;
+    }
+    float4 f = make_float4(fx, fy, fz, 0.f);
+    TR_CUDA(cudaMemcpyAsync(w->force + id, &f, sizeof(f), cudaMemcpyHostToDevice, w->stream));
+    TR_CUDA(cudaStreamSynchronize(w->stream));
+    return TR_OK;
+}
+
+int tr_read_contacts(tr_world* w, int32_t* pairs_ij, uint64_t cap, uint64_t* n) {
+    TR_TRY(check_world(w));
+    return collide_read_contacts(w, pairs_ij, cap, n);
+}
+
+int tr_debug_grid(tr_world* w, uint32_t* keys, uint32_t* sorted_ids, uint64_t* m, float* cell, float* inv_cell,
+                  int32_t* bits) {
+    TR_TRY(check_world(w));
+    return collide_debug_grid(w, keys, sorted_ids, m, cell, inv_cell, bits);
+}
+
+int tr_debug_candidates(tr_world* w, int32_t* pairs_ij, uint64_t cap, uint64_t* n) {
+    TR_TRY(check_world(w));
+    TR_TRY(flush_created(w));
+    return collide_debug_candidates(w, pairs_ij, cap, n);
+}
+
+int tr_debug_gravity(tr_world* w, float* force_xyz) {
+    TR_TRY(check_world(w));
+    TR_TRY(flush_created(w));
+    if (!force_xyz) return TR_ERR_INVALID_ARG;
+    if (w->own_count == 0) return TR_OK;
+    float4* d = nullptr;
+    TR_CUDA(cudaMalloc(&d, w->own_count * sizeof(float4)));
+    int rc = gravity_step(w, consts_of(w), false, d);
+    std::vector<float4> h(w->own_count);
+    cudaError_t e = cudaSuccess;
+    if (rc == TR_OK) {
+        e = cudaMemcpyAsync(h.data(), d, w->own_count * sizeof(float4), cudaMemcpyDeviceToHost, w->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+    }
+    cudaFree(d);
+    if (rc != TR_OK) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "tr_debug_gravity copy", __FILE__, __LINE__);
+    for (uint64_t i = 0; i < w->own_count; ++i) {
+        force_xyz[3 * i + 0] = h[i].x;
+        force_xyz[3 * i + 1] = h[i].y;
+        force_xyz[3 * i + 2] = h[i].z;
+    }
+    return TR_OK;
+}
+
+int tr_get_stats(tr_world* w, tr_stats* s) {
+    if (!w || !s) return TR_ERR_INVALID_ARG;
+    // only completed work is folded in; call tr_sync first for exact numbers
+    cudaSetDevice(w->device);
+    if (cudaStreamQuery(w->stream) == cudaSuccess) timers_collect(w);
+    *s = w->stats;
+    return TR_OK;
+}
+
+int tr_reset_stats(tr_world* w) {
+    TR_TRY(check_world(w));
+    TR_CUDA(cudaStreamSynchronize(w->stream));
+    timers_collect(w);
+    uint32_t side = w->stats.side_list_size;
+    w->stats = tr_stats{};
+    w->stats.side_list_size = side;
+    return TR_OK;
+}
+
+int tr_enable_timing(tr_world* w, int on) {
+    TR_TRY(check_world(w));
+    TR_CUDA(cudaStreamSynchronize(w->stream));
+    timers_collect(w);
+    w->timing = on != 0;
+    return TR_OK;
+}
+
+int tr_measure_fma_peak(int device, double* lane_ops_per_s, double* sm_clock_mhz) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) {
+        set_error("no such CUDA device %d", device);
+        return TR_ERR_NO_DEVICE;
+    }
+    return measure_fma_peak(device, lane_ops_per_s, sm_clock_mhz);
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+// Internal definitions shared by the translation units of libtraceit_b200.so.
+// Not part of the ABI (include/traceit_b200.h is).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/traceit_b200.h"
+
+namespace tr {
+
+// ---- error plumbing -------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define TR_CUDA(call)                                                            \
+    do {                                                                         \
+        cudaError_t e__ = (call);                                                \
+        if (e__ != cudaSuccess) return ::tr::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define TR_TRY(call)                 \
+    do {                             \
+        int rc__ = (call);           \
+        if (rc__ != TR_OK) return rc__; \
+    } while (0)
+
+// ---- body flags (SoA byte) ------------------------------------------------------------
+enum : uint8_t {
+    F_STATIONARY = 1,  // object::stationary      reference src/main.cpp:98
+    F_STATIC = 2,      // collider::isStatic      reference src/main.cpp:84
+    F_SPHERE = 4,      // collider::isSphere      reference src/main.cpp:83
+    F_GRID = 8         // lives in the uniform grid this step (else: side list)
+};
+
+// ---- gravity tiling constants (see DESIGN.md "K1") -------------------------------------
+constexpr int GRAV_THREADS = 256;
+#ifndef TR_GRAV_PAIRS
+#define TR_GRAV_PAIRS 4
+#endif
+#ifndef TR_GRAV_MINBLOCKS
+#define TR_GRAV_MINBLOCKS 3
+#endif
+constexpr int GRAV_PAIRS = TR_GRAV_PAIRS;             // packed f32x2 target pairs per thread
+constexpr int GRAV_T = 2 * GRAV_PAIRS;                 // targets per thread
+constexpr int GRAV_TILE = GRAV_THREADS * GRAV_T;       // 2048 targets per tile
+constexpr int GRAV_SUB = 512;                          // sources per TMA stage (8 KB)
+constexpr int GRAV_STAGES = 3;
+constexpr int GRAV_MAX_CHUNKS = 64;                    // partial sums per target
+
+// chunk length is a function of N only, so a sharded run adds the same partial sums in
+// the same order as an unsharded one (bit-identical for any rank count).
+inline uint32_t grav_chunk_len(uint64_t n) {
+    uint64_t c = (n + GRAV_MAX_CHUNKS - 1) / GRAV_MAX_CHUNKS;
+    c = (c + GRAV_SUB - 1) / GRAV_SUB * GRAV_SUB;
+    if (c < 1024) c = 1024;
+    return (uint32_t)c;
+}
+
+struct StepConsts {
+    float gx, gy, gz;
+    float dt;
+    float rho;
+    float G;
+};
+
+// ---- per-kernel timing ----------------------------------------------------------------
+enum TimerCat { T_GRAVITY = 0, T_BROAD, T_NARROW, T_RESPONSE, T_INTEGRATE, T_ALLGATHER, T_NCAT };
+
+struct PendingTimer {
+    cudaEvent_t a, b;
+    int cat;
+};
+
+struct NcclApi;  // nccl_dyn.cu
+
+}  // namespace tr
+
+// The opaque world.  Device buffers are plain SoA fp32 arrays sized to `cap` bodies.
+struct tr_world {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int num_sms = 0;
+    tr_world_params params{};
+
+    // host-side staging of created bodies (uploaded lazily before the next step)
+    std::vector<tr_body_desc> host_bodies;
+    uint64_t n = 0;          // bodies resident on the device
+    uint64_t cap = 0;        // allocated capacity (bodies)
+    bool dirty_upload = false;
+    bool classified = false; // grid / side-list split is current
+
+    // sharding
+    int rank = 0, nranks = 1;
+    uint64_t own_first = 0, own_count = 0;
+    void* nccl_comm = nullptr;
+
+    // SoA state
+    float4* pos_m[2] = {nullptr, nullptr};  // x,y,z,mass ; [cur] is live
+    int cur = 0;
+    float4* vel_rest = nullptr;             // vx,vy,vz,restitution
+    float4* force = nullptr;                // external force xyz, pad
+    float2* drag = nullptr;                 // Cd, area
+    float4* center_r = nullptr;             // collider centre xyz, radius
+    float4* half_ext = nullptr;             // collider size xyz (AABB half extents), pad
+    uint8_t* flags = nullptr;
+    tr_body_desc* aos = nullptr;            // device AoS staging for pack/unpack
+    uint64_t aos_cap = 0;
+    tr_body_desc* pinned = nullptr;         // pinned host staging
+    uint64_t pinned_cap = 0;
+
+    // gravity scratch
+    float4* grav_partial = nullptr;         // [chunks][own_padded]
+    uint64_t grav_partial_elems = 0;
+    uint32_t* grav_ctrl = nullptr;          // [0]=work counter, [1..]=per-tile arrival counters
+    uint64_t grav_ctrl_elems = 0;
+    float4* grav_force_dbg = nullptr;
+
+    // collision scratch (collide.cu)
+    struct Collide* col = nullptr;
+
+    // stats / timing
+    tr_stats stats{};
+    bool timing = false;
+    std::vector<tr::PendingTimer> pending;
+    std::vector<cudaEvent_t> event_pool;
+    int deferred_error = TR_OK;
+    std::string deferred_msg;
+};
+
+namespace tr {
+
+// timing helpers (api.cu)
+void timer_begin(tr_world* w, int cat, PendingTimer* t);
+void timer_end(tr_world* w, PendingTimer* t);
+void timers_collect(tr_world* w);
+
+// gravity.cu
+int gravity_step(tr_world* w, const StepConsts& c, bool integrate_fused, float4* force_out);
+int integrate_only(tr_world* w, const StepConsts& c);
+int measure_fma_peak(int device, double* lane_ops_per_s, double* sm_clock_mhz);
+
+// collide.cu
+int collide_step(tr_world* w, bool emit_candidates);
+int collide_free(tr_world* w);
+int collide_read_contacts(tr_world* w, int32_t* pairs, uint64_t cap, uint64_t* n);
+int collide_debug_grid(tr_world* w, uint32_t* keys, uint32_t* sorted_ids, uint64_t* m, float* cell, float* inv_cell,
+                       int32_t* bits);
+int collide_debug_candidates(tr_world* w, int32_t* pairs, uint64_t cap, uint64_t* n);
+int collide_classify(tr_world* w);
+
+// nccl_dyn.cu
+int nccl_unique_id(void* out128);
+int nccl_init(tr_world* w, const void* id128);
+int nccl_allgather_pos(tr_world* w, float4* buf);
+void nccl_destroy(tr_world* w);
+
+}  // namespace tr
