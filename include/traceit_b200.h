@@ -124,7 +124,8 @@ int tr_world_create_sharded(const tr_world_params* p, int device, int rank, int 
 int tr_world_destroy(tr_world* w);
 int tr_world_set_params(tr_world* w, const tr_world_params* p);   /* world field writes  */
 int tr_world_get_params(tr_world* w, tr_world_params* p);
-/* Run on the caller's CUDA stream (cudaStream_t) instead of the world's own.           */
+/* Run on the caller's CUDA stream (cudaStream_t; NULL = the legacy default stream)
+ * instead of the world's own non-blocking stream.                                      */
 int tr_world_set_stream(tr_world* w, void* cuda_stream);
 
 /* ---- body creation: replaces w.objects.push_back(obj) (src/main.cpp:1242,1491) ----- */

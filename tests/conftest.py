@@ -21,8 +21,14 @@ def bits(a):
 
 
 def assert_bits_equal(a, b, what=""):
-    a, b = bits(a), bits(b)
+    """Exact bit equality (signed zeros and infinities included).  NaNs compare equal to
+    NaNs: IEEE 754 leaves the payload of a generated NaN unspecified and the platforms differ
+    (x86 SSE produces 0xFFC00000, NVIDIA GPUs 0x7FFFFFFF)."""
+    fa, fb = np.ascontiguousarray(a, dtype=np.float32), np.ascontiguousarray(b, dtype=np.float32)
+    a, b = bits(fa).copy(), bits(fb).copy()
     assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    a[np.isnan(fa)] = 0x7FC00000
+    b[np.isnan(fb)] = 0x7FC00000
     bad = np.nonzero(a != b)
     assert len(bad[0]) == 0, f"{what}: {len(bad[0])} of {a.size} words differ, first at {tuple(x[0] for x in bad)}"
 

@@ -231,18 +231,49 @@ def _traj_errors(got, want):
     return epos, evel
 
 
-@pytest.mark.parametrize("n,steps", [(8192, 100), (65536, 4)])
+@pytest.mark.parametrize("n,steps", [(8192, 100), (16384, 100)])
 def test_gravity_trajectory_vs_restated_oracle(tr, oracle, n, steps):
-    """Config 2 shape: gravity + drag + integration, collisions off, K steps."""
+    """Config 2 shape (gravity + drag + integration, collisions off), K = 100 steps, in the
+    regime where fp32 trajectories are well conditioned (G = 1e-3: no hard two-body
+    encounters within the horizon): max error vs the fp32 restated oracle <= 1e-4 of the
+    cloud extent / rms speed."""
     b = scenes.random_cloud(n, scenes.SEED_CFG2, spheres=True)
-    flags = tr.PAIR_GRAVITY
-    got, _, st = gpu_run(tr, b, steps, flags=flags, G=np.float32(1.0), g=(0, 0, 0))
+    G = np.float32(1e-3)
+    got, _, st = gpu_run(tr, b, steps, flags=tr.PAIR_GRAVITY, G=G, g=(0, 0, 0))
     want = b.copy()
-    oracle.step(want, oracle.default_params(flags=oracle.PAIR_GRAVITY, G=np.float32(1.0), g=(0, 0, 0)), steps)
+    oracle.step(want, oracle.default_params(flags=oracle.PAIR_GRAVITY, G=G, g=(0, 0, 0)), steps)
     epos, evel = _traj_errors(got, want)
-    print(f"n={n} K={steps}: max pos err / extent = {epos:.3e}, max vel err / vrms = {evel:.3e}")
+    print(f"n={n} K={steps} G=1e-3: max pos err / extent = {epos:.3e}, max vel err / vrms = {evel:.3e}")
     assert epos <= TRAJ_REL_TOL and evel <= TRAJ_REL_TOL
     assert st.interactions == n * n * steps
+
+
+def _rms_errors(a, b):
+    extent = np.abs(b["pos"]).max()
+    vrms = np.sqrt((b["vel"].astype(np.float64) ** 2).sum(axis=1).mean())
+    dp = a["pos"].astype(np.float64) - b["pos"]
+    dv = a["vel"].astype(np.float64) - b["vel"]
+    return np.sqrt((dp ** 2).sum(axis=1).mean()) / extent, np.sqrt((dv ** 2).sum(axis=1).mean()) / vrms
+
+
+@pytest.mark.parametrize("n,steps", [(8192, 100), (65536, 4)])
+def test_gravity_trajectory_cfg2_vs_fp64_yardstick(tr, oracle, n, steps):
+    """Config 2 as the survey states it (G = 1, masses 1..10): hard close encounters make the
+    K-step trajectory chaotic in fp32 - the CPU fp32 restatement itself drifts from the fp64
+    restatement by up to several percent (max norm) at K = 100.  The honest bar there is the
+    fp64 yardstick: the GPU must be at least as close to it as the CPU fp32
+    restatement is (x1.5 slack), in rms position and velocity error."""
+    b = scenes.random_cloud(n, scenes.SEED_CFG2, spheres=True)
+    G = np.float32(1.0)
+    got, _, _ = gpu_run(tr, b, steps, flags=tr.PAIR_GRAVITY, G=G, g=(0, 0, 0))
+    w32 = b.copy()
+    oracle.step(w32, oracle.default_params(flags=oracle.PAIR_GRAVITY, G=G, g=(0, 0, 0)), steps)
+    w64 = b.copy()
+    oracle.step(w64, oracle.default_params(flags=oracle.PAIR_GRAVITY | oracle.GRAVITY_F64, G=G, g=(0, 0, 0)), steps)
+    gp, gv = _rms_errors(got, w64)
+    cp, cv = _rms_errors(w32, w64)
+    print(f"n={n} K={steps} G=1: rms err vs fp64  GPU pos {gp:.2e} vel {gv:.2e} | CPU fp32 pos {cp:.2e} vel {cv:.2e}")
+    assert gp <= 1.5 * cp + 1e-7 and gv <= 1.5 * cv + 1e-7
 
 
 def test_gravity_plus_collisions_small(tr, oracle):

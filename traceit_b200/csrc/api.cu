@@ -473,13 +473,9 @@ int tr_world_set_stream(tr_world* w, void* cuda_stream) {
     TR_CUDA(cudaStreamSynchronize(w->stream));
     timers_collect(w);
     if (w->own_stream && w->stream) cudaStreamDestroy(w->stream);
-    if (cuda_stream) {
-        w->stream = (cudaStream_t)cuda_stream;
-        w->own_stream = false;
-    } else {
-        TR_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
-        w->own_stream = true;
-    }
+    // the handle is used as given; NULL is CUDA's legacy default stream
+    w->stream = (cudaStream_t)cuda_stream;
+    w->own_stream = false;
     return TR_OK;
 }
 
@@ -564,8 +560,19 @@ int tr_step_host(tr_world* w, uint64_t n, tr_body_desc* bodies, int nsteps) {
     TR_TRY(check_world(w));
     if (!bodies && n) return TR_ERR_INVALID_ARG;
     if (w->nranks > 1) {
-        set_error("tr_step_host is for unsharded worlds");
-        return TR_ERR_STATE;
+        // sharded: `bodies` is this rank's owned block; positions are re-gathered so that
+        // every rank sees every other rank's freshly uploaded sources
+        TR_TRY(flush_created(w));
+        if (n != w->own_count) {
+            set_error("tr_step_host (sharded): %llu bodies passed, this rank owns %llu", (unsigned long long)n,
+                      (unsigned long long)w->own_count);
+            return TR_ERR_INVALID_ARG;
+        }
+        TR_TRY(upload_range(w, w->own_first, n, bodies));
+        TR_TRY(nccl_allgather_pos(w, w->pos_m[w->cur]));
+        TR_TRY(tr_step(w, nsteps));
+        TR_TRY(download_range(w, w->own_first, n, bodies));
+        return tr_sync(w);
     }
     if (w->host_bodies.empty() && w->n == 0) {
         TR_TRY(tr_bodies_add(w, n, bodies, nullptr));
@@ -662,6 +669,7 @@ int tr_read_contacts(tr_world* w, int32_t* pairs_ij, uint64_t cap, uint64_t* n) 
 int tr_debug_grid(tr_world* w, uint32_t* keys, uint32_t* sorted_ids, uint64_t* m, float* cell, float* inv_cell,
                   int32_t* bits) {
     TR_TRY(check_world(w));
+    TR_TRY(flush_created(w));
     return collide_debug_grid(w, keys, sorted_ids, m, cell, inv_cell, bits);
 }
 

@@ -42,7 +42,7 @@ constexpr int GRAV_THREADS = 256;
 #define TR_GRAV_PAIRS 4
 #endif
 #ifndef TR_GRAV_MINBLOCKS
-#define TR_GRAV_MINBLOCKS 3
+#define TR_GRAV_MINBLOCKS 2
 #endif
 constexpr int GRAV_PAIRS = TR_GRAV_PAIRS;             // packed f32x2 target pairs per thread
 constexpr int GRAV_T = 2 * GRAV_PAIRS;                 // targets per thread

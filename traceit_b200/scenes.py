@@ -107,15 +107,19 @@ def cfg4_cloud(n: int = 1 << 22) -> np.ndarray:
     return random_cloud(n, SEED_CFG4, spheres=True)
 
 
-def dense_lattice(n_side: int, seed: int = SEED_CFG5, pitch: float = 0.98, jitter: float = 0.01,
+def dense_lattice(n_side, seed: int = SEED_CFG5, pitch: float = 0.98, jitter: float = 0.01,
                   shuffle_ids: bool = False) -> np.ndarray:
-    """Config 5: jittered cubic lattice of radius-0.5 spheres at pitch 0.98 (every body overlaps
-    its ~6 face neighbours), velocities uniform in [-0.1,0.1]^3.  n = n_side^3."""
+    """Config 5: jittered lattice of radius-0.5 spheres at pitch 0.98 (every body overlaps its
+    ~6 face neighbours), velocities uniform in [-0.1,0.1]^3.  n_side is an int (cube) or a
+    (nx, ny, nz) tuple; ids run x-fastest in lattice order unless shuffled."""
+    dims = (n_side,) * 3 if np.isscalar(n_side) else tuple(int(d) for d in n_side)
+    nx, ny, nz = dims
     rs = np.random.RandomState(seed & 0xFFFFFFFF)
-    n = n_side ** 3
+    n = nx * ny * nz
     idx = np.arange(n)
-    ix, iy, iz = idx % n_side, (idx // n_side) % n_side, idx // (n_side * n_side)
-    base = (np.stack([ix, iy, iz], axis=1).astype(np.float64) - (n_side - 1) / 2.0) * pitch
+    ix, iy, iz = idx % nx, (idx // nx) % ny, idx // (nx * ny)
+    centre = np.array([(nx - 1) / 2.0, (ny - 1) / 2.0, (nz - 1) / 2.0])
+    base = (np.stack([ix, iy, iz], axis=1).astype(np.float64) - centre) * pitch
     pos = (base + rs.uniform(-jitter, jitter, size=(n, 3))).astype(np.float32)
     vel = rs.uniform(-0.1, 0.1, size=(n, 3)).astype(np.float32)
     if shuffle_ids:
@@ -131,6 +135,16 @@ def dense_lattice(n_side: int, seed: int = SEED_CFG5, pitch: float = 0.98, jitte
     b["radius"] = np.float32(0.5)
     b["isSphere"] = 1
     return b
+
+
+def cfg5_dense(n: int = 1 << 20) -> np.ndarray:
+    """1,048,576 = 128 x 128 x 64 packed spheres (smaller powers of two scale the box down)."""
+    e = int(np.log2(n))
+    assert 1 << e == n, "cfg5 sizes are powers of two"
+    ex = (e + 2) // 3
+    ey = (e - ex + 1) // 2
+    ez = e - ex - ey
+    return dense_lattice((1 << ex, 1 << ey, 1 << ez))
 
 
 assert new_bodies(0).dtype == BODY_DTYPE
