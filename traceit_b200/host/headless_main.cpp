@@ -1,0 +1,164 @@
+// Headless harness: the reference's frame loop with the ncurses renderer detached.
+//
+// Seeds the world the way the reference's main() does (earth slab, src/main.cpp:1482-1491),
+// adds projectiles with the creation form's parameters (src/main.cpp:1206-1311) and calls
+// updatePhysics(w, coords) once per frame (src/main.cpp:1589) - here the B200 shim from
+// traceit_host.hpp.  Prints a state hash (FNV-1a over pos/vel bit patterns, the same hash the
+// golden vectors store) so tests can compare a whole run with the verbatim reference.
+//
+//   traceit_headless [--steps K] [--cloud N] [--gravity G] [--no-file] [--trace I]
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "traceit_host.hpp"
+
+// Mirror of the reference's data model, same member names (src/main.cpp:51-54,79-105,118-126);
+// render-only members (mesh, matrices other than transform) are not needed headless.
+struct vec3d { float x, y, z; };
+struct matrx4d { float m[4][4]; };
+struct collider {
+    vec3d center;
+    vec3d size;
+    float radius;
+    bool isSphere;
+    bool isStatic;
+    float rest;
+};
+struct object {
+    vec3d pos;
+    vec3d vel;
+    vec3d force;
+    float mass;
+    matrx4d transform;
+    float Cd;
+    float area;
+    bool stationary;
+    std::vector<vec3d> trajectory;
+    int maxTrajectoryPoints = 300;
+    bool trajWritten = false;
+    collider col;
+};
+struct world {
+    std::vector<object> objects;
+    float globalScale;
+    float atmDensity;
+    float g;
+};
+
+static uint64_t state_hash(const world& w) {
+    uint64_t h = 1469598103934665603ULL;
+    for (const object& o : w.objects) {
+        const float f[6] = {o.pos.x, o.pos.y, o.pos.z, o.vel.x, o.vel.y, o.vel.z};
+        for (int k = 0; k < 6; ++k) {
+            uint32_t u;
+            std::memcpy(&u, &f[k], 4);
+            for (int s = 0; s < 4; ++s) {
+                h ^= (uint64_t)((u >> (8 * s)) & 0xffu);
+                h *= 1099511628211ULL;
+            }
+        }
+    }
+    return h;
+}
+
+// One projectile as the creation form builds it (src/main.cpp:1293-1307).
+static object make_projectile(float mass, float Cd, float elev, float azim, float magn, float size, vec3d pos) {
+    object o{};
+    o.mass = mass;
+    o.Cd = Cd;
+    o.pos = pos;
+    o.force = {0, 0, 0};
+    o.vel = traceit_b200::toSpherical<vec3d>(elev, azim, magn);
+    o.area = tr_area_from_size(size);
+    o.col.center = pos;
+    o.col.size = {size, size, size};
+    o.col.radius = 0.0f;
+    o.col.isSphere = false;
+    o.col.isStatic = false;
+    o.col.rest = 0.5f;
+    o.stationary = false;
+    return o;
+}
+
+int main(int argc, char** argv) {
+    int steps = 1000, cloud = 0, trace = 1;
+    float G = 0.0f;
+    bool file = true;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        if (a == "--steps" && i + 1 < argc) steps = std::atoi(argv[++i]);
+        else if (a == "--cloud" && i + 1 < argc) cloud = std::atoi(argv[++i]);
+        else if (a == "--gravity" && i + 1 < argc) G = (float)std::atof(argv[++i]);
+        else if (a == "--trace" && i + 1 < argc) trace = std::atoi(argv[++i]);
+        else if (a == "--no-file") file = false;
+        else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
+    }
+
+    world w;
+    w.globalScale = 1.0f;
+    w.atmDensity = 1.2f;    // createWorldUI default (src/main.cpp:1141)
+    w.g = 9.8f;             // set by the UI, never read by the step (src/main.cpp:1140 vs 749)
+
+    if (cloud <= 0) {
+        // the reference's seeded "earth" (src/main.cpp:1482-1491)
+        object earth{};
+        earth.pos = {0, -20, 0};
+        earth.mass = 1000;
+        earth.Cd = 1000.0f;
+        earth.area = 1000.0f;
+        earth.stationary = true;
+        earth.col.center = earth.pos;
+        earth.col.size = {10000, 5, 10000};
+        earth.col.isSphere = false;
+        earth.col.isStatic = false;
+        earth.col.rest = 1.0f;
+        earth.trajWritten = false;
+        w.objects.push_back(earth);
+        // config 1 projectiles
+        w.objects.push_back(make_projectile(10, 0.42f, 45, 0, 30, 1, {0, 0, 0}));
+        w.objects.push_back(make_projectile(5, 0.42f, 60, 90, 20, 2, {5, 0, 0}));
+    } else {
+        std::mt19937 rng(0xC0FFEE02u);
+        float L = 4.0f * std::cbrt((float)cloud);
+        std::uniform_real_distribution<float> up(-L, L), uv(-1.0f, 1.0f), um(1.0f, 10.0f);
+        for (int i = 0; i < cloud; ++i) {
+            object o{};
+            o.pos = {up(rng), up(rng), up(rng)};
+            o.vel = {uv(rng), uv(rng), uv(rng)};
+            o.mass = um(rng);
+            o.Cd = 0.42f;
+            o.area = tr_area_from_size(0.5f);
+            o.col = {o.pos, {0.5f, 0.5f, 0.5f}, 0.5f, true, false, 0.5f};
+            o.stationary = false;
+            w.objects.push_back(o);
+        }
+    }
+
+    traceit_b200::options().pair_gravity = G != 0.0f;
+    traceit_b200::options().G = G;
+    traceit_b200::options().write_trajectory_file = file;
+
+    std::ofstream coords;
+    try {
+        for (int s = 0; s < steps; ++s) {
+            traceit_b200::updatePhysics(w, coords);   // the call of src/main.cpp:1589
+            if ((s + 1 == 100 || s + 1 == steps) && trace >= 0 && trace < (int)w.objects.size()) {
+                const object& o = w.objects[trace];
+                std::printf("step %d body %d pos %.9g %.9g %.9g vel %.9g %.9g %.9g\n", s + 1, trace, o.pos.x, o.pos.y, o.pos.z,
+                            o.vel.x, o.vel.y, o.vel.z);
+            }
+        }
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "%s\n", e.what());
+        return 1;
+    }
+    std::printf("bodies %zu steps %d hash 0x%016llx\n", w.objects.size(), steps, (unsigned long long)state_hash(w));
+    traceit_b200::release(w);
+    return 0;
+}

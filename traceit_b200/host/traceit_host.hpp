@@ -1,0 +1,186 @@
+// traceit_host.hpp - C++ host shim: the reference's per-frame call, on the GPU.
+//
+// Restores the reference's own entry point
+//     void updatePhysics(world& w, ofstream& coords)            reference src/main.cpp:748
+// (called once per frame at src/main.cpp:1589) on top of the C ABI in
+// include/traceit_b200.h.  The shim is a template over the caller's world/object types, so
+// it binds to the reference's OWN structs when included from its main.cpp
+// and to the mirror structs of the headless harness here.  Required members, named exactly
+// as in the reference (src/main.cpp:79-126):
+//     World : objects (std::vector<Object>), atmDensity
+//     Object: pos, vel, force {x,y,z}; mass, Cd, area, stationary;
+//             col { center, size {x,y,z}, radius, isSphere, isStatic, rest }
+// optional (used when present): trajectory, maxTrajectoryPoints, trajWritten, transform.
+//
+// Per call: AoS objects -> tr_body_desc -> tr_step_host (upload, one step on the B200,
+// read back) -> AoS.  The world's side effects are reproduced on the host:
+//   * trajectory history + one-shot dump to "Координаты.txt"   src/main.cpp:754-761,793-808,814
+//     (the reference pushes the position right after integration, i.e. before the collision
+//      nudges; that value is the refreshed collider centre, src/main.cpp:791)
+//   * object.transform = translation(pos)                      src/main.cpp:641-644,810
+// Error behaviour: the reference step returns void and cannot fail; here a failure (no
+// B200, CUDA error, contact-buffer overflow) throws std::runtime_error with tr_last_error()
+// - there is no CPU fallback to fall into.
+#pragma once
+
+#include <cstdint>
+#include <fstream>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "../../include/traceit_b200.h"
+
+namespace traceit_b200 {
+
+namespace detail {
+
+template <class T, class = void> struct has_trajectory : std::false_type {};
+template <class T>
+struct has_trajectory<T, std::void_t<decltype(std::declval<T&>().trajectory), decltype(std::declval<T&>().trajWritten),
+                                     decltype(std::declval<T&>().maxTrajectoryPoints)>> : std::true_type {};
+template <class T, class = void> struct has_transform : std::false_type {};
+template <class T> struct has_transform<T, std::void_t<decltype(std::declval<T&>().transform.m[0][0])>> : std::true_type {};
+
+inline void check(int rc, const char* what) {
+    if (rc != TR_OK) throw std::runtime_error(std::string("traceit_b200: ") + what + ": " + tr_last_error());
+}
+
+struct Session {
+    tr_world* w = nullptr;
+    std::vector<tr_body_desc> staging;
+    size_t n = 0;
+    ~Session() { if (w) tr_world_destroy(w); }
+};
+
+// One device world per host world object (keyed by address), created on first use.
+inline std::map<const void*, Session>& sessions() {
+    static std::map<const void*, Session> s;
+    return s;
+}
+
+template <class Object>
+inline void to_desc(const Object& o, tr_body_desc& d) {
+    d.pos[0] = o.pos.x; d.pos[1] = o.pos.y; d.pos[2] = o.pos.z;
+    d.vel[0] = o.vel.x; d.vel[1] = o.vel.y; d.vel[2] = o.vel.z;
+    d.force[0] = o.force.x; d.force[1] = o.force.y; d.force[2] = o.force.z;
+    d.mass = o.mass; d.Cd = o.Cd; d.area = o.area;
+    d.stationary = o.stationary ? 1 : 0;
+    d.center[0] = o.col.center.x; d.center[1] = o.col.center.y; d.center[2] = o.col.center.z;
+    d.size[0] = o.col.size.x; d.size[1] = o.col.size.y; d.size[2] = o.col.size.z;
+    d.radius = o.col.radius;
+    d.isSphere = o.col.isSphere ? 1 : 0;
+    d.isStatic = o.col.isStatic ? 1 : 0;
+    d.rest = o.col.rest;
+}
+
+template <class Object>
+inline void from_desc(const tr_body_desc& d, Object& o) {
+    o.pos.x = d.pos[0]; o.pos.y = d.pos[1]; o.pos.z = d.pos[2];
+    o.vel.x = d.vel[0]; o.vel.y = d.vel[1]; o.vel.z = d.vel[2];
+    o.force.x = d.force[0]; o.force.y = d.force[1]; o.force.z = d.force[2];
+    o.col.center.x = d.center[0]; o.col.center.y = d.center[1]; o.col.center.z = d.center[2];
+}
+
+}  // namespace detail
+
+// World-level knobs the reference hard-codes inside the step (g, dt: src/main.cpp:749-750)
+// or leaves dead (pair gravity: src/main.cpp:679-693).  Defaults = reference behaviour.
+struct StepOptions {
+    bool pair_gravity = false;
+    float G = 6.6743e-11f;
+    bool collisions = true;
+    bool write_trajectory_file = true;   // the "Координаты.txt" side effect
+    int device = 0;
+};
+
+inline StepOptions& options() {
+    static StepOptions o;
+    return o;
+}
+
+// Drop the device world bound to `w` (e.g. before the host world is destroyed).
+template <class World>
+inline void release(World& w) { detail::sessions().erase(static_cast<const void*>(&w)); }
+
+// The reference's per-frame entry point, same signature (src/main.cpp:748).
+template <class World>
+void updatePhysics(World& w, std::ofstream& coords) {
+    using Object = typename std::decay<decltype(w.objects[0])>::type;
+    detail::Session& s = detail::sessions()[static_cast<const void*>(&w)];
+    const StepOptions& opt = options();
+    const size_t n = w.objects.size();
+
+    tr_world_params p;
+    detail::check(tr_default_params(&p), "tr_default_params");
+    p.atm_density = w.atmDensity;            // world::atmDensity, read by the drag term (main.cpp:777)
+    p.G = opt.G;
+    p.flags = (opt.pair_gravity ? TR_PAIR_GRAVITY : 0u) | (opt.collisions ? TR_COLLISIONS : 0u);
+
+    if (s.w && s.n != n) {                   // bodies were pushed or erased: rebuild the device world
+        tr_world_destroy(s.w);
+        s.w = nullptr;
+    }
+    if (!s.w) {
+        detail::check(tr_world_create(&p, opt.device, &s.w), "tr_world_create");
+        s.n = n;
+    } else {
+        detail::check(tr_world_set_params(s.w, &p), "tr_world_set_params");
+    }
+
+    static bool headerWritten = false;       // same one-shot header as main.cpp:754-761
+    if (opt.write_trajectory_file) {
+        coords.open("Координаты.txt", std::ios::app);
+        if (!headerWritten) {
+            coords << "Координаты в формате (x, y, z, время):\n";
+            headerWritten = true;
+        }
+    }
+
+    if (n) {
+        s.staging.resize(n);
+        for (size_t i = 0; i < n; ++i) detail::to_desc(w.objects[i], s.staging[i]);
+        detail::check(tr_step_host(s.w, n, s.staging.data(), 1), "tr_step_host");
+        for (size_t i = 0; i < n; ++i) {
+            Object& o = w.objects[i];
+            const bool moved = !o.stationary;
+            detail::from_desc(s.staging[i], o);
+            if (!moved) continue;            // the reference touches only non-stationary bodies below
+            if constexpr (detail::has_trajectory<Object>::value) {
+                // position right after integration == refreshed collider centre
+                o.trajectory.push_back(o.col.center);
+                if (o.trajectory.size() == (size_t)o.maxTrajectoryPoints && !o.trajWritten) {
+                    if (opt.write_trajectory_file) {
+                        coords << "\nТраектория объекта [" << "obj.id" << "]:\n";
+                        for (const auto& pt : o.trajectory) coords << pt.x << "(м)\t" << pt.y << "(м)\t" << pt.z << "(м)\n";
+                    }
+                    o.trajWritten = true;
+                }
+                if (o.trajectory.size() > (size_t)o.maxTrajectoryPoints) o.trajectory.erase(o.trajectory.begin());
+            }
+            if constexpr (detail::has_transform<Object>::value) {
+                // createTranslationMatrix(centre) - note: the reference builds it from the
+                // post-integration, pre-collision position (main.cpp:810 runs before 816)
+                for (int r = 0; r < 4; ++r)
+                    for (int c = 0; c < 4; ++c) o.transform.m[r][c] = (r == c) ? 1.0f : 0.0f;
+                o.transform.m[0][3] = o.col.center.x;   // translation sits in the 4th column (main.cpp:483-493)
+                o.transform.m[1][3] = o.col.center.y;
+                o.transform.m[2][3] = o.col.center.z;
+            }
+        }
+    }
+    if (opt.write_trajectory_file) coords.close();
+}
+
+// toSpherical of the creation form (src/main.cpp:1080-1089), any {x,y,z} aggregate.
+template <class Vec3>
+inline Vec3 toSpherical(const float& elev, const float& azim, const float& magn) {
+    float v[3];
+    tr_to_spherical(elev, azim, magn, v);
+    return Vec3{v[0], v[1], v[2]};
+}
+
+}  // namespace traceit_b200
