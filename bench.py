@@ -240,9 +240,7 @@ def main():
     params = tr.default_params(flags=flags, G=np.float32(GRAVITY_G), g=(0, 0, 0))
 
     if world_size > 1:
-        if cfg["collisions"]:
-            raise SystemExit(f"workload {name} has collisions: sharded worlds run gravity + integration only (use cfg4)")
-        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        uid =torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
             uid = torch.frombuffer(bytearray(tr.comm_unique_id()), dtype=torch.uint8).to(dev)
         dist.broadcast(uid, 0)

@@ -352,3 +352,39 @@ def test_full_size_1m_properties(tr, oracle):
         hit = hit[hit != i]
         mine = set(map(tuple, contacts[(contacts[:, 0] == i) | (contacts[:, 1] == i)].tolist()))
         assert mine == {(min(i, j), max(i, j)) for j in hit.tolist()}
+
+
+def test_crowded_cell_falls_back_to_radix_sort(tr, oracle):
+    """More bodies in one cell than the quadratic rank step accepts (OCC_LIMIT = 1024): the
+    broad phase must switch to its radix-sort fallback and still produce the exact keys, order,
+    candidates and contact set."""
+    n = 6000
+    b = scenes.random_cloud(n, 5150, spheres=True, density_l=0.8)
+    rs = np.random.RandomState(3)
+    # 1500 bodies packed into a ball much smaller than one cell (cell edge ~1.008)
+    b["pos"][:1500] = (rs.uniform(-0.05, 0.05, size=(1500, 3)) + np.array([0.5, 0.5, 0.5])).astype(np.float32)
+    b["center"] = b["pos"]
+    b["vel"][:1500] = 0
+    p = tr.default_params(g=(0, 0, 0), max_contacts=4_000_000)
+    with tr.World(p) as w:
+        w.add(b)
+        g = w.debug_grid()
+        ncand, cand = w.debug_candidates()
+        w.step(1)
+        got = w.read_bodies()
+        contacts = w.contacts()
+    keys = oracle.grid_keys(b, (0, 0, 0), g["inv_cell"], g["bits"])
+    assert np.array_equal(g["keys"], keys)
+    assert np.bincount(keys).max() >= 1500
+    order, _ = oracle.grid_sort(keys, np.arange(n, dtype=np.int32), g["bits"])
+    assert np.array_equal(g["sorted_ids"].astype(np.int32), order)
+    ocand, _, nc, _ = oracle.grid_pairs(b, np.ones(n, np.uint8), (0, 0, 0), g["inv_cell"], g["bits"], want_contacts=False)
+    assert ncand == nc and np.array_equal(cand, ocand)
+    want = b.copy()
+    op = oracle.default_params(g=(0, 0, 0))
+    oracle.integrate(want, op)
+    oc = oracle.contacts(want)
+    oracle.resolve_list(want, oc)
+    assert len(oc) > 1_000_000
+    assert np.array_equal(contacts, oc)
+    check_state(got, want, "crowded cell")

@@ -28,3 +28,14 @@ def test_two_ranks_equal_unsharded(n):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SHARDED_OK" in r.stdout
+
+
+def test_two_ranks_with_replicated_collisions_equal_unsharded():
+    """gravity + collisions on 2 ranks == unsharded, bit for bit."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29545", os.path.join(ROOT, "tools", "sharded_check.py"), "12001", "5", "collide"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "SHARDED_OK" in r.stdout

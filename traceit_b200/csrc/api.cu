@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(256) unpack_kernel(const tr_body_desc* __restr
     if (b.stationary) f |= F_STATIONARY;
     if (b.isStatic) f |= F_STATIC;
     if (b.isSphere) f |= F_SPHERE;
+    if (!(b.mass <= 0)) f |= F_LIVE;
     s.flags[i] = f;
 }
 
@@ -143,6 +144,18 @@ __global__ void __launch_bounds__(256) read_state_kernel(const float4* __restric
 __global__ void copy_pos_kernel(const float4* __restrict__ a, float4* __restrict__ b, uint32_t n) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) b[t] = a[t];
+}
+
+// sharded collisions: collider centres of bodies integrated by OTHER ranks
+__global__ void __launch_bounds__(256) refresh_remote_centers(const float4* __restrict__ pos_m, float4* center_r,
+                                                              const uint8_t* __restrict__ flags, uint32_t n,
+                                                              uint32_t own_first, uint32_t own_count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (i >= own_first && i < own_first + own_count)) return;
+    if (flags[i] & F_STATIONARY) return;
+    float4 p = pos_m[i];
+    float4 c = center_r[i];
+    center_r[i] = make_float4(p.x, p.y, p.z, c.w);
 }
 
 static SoA soa_of(tr_world* w) {
@@ -348,11 +361,6 @@ static int step_once(tr_world* w) {
     const StepConsts c = consts_of(w);
     const bool grav = (w->params.flags & TR_PAIR_GRAVITY) != 0;
     const bool coll = (w->params.flags & TR_COLLISIONS) != 0;
-    if (coll && w->nranks > 1) {
-        set_error("sharded worlds run gravity + drag + integration only; collisions under sharding are not "
-                  "implemented (SURVEY.md 8f row 4)");
-        return TR_ERR_STATE;
-    }
     if (grav) {
         TR_TRY(gravity_step(w, c, true, nullptr));
         w->cur ^= 1;
@@ -362,6 +370,19 @@ static int step_once(tr_world* w) {
     } else {
         TR_TRY(integrate_only(w, c));
         if (w->nranks > 1) TR_TRY(nccl_allgather_pos(w, w->pos_m[w->cur]));
+    }
+    if (coll && w->nranks > 1) {
+        // Sharded collisions: the collision pipeline is cheap next to
+        // gravity (~140 B/body vs N interactions/body), so it is REPLICATED: gather the freshly
+        // integrated velocities too, refresh the collider centres of the bodies other ranks
+        // integrated (centre := pos for non-stationary bodies, main.cpp:791), then every rank
+        // runs the same deterministic detection + ordered response on the full state.
+        TR_TRY(nccl_allgather_pos(w, w->vel_rest));
+        unsigned blocks = (unsigned)((w->n + 255) / 256);
+        refresh_remote_centers<<<blocks, 256, 0, w->stream>>>(w->pos_m[w->cur], w->center_r, w->flags, (uint32_t)w->n,
+                                                              (uint32_t)w->own_first, (uint32_t)w->own_count);
+        TR_CUDA(cudaGetLastError());
+        w->stats.kernel_launches += 1;
     }
     if (coll) TR_TRY(collide_step(w, false));
     w->stats.steps += 1;
@@ -546,6 +567,7 @@ int tr_sync(tr_world* w) {
     TR_TRY(check_world(w));
     TR_CUDA(cudaStreamSynchronize(w->stream));
     timers_collect(w);
+    collide_poll_stats(w);
     if (w->deferred_error != TR_OK) {
         int rc = w->deferred_error;
         set_error("%s", w->deferred_msg.c_str());
@@ -708,7 +730,10 @@ int tr_get_stats(tr_world* w, tr_stats* s) {
     if (!w || !s) return TR_ERR_INVALID_ARG;
     // only completed work is folded in; call tr_sync first for exact numbers
     cudaSetDevice(w->device);
-    if (cudaStreamQuery(w->stream) == cudaSuccess) timers_collect(w);
+    if (cudaStreamQuery(w->stream) == cudaSuccess) {
+        timers_collect(w);
+        collide_poll_stats(w);
+    }
     *s = w->stats;
     return TR_OK;
 }

@@ -4,15 +4,20 @@
 // i<j sweep with checkSphereCollision / checkAABBCollision (src/main.cpp:648-660) and a
 // Gauss-Seidel impulse + positional nudge (src/main.cpp:709-742).
 //
-//   K2  cell keys            one thread per body: wrapped uniform-grid key from the collider
-//                            centre; bodies that cannot live in the grid (boxes, oversize or
-//                            out-of-domain spheres) are appended to a side list; mass<=0
+// Broad phase = ONE-DIGIT radix sort of the wrapped cell keys (radix = number of cells):
+//   K2  keys_count_kernel    one thread per body: cell key from the collider centre, per-cell
+//                            histogram by atomics; bodies that cannot live in the grid (boxes,
+//                            oversize / out-of-domain spheres) go to a side list; mass<=0
 //                            bodies are dropped (they can never collide, main.cpp:696).
-//   K3  radix sort           (key, id) pairs, stable => (key,id) order.
-//   K4  cell ranges + gather first slot of every occupied cell; centres gathered to sorted order.
-//   K5  narrow phase         27-cell stencil per grid body, exact reference predicate
-//                            (no FMA contraction), emits (i<j) contacts.
-//   K5b side list            every side-list body against every live body.
+//   K3a tile_sums + scan     exclusive scan of the histogram in two unchained kernels
+//                            -> dense cell_start[ncell+1] table.
+//   K3b scatter_kernel       body ids into their cell's segment (arrival order).
+//   K4  rank_gather_kernel   rank of each id inside its cell (ascending id) -> the stable
+//                            (key,id) order; collider centres gathered into that order.
+//   (fallback for pathological occupancy: CUB radix sort + binary-search cell table.)
+//   K5  narrow_kernel        27-cell stencil as 9 contiguous key ranges, exact reference
+//                            predicate (no FMA contraction), emits (i<j) contacts.
+//   K5b side_kernel          every side-list body against every live body.
 //   K6  ordered response     contacts sorted by (i,j); a dependency wavefront replays the
 //                            reference's Gauss-Seidel order exactly: a contact runs when
 //                            the previous contact of BOTH its bodies has run, so results
@@ -36,6 +41,14 @@ namespace tr {
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t ID_MASK = 0x7FFFFFFFu;
 constexpr uint32_t STATIC_BIT = 0x80000000u;
+constexpr uint32_t OCC_LIMIT = 1024;      // bodies per cell above which the O(occ^2) rank step is refused
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+// counters[] slots
+enum { C_SIDE = 0, C_GRID = 1, C_CONTACTS = 2 /*u64*/, C_CAND = 4 /*u64*/, C_MAXOCC = 6, C_FRONT = 8 /*3*/, C_ROUNDS = 11,
+       C_NCOUNTERS = 16 };
 
 }  // namespace tr
 
@@ -44,6 +57,8 @@ struct Collide {
     float cell = 1.f, inv_cell = 1.f, rmax_grid = 0.f;
     float origin[3] = {0, 0, 0};
     int bits = 2;
+    bool may_have_side = true;    // some body is statically outside the grid (box / oversize / NaN radius)
+    bool use_cub = false;         // occupancy fallback engaged
     uint64_t cap_bodies = 0;      // arrays below sized for this many bodies
     uint64_t ncell_alloc = 0;
     uint64_t cap_contacts = 0;
@@ -51,19 +66,22 @@ struct Collide {
     // per body
     uint32_t* keys = nullptr;        // K2 out: key, or sentinel 1<<(3*bits) for non-grid bodies
     uint32_t* keys_sorted = nullptr;
-    uint32_t* vals = nullptr;        // id | static<<31
-    uint32_t* vals_sorted = nullptr;
+    uint32_t* vals = nullptr;        // fallback path: id | static<<31
+    uint32_t* vals_sorted = nullptr; // id | static<<31 in (key,id) order
+    uint2* tmp_ids = nullptr;        // K3b out: (id|static, key) grouped by cell, arrival order
+    uint32_t* tile_sum = nullptr;    // scan: per-tile histogram sums
     float4* sorted_center_r = nullptr;
-    uint32_t* cell_start = nullptr;  // [ncell]
+    uint32_t* cell_count = nullptr;  // [ncell] histogram; self-cleaning (K3b counts it back to zero)
+    uint32_t* cell_start = nullptr;  // [ncell+1] dense exclusive prefix
     uint32_t* side_list = nullptr;   // ids of side-list bodies
     uint8_t* klass = nullptr;        // 0 dropped, 1 grid, 2 side
     uint32_t* row_start = nullptr;   // per body: first contact with i == body
     uint32_t* col_last = nullptr;    // per body: last column-order slot with j == body
 
-    // counters: [0] side count, [1] grid count, [2..3] contact count (u64), [4..5] candidates (u64),
-    // [8..10] frontier counts, [11] rounds
     uint32_t* counters = nullptr;
-    uint32_t* h_counters = nullptr;  // pinned mirror
+    uint32_t* h_counters = nullptr;  // pinned mirror (detection read-back)
+    uint32_t* h_rounds = nullptr;    // pinned: response wavefront count, fetched lazily
+    bool rounds_pending = false;
 
     // per contact
     unsigned long long* ckeys = nullptr;      // (i<<32)|j, unsorted then sorted
@@ -80,6 +98,11 @@ struct Collide {
 
     void* cub_tmp = nullptr;
     size_t cub_tmp_bytes = 0;
+
+    // K2-K4 as one CUDA graph (memset + 5 kernels): launch parameters only change when the
+    // buffers, the grid or the body count change, so the graph is re-captured only then
+    cudaGraphExec_t bp_graph = nullptr;
+    uint64_t bp_sig[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
     uint64_t last_contacts = 0;
     uint64_t last_grid = 0;
@@ -111,11 +134,6 @@ __device__ __forceinline__ bool aabb_hit(const float4 ca, const float4 ha, const
            fabsf(__fsub_rn(ca.z, cb.z)) <= __fadd_rn(ha.z, hb.z);
 }
 
-__device__ __forceinline__ int cell_coord(float center, float origin, float inv_cell) {
-    float u = __fmul_rn(__fsub_rn(center, origin), inv_cell);
-    return __float2int_rd(u);   // floor, saturating, NaN -> 0
-}
-
 __device__ __forceinline__ uint32_t pack_key(int cx, int cy, int cz, int bits) {
     uint32_t m = (1u << bits) - 1u;
     return ((uint32_t)cx & m) | (((uint32_t)cy & m) << bits) | (((uint32_t)cz & m) << (2 * bits));
@@ -127,64 +145,215 @@ struct GridParams {
 };
 
 // ---------------------------------------------------------------------------------------
-// K2: keys + classification
+// K2: keys + classification (+ per-cell histogram on the fast path)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ center_r, const float4* __restrict__ pos_m,
+template <bool COUNT>
+__global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ center_r,
                                                    const uint8_t* __restrict__ flags, uint32_t n, GridParams g,
                                                    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                                    uint8_t* __restrict__ klass, uint32_t* __restrict__ side_list,
-                                                   uint32_t* counters) {
+                                                   uint32_t* __restrict__ cell_count, uint32_t* counters) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 c = center_r[i];
-    const float mass = pos_m[i].w;
-    const uint8_t f = flags[i];
-    const uint32_t sentinel = 1u << (3 * g.bits);
-    uint32_t key = sentinel;
-    uint8_t k = 0;
-    if (!(mass <= 0)) {   // main.cpp:696 drops mass<=0 bodies from every pair
-        float ux = __fmul_rn(__fsub_rn(c.x, g.ox), g.inv_cell);
-        float uy = __fmul_rn(__fsub_rn(c.y, g.oy), g.inv_cell);
-        float uz = __fmul_rn(__fsub_rn(c.z, g.oz), g.inv_cell);
-        bool in_domain = fabsf(ux) < 32768.0f && fabsf(uy) < 32768.0f && fabsf(uz) < 32768.0f;
-        bool grid_ok = (f & F_SPHERE) && in_domain && fabsf(c.w) <= g.rmax_grid;
-        if (grid_ok) {
-            key = pack_key(__float2int_rd(ux), __float2int_rd(uy), __float2int_rd(uz), g.bits);
-            k = 1;
-        } else {
-            k = 2;
-            uint32_t slot = atomicAdd(&counters[0], 1u);
-            side_list[slot] = i;
-        }
+    if (COUNT) {
+        // stream the (zeroed) histogram into L2 ahead of the scattered REDs: one 128-byte line per
+        // thread of the leading CTAs, so random cloud ids do not pay a DRAM round trip per atomic
+        const uint32_t ncell = 1u << (3 * g.bits);
+        if (i < ncell / 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(cell_count + (size_t)i * 32));
     }
-    keys[i] = key;
-    vals[i] = i | ((f & F_STATIC) ? STATIC_BIT : 0u);
-    klass[i] = k;
+    if (i < n) {
+        const float4 c = center_r[i];
+        const uint8_t f = flags[i];
+        const uint32_t sentinel = 1u << (3 * g.bits);
+        uint32_t key = sentinel;
+        uint8_t k = 0;
+        if (f & F_LIVE) {   // main.cpp:696 drops mass<=0 bodies from every pair (flag set at upload)
+            float ux = __fmul_rn(__fsub_rn(c.x, g.ox), g.inv_cell);
+            float uy = __fmul_rn(__fsub_rn(c.y, g.oy), g.inv_cell);
+            float uz = __fmul_rn(__fsub_rn(c.z, g.oz), g.inv_cell);
+            bool in_domain = fabsf(ux) < 32768.0f && fabsf(uy) < 32768.0f && fabsf(uz) < 32768.0f;
+            bool grid_ok = (f & F_SPHERE) && in_domain && fabsf(c.w) <= g.rmax_grid;
+            if (grid_ok) {
+                key = pack_key(__float2int_rd(ux), __float2int_rd(uy), __float2int_rd(uz), g.bits);
+                k = 1;
+                if (COUNT) atomicAdd(&cell_count[key], 1u);   // result unused: a fire-and-forget RED
+            } else {
+                k = 2;
+                uint32_t slot = atomicAdd(&counters[C_SIDE], 1u);
+                side_list[slot] = i;
+            }
+        }
+        keys[i] = key;
+        if (!COUNT) vals[i] = i | ((f & F_STATIC) ? STATIC_BIT : 0u);
+        klass[i] = k;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
-// K4: cell ranges + gather to sorted order
+// K3a: exclusive scan of the histogram in two unchained kernels (a look-back chain over
+// ~1000 tiles costs more in latency than the second launch):
+//   tile_sums_kernel   one CTA per tile of 2048 cells -> tile_sum[tile], and the occupancy guard
+//   scan_kernel        each CTA adds up the sums of the tiles before it (<= 4 KB, L2 hits),
+//                      scans its own tile and writes the dense cell_start table.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ranges_kernel(const uint32_t* __restrict__ keys_sorted,
-                                                     const uint32_t* __restrict__ vals_sorted,
-                                                     const float4* __restrict__ center_r, uint32_t n, uint32_t sentinel,
-                                                     uint32_t* __restrict__ cell_start,
-                                                     float4* __restrict__ sorted_center_r, uint32_t* counters) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    uint32_t k = keys_sorted[t];
-    uint32_t kp = t ? keys_sorted[t - 1] : EMPTY;
-    if (k == sentinel) {
-        if (kp != sentinel) counters[1] = t;   // number of grid bodies
-        return;
+__device__ __forceinline__ void load_tile_items(const uint32_t* __restrict__ cell_count, uint32_t base, uint32_t ncell,
+                                                uint32_t (&v)[SCAN_ITEMS]) {
+    if (base + SCAN_ITEMS <= ncell) {
+        const uint4 a = *reinterpret_cast<const uint4*>(cell_count + base);
+        const uint4 b = *reinterpret_cast<const uint4*>(cell_count + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) v[k] = (base + k < ncell) ? cell_count[base + k] : 0u;
     }
-    if (t == n - 1) counters[1] = n;
-    if (k != kp) cell_start[k] = t;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) tile_sums_kernel(const uint32_t* __restrict__ cell_count, uint32_t ncell,
+                                                                 uint32_t* __restrict__ tile_sum, uint32_t* counters) {
+    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+    uint32_t v[SCAN_ITEMS];
+    load_tile_items(cell_count, blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS, ncell, v);
+    uint32_t tsum = 0, vmax = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        tsum += v[k];
+        vmax = max(vmax, v[k]);
+    }
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // largest cell population guards the O(occ^2) rank step; almost never above a handful
+    vmax = __reduce_max_sync(0xFFFFFFFFu, vmax);
+    if (lane == 0 && vmax > OCC_LIMIT) atomicMax(&counters[C_MAXOCC], vmax);
+    tsum = __reduce_add_sync(0xFFFFFFFFu, tsum);
+    if (lane == 0) s_warp[wid] = tsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_THREADS / 32; ++k) t += s_warp[k];
+        tile_sum[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const uint32_t* __restrict__ cell_count,
+                                                            const uint32_t* __restrict__ tile_sum,
+                                                            uint32_t* __restrict__ cell_start, uint32_t ncell,
+                                                            uint32_t* counters) {
+    __shared__ uint32_t s_warp[SCAN_THREADS / 32], s_red[SCAN_THREADS / 32], s_prefix;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // prefix of this tile = sum of the tile sums before it
+    uint32_t pre = 0;
+    for (uint32_t k = threadIdx.x; k < tile; k += SCAN_THREADS) pre += tile_sum[k];
+    pre = __reduce_add_sync(0xFFFFFFFFu, pre);
+    if (lane == 0) s_red[wid] = pre;
+    const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    load_tile_items(cell_count, base, ncell, v);
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) tsum += v[k];
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (uint32_t)o) incl += y;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t wv = lane < SCAN_THREADS / 32 ? s_warp[lane] : 0u;
+        uint32_t wi = wv;
+#pragma unroll
+        for (int o = 1; o < SCAN_THREADS / 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+            if (lane >= (uint32_t)o) wi += y;
+        }
+        if (lane < SCAN_THREADS / 32) s_warp[lane] = wi - wv;            // exclusive warp offsets
+        uint32_t r = lane < SCAN_THREADS / 32 ? s_red[lane] : 0u;
+        r = __reduce_add_sync(0xFFFFFFFFu, r);
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, wi, SCAN_THREADS / 32 - 1);
+        if (lane == 0) {
+            s_prefix = r;
+            if ((tile + 1) * (uint32_t)SCAN_TILE >= ncell) {   // last tile: grand total = number of grid bodies
+                cell_start[ncell] = r + total;
+                counters[C_GRID] = r + total;
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t ex = s_prefix + s_warp[wid] + (incl - tsum);
+    uint32_t o[SCAN_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        o[k] = ex;
+        ex += v[k];
+    }
+    if (base + SCAN_ITEMS <= ncell) {
+        *reinterpret_cast<uint4*>(cell_start + base) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(cell_start + base + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k)
+            if (base + k < ncell) cell_start[base + k] = o[k];
+    }
+}
+
+// K3b: (id|static, key) into the cell's segment; counting the histogram back down leaves it
+// zeroed for the next step.
+__global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict__ keys, uint32_t sentinel,
+                                                      const uint8_t* __restrict__ flags, uint32_t n,
+                                                      const uint32_t* __restrict__ cell_start,
+                                                      uint32_t* __restrict__ cell_count, uint2* __restrict__ tmp) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t key = keys[i];
+    if (key >= sentinel) return;          // side-list or dropped body
+    const uint32_t old = atomicSub(&cell_count[key], 1u);
+    tmp[cell_start[key] + old - 1u] = make_uint2(i | ((flags[i] & F_STATIC) ? STATIC_BIT : 0u), key);
+}
+
+// K4: deterministic order inside each cell (ascending id) + gather to sorted order.
+__global__ void __launch_bounds__(256) rank_gather_kernel(const uint2* __restrict__ tmp, const uint32_t* __restrict__ cell_start,
+                                                          const float4* __restrict__ center_r,
+                                                          const uint32_t* __restrict__ counters,
+                                                          uint32_t* __restrict__ keys_sorted, uint32_t* __restrict__ vals_sorted,
+                                                          float4* __restrict__ sorted_center_r) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= counters[C_GRID] || counters[C_MAXOCC] > OCC_LIMIT) return;
+    const uint2 me = tmp[t];
+    const uint32_t id = me.x & ID_MASK;
+    const float4 c = center_r[id];                        // issue the gather before the rank loop
+    const uint32_t s = cell_start[me.y], e = cell_start[me.y + 1];
+    uint32_t rank = 0;
+    for (uint32_t u = s; u < e; ++u) rank += ((tmp[u].x & ID_MASK) < id) ? 1u : 0u;
+    const uint32_t f = s + rank;
+    keys_sorted[f] = me.y;
+    vals_sorted[f] = me.x;
+    sorted_center_r[f] = c;
+}
+
+// ---- fallback path (cell population above OCC_LIMIT): CUB radix sort, then the same tables ----
+__global__ void __launch_bounds__(256) dense_start_kernel(const uint32_t* __restrict__ keys_sorted, uint32_t n, uint32_t ncell,
+                                                          uint32_t* __restrict__ cell_start, uint32_t* counters) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > ncell) return;
+    uint32_t lo = 0, hi = n;              // first slot whose key >= k   (sentinel keys sort last)
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (keys_sorted[mid] < k) lo = mid + 1; else hi = mid;
+    }
+    cell_start[k] = lo;
+    if (k == ncell) counters[C_GRID] = lo;
+}
+
+__global__ void __launch_bounds__(256) gather_kernel(const uint32_t* __restrict__ vals_sorted, const float4* __restrict__ center_r,
+                                                     const uint32_t* __restrict__ counters, float4* __restrict__ sorted_center_r) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= counters[C_GRID]) return;
     sorted_center_r[t] = center_r[vals_sorted[t] & ID_MASK];
 }
 
 // ---------------------------------------------------------------------------------------
-// K5: narrow phase over the 27-cell stencil
+// K5: narrow phase over the 27-cell stencil (9 runs of up to 3 key-contiguous cells)
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void emit_pair(unsigned long long* out, unsigned long long cap, unsigned long long* counter,
                                           uint32_t i, uint32_t j) {
@@ -193,54 +362,71 @@ __device__ __forceinline__ void emit_pair(unsigned long long* out, unsigned long
 }
 
 template <bool CANDIDATES>
+__device__ __forceinline__ void test_range(uint32_t s, uint32_t e, uint32_t va, uint32_t ida, const float4 ca,
+                                           const uint32_t* __restrict__ vals_sorted,
+                                           const float4* __restrict__ sorted_center_r, unsigned long long* out,
+                                           unsigned long long cap, unsigned long long* counter) {
+    for (uint32_t u = s; u < e; ++u) {
+        const uint32_t vb = vals_sorted[u];
+        const uint32_t idb = vb & ID_MASK;
+        if (idb <= ida) continue;
+        if (CANDIDATES) {
+            emit_pair(out, cap, counter, ida, idb);
+        } else {
+            if (va & vb & STATIC_BIT) continue;                      // main.cpp:695
+            if (sphere_hit(ca, sorted_center_r[u])) emit_pair(out, cap, counter, ida, idb);
+        }
+    }
+}
+
+template <bool CANDIDATES>
 __global__ void __launch_bounds__(128) narrow_kernel(const uint32_t* __restrict__ keys_sorted,
                                                      const uint32_t* __restrict__ vals_sorted,
                                                      const float4* __restrict__ sorted_center_r,
-                                                     const uint32_t* __restrict__ cell_start, uint32_t m, int bits,
-                                                     unsigned long long* out, unsigned long long cap,
+                                                     const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ counters,
+                                                     int bits, bool check_occ, unsigned long long* out, unsigned long long cap,
                                                      unsigned long long* counter) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m) return;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= counters[C_GRID]) return;
+    if (check_occ && counters[C_MAXOCC] > OCC_LIMIT) return;   // fast path refused; the host reruns through the fallback
     const uint32_t key = keys_sorted[t];
     const uint32_t va = vals_sorted[t];
     const uint32_t ida = va & ID_MASK;
     const float4 ca = sorted_center_r[t];
     const uint32_t msk = (1u << bits) - 1u;
     const uint32_t cx = key & msk, cy = (key >> bits) & msk, cz = (key >> (2 * bits)) & msk;
+    const bool interior = cx > 0 && cx < msk;
 #pragma unroll 1
     for (int dz = -1; dz <= 1; ++dz) {
 #pragma unroll 1
         for (int dy = -1; dy <= 1; ++dy) {
+            const uint32_t row = (((cy + dy) & msk) << bits) | (((cz + dz) & msk) << (2 * bits));
+            if (interior) {
+                // cells (cx-1, cx, cx+1) of this row are consecutive keys: one contiguous slot range
+                test_range<CANDIDATES>(cell_start[row + cx - 1], cell_start[row + cx + 2], va, ida, ca, vals_sorted,
+                                       sorted_center_r, out, cap, counter);
+            } else {
 #pragma unroll 1
-            for (int dx = -1; dx <= 1; ++dx) {
-                uint32_t nk = ((cx + dx) & msk) | (((cy + dy) & msk) << bits) | (((cz + dz) & msk) << (2 * bits));
-                uint32_t s = cell_start[nk];
-                if (s == EMPTY) continue;
-                for (uint32_t u = s; u < m && keys_sorted[u] == nk; ++u) {
-                    const uint32_t vb = vals_sorted[u];
-                    const uint32_t idb = vb & ID_MASK;
-                    if (idb <= ida) continue;
-                    if (CANDIDATES) {
-                        emit_pair(out, cap, counter, ida, idb);
-                    } else {
-                        if (va & vb & STATIC_BIT) continue;                      // main.cpp:695
-                        if (sphere_hit(ca, sorted_center_r[u])) emit_pair(out, cap, counter, ida, idb);
-                    }
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const uint32_t nk = row | ((cx + dx) & msk);
+                    test_range<CANDIDATES>(cell_start[nk], cell_start[nk + 1], va, ida, ca, vals_sorted, sorted_center_r, out,
+                                           cap, counter);
                 }
             }
         }
     }
 }
 
-// K5b: side-list bodies against every live body.  grid = (ceil(n/256), side_count).
-__global__ void __launch_bounds__(256) side_kernel(const uint32_t* __restrict__ side_list, uint32_t side_count,
+// K5b: side-list bodies against every live body.  grid = (ceil(n/256), up to 64).
+__global__ void __launch_bounds__(256) side_kernel(const uint32_t* __restrict__ side_list, const uint32_t* __restrict__ counters,
                                                    const float4* __restrict__ center_r,
                                                    const float4* __restrict__ half_ext,
                                                    const uint8_t* __restrict__ flags, const uint8_t* __restrict__ klass,
                                                    uint32_t n, unsigned long long* out, unsigned long long cap,
                                                    unsigned long long* counter) {
+    const uint32_t side_count = counters[C_SIDE];
     uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= n) return;
+    if (x >= n || blockIdx.y >= side_count) return;
     const uint8_t kx = klass[x];
     if (kx == 0) return;
     const float4 cx = center_r[x], hx = half_ext[x];
@@ -459,6 +645,15 @@ int collide_classify(tr_world* w) {
         }
     }
     c->rmax_grid = rmax;
+    // can any body be outside the grid for a reason known at creation time?
+    c->may_have_side = false;
+    for (const tr_body_desc& b : w->host_bodies) {
+        if (b.mass <= 0) continue;
+        if (!b.isSphere || !(std::fabs(b.radius) <= rmax)) {
+            c->may_have_side = true;
+            break;
+        }
+    }
     float cell = p.grid_cell;
     if (cell <= 0.f) {
         cell = (2.0f * rmax) * 1.0078125f;   // 2*rmax*(1+2^-7): margin analysed in DESIGN.md
@@ -474,6 +669,7 @@ int collide_classify(tr_world* w) {
         while (bits < 10 && (1ull << (3 * bits)) < want) ++bits;
     }
     c->bits = bits;
+    c->use_cub = false;
     w->classified = true;
     return TR_OK;
 }
@@ -487,6 +683,7 @@ static int ensure_buffers(tr_world* w) {
         TR_TRY(realloc_dev(&c->keys_sorted, cap));
         TR_TRY(realloc_dev(&c->vals, cap));
         TR_TRY(realloc_dev(&c->vals_sorted, cap));
+        TR_TRY(realloc_dev(&c->tmp_ids, cap));
         TR_TRY(realloc_dev(&c->sorted_center_r, cap));
         TR_TRY(realloc_dev(&c->side_list, cap));
         TR_TRY(realloc_dev(&c->klass, cap));
@@ -496,7 +693,11 @@ static int ensure_buffers(tr_world* w) {
     }
     const uint64_t ncell = 1ull << (3 * c->bits);
     if (ncell > c->ncell_alloc) {
-        TR_TRY(realloc_dev(&c->cell_start, ncell));
+        TR_TRY(realloc_dev(&c->cell_start, ncell + 1));
+        TR_TRY(realloc_dev(&c->cell_count, ncell));
+        TR_TRY(realloc_dev(&c->tile_sum, (ncell + SCAN_TILE - 1) / SCAN_TILE));
+        // zeroed ONCE: the histogram counts itself back to zero every step (scatter_kernel)
+        TR_CUDA(cudaMemsetAsync(c->cell_count, 0, ncell * sizeof(uint32_t), w->stream));
         c->ncell_alloc = ncell;
     }
     uint64_t want_c = w->params.max_contacts ? w->params.max_contacts : 8 * n + 4096;
@@ -517,8 +718,10 @@ static int ensure_buffers(tr_world* w) {
         c->cap_contacts = want_c;
     }
     if (!c->counters) {
-        TR_CUDA(cudaMalloc(&c->counters, 16 * sizeof(uint32_t)));
-        TR_CUDA(cudaMallocHost(&c->h_counters, 16 * sizeof(uint32_t)));
+        TR_CUDA(cudaMalloc(&c->counters, C_NCOUNTERS * sizeof(uint32_t)));
+        TR_CUDA(cudaMallocHost(&c->h_counters, C_NCOUNTERS * sizeof(uint32_t)));
+        TR_CUDA(cudaMallocHost(&c->h_rounds, sizeof(uint32_t)));
+        *c->h_rounds = 0;
     }
     // CUB scratch sized for the largest of the three sorts
     size_t need = 0, b = 0;
@@ -543,67 +746,142 @@ static int bits_for(uint64_t max_value) {
     return b;
 }
 
-// Broad phase K2-K4.  Leaves counters[0] (side count) and counters[1] (grid count) on the device.
+static int launch_fast_broad(tr_world* w, cudaStream_t st) {
+    Collide* c = state(w);
+    const uint32_t n = (uint32_t)w->n;
+    const uint32_t blocks = (n + 255) / 256;
+    const uint32_t ncell = 1u << (3 * c->bits);
+    const uint32_t ntiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
+    GridParams g{c->origin[0], c->origin[1], c->origin[2], c->inv_cell, c->rmax_grid, c->bits};
+    TR_CUDA(cudaMemsetAsync(c->counters, 0, C_NCOUNTERS * sizeof(uint32_t), st));
+    keys_kernel<true><<<blocks, 256, 0, st>>>(w->center_r, w->flags, n, g, c->keys, c->vals, c->klass, c->side_list,
+                                              c->cell_count, c->counters);
+    tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, ncell, c->tile_sum, c->counters);
+    scan_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, c->tile_sum, c->cell_start, ncell, c->counters);
+    scatter_kernel<<<blocks, 256, 0, st>>>(c->keys, ncell, w->flags, n, c->cell_start, c->cell_count, c->tmp_ids);
+    rank_gather_kernel<<<blocks, 256, 0, st>>>(c->tmp_ids, c->cell_start, w->center_r, c->counters, c->keys_sorted,
+                                               c->vals_sorted, c->sorted_center_r);
+    TR_CUDA(cudaGetLastError());
+    return TR_OK;
+}
+
+// Broad phase K2-K4.  Leaves counters[C_SIDE] / [C_GRID] / [C_MAXOCC] on the device; no host sync.
 static int broad_phase(tr_world* w) {
     Collide* c = state(w);
     const uint32_t n = (uint32_t)w->n;
     const uint32_t blocks = (n + 255) / 256;
-    GridParams g{c->origin[0], c->origin[1], c->origin[2], c->inv_cell, c->rmax_grid, c->bits};
-    const uint32_t sentinel = 1u << (3 * c->bits);
+    const uint32_t ncell = 1u << (3 * c->bits);
     PendingTimer t;
-    timer_begin(w, T_BROAD, &t);
-    TR_CUDA(cudaMemsetAsync(c->counters, 0, 16 * sizeof(uint32_t), w->stream));
-    TR_CUDA(cudaMemsetAsync(c->cell_start, 0xFF, (1ull << (3 * c->bits)) * sizeof(uint32_t), w->stream));
-    keys_kernel<<<blocks, 256, 0, w->stream>>>(w->center_r, w->pos_m[w->cur], w->flags, n, g, c->keys, c->vals, c->klass,
-                                               c->side_list, c->counters);
-    size_t tmp = c->cub_tmp_bytes;
-    TR_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, c->keys, c->keys_sorted, c->vals, c->vals_sorted, n, 0,
-                                            3 * c->bits + 1, w->stream));
-    ranges_kernel<<<blocks, 256, 0, w->stream>>>(c->keys_sorted, c->vals_sorted, w->center_r, n, sentinel, c->cell_start,
-                                                 c->sorted_center_r, c->counters);
-    timer_end(w, &t);
+    if (!c->use_cub) {
+        // signature of everything the captured launches depend on
+        uint64_t sig[8] = {(uint64_t)(uintptr_t)w->center_r, (uint64_t)(uintptr_t)w->flags, (uint64_t)(uintptr_t)c->keys,
+                           (uint64_t)(uintptr_t)c->cell_count, (uint64_t)(uintptr_t)c->ckeys ^ (uint64_t)(uintptr_t)c->tmp_ids,
+                           ((uint64_t)n << 8) | (uint64_t)c->bits, 0, 0};
+        memcpy(&sig[6], &c->inv_cell, 4);
+        memcpy((char*)&sig[6] + 4, &c->rmax_grid, 4);
+        memcpy(&sig[7], &c->origin[0], 8);
+        uint32_t oz = 0;
+        memcpy(&oz, &c->origin[2], 4);
+        sig[7] ^= (uint64_t)oz << 13;
+        if (!c->bp_graph || memcmp(sig, c->bp_sig, sizeof(sig)) != 0) {
+            if (c->bp_graph) cudaGraphExecDestroy(c->bp_graph);
+            c->bp_graph = nullptr;
+            cudaGraph_t graph = nullptr;
+            TR_CUDA(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = launch_fast_broad(w, w->stream);
+            cudaError_t e = cudaStreamEndCapture(w->stream, &graph);
+            if (rc != TR_OK) return rc;
+            if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+            e = cudaGraphInstantiate(&c->bp_graph, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+            memcpy(c->bp_sig, sig, sizeof(sig));
+        }
+        timer_begin(w, T_BROAD, &t);
+        TR_CUDA(cudaGraphLaunch(c->bp_graph, w->stream));
+        timer_end(w, &t);
+        w->stats.kernel_launches += 5;
+    } else {
+        GridParams g{c->origin[0], c->origin[1], c->origin[2], c->inv_cell, c->rmax_grid, c->bits};
+        timer_begin(w, T_BROAD, &t);
+        TR_CUDA(cudaMemsetAsync(c->counters, 0, C_NCOUNTERS * sizeof(uint32_t), w->stream));
+        keys_kernel<false><<<blocks, 256, 0, w->stream>>>(w->center_r, w->flags, n, g, c->keys, c->vals, c->klass, c->side_list,
+                                                          c->cell_count, c->counters);
+        size_t tmp = c->cub_tmp_bytes;
+        TR_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, c->keys, c->keys_sorted, c->vals, c->vals_sorted, n, 0,
+                                                3 * c->bits + 1, w->stream));
+        dense_start_kernel<<<(ncell + 1 + 255) / 256, 256, 0, w->stream>>>(c->keys_sorted, n, ncell, c->cell_start, c->counters);
+        gather_kernel<<<blocks, 256, 0, w->stream>>>(c->vals_sorted, w->center_r, c->counters, c->sorted_center_r);
+        timer_end(w, &t);
+        w->stats.kernel_launches += 3;
+    }
     TR_CUDA(cudaGetLastError());
-    w->stats.kernel_launches += 2;   // keys + ranges (CUB's sort passes are library kernels, not counted)
     return TR_OK;
 }
 
 static int read_counters(tr_world* w) {
     Collide* c = state(w);
-    TR_CUDA(cudaMemcpyAsync(c->h_counters, c->counters, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+    TR_CUDA(cudaMemcpyAsync(c->h_counters, c->counters, C_NCOUNTERS * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
     TR_CUDA(cudaStreamSynchronize(w->stream));
     return TR_OK;
 }
 
-// Detection: broad phase + narrow phase + side list.  On return the UNSORTED pairs are in
-// ckeys and *count is their number (may exceed cap_contacts => overflow).
+static int launch_side(tr_world* w, unsigned long long* out, uint64_t cap, unsigned long long* counter) {
+    Collide* c = state(w);
+    dim3 grid((uint32_t)((w->n + 255) / 256), 64);
+    side_kernel<<<grid, 256, 0, w->stream>>>(c->side_list, c->counters, w->center_r, w->half_ext, w->flags, c->klass,
+                                             (uint32_t)w->n, out, cap, counter);
+    TR_CUDA(cudaGetLastError());
+    w->stats.kernel_launches += 1;
+    return TR_OK;
+}
+
+// Detection: broad phase + narrow phase + side list, ONE host read-back at the end.  On return
+// the UNSORTED pairs are in `out` and *count is their number (may exceed cap => overflow).
 template <bool CANDIDATES>
 static int detect(tr_world* w, unsigned long long* out, uint64_t cap, uint64_t* count) {
     Collide* c = state(w);
-    TR_TRY(broad_phase(w));
-    TR_TRY(read_counters(w));
-    const uint32_t side = c->h_counters[0];
-    const uint32_t m = c->h_counters[1];
-    c->last_side = side;
-    c->last_grid = m;
-    unsigned long long* counter = (unsigned long long*)(c->counters + (CANDIDATES ? 4 : 2));
-    PendingTimer t;
-    timer_begin(w, T_NARROW, &t);
-    if (m) {
-        narrow_kernel<CANDIDATES><<<(m + 127) / 128, 128, 0, w->stream>>>(c->keys_sorted, c->vals_sorted, c->sorted_center_r,
-                                                                          c->cell_start, m, c->bits, out, cap, counter);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        TR_TRY(broad_phase(w));
+        unsigned long long* counter = (unsigned long long*)(c->counters + (CANDIDATES ? C_CAND : C_CONTACTS));
+        PendingTimer t;
+        timer_begin(w, T_NARROW, &t);
+        const uint32_t nb = (uint32_t)((w->n + 127) / 128);
+        narrow_kernel<CANDIDATES><<<nb, 128, 0, w->stream>>>(c->keys_sorted, c->vals_sorted, c->sorted_center_r, c->cell_start,
+                                                             c->counters, c->bits, !c->use_cub, out, cap, counter);
         w->stats.kernel_launches += 1;
+        const bool side_launched = c->may_have_side && !CANDIDATES;
+        if (side_launched) TR_TRY(launch_side(w, out, cap, counter));
+        timer_end(w, &t);
+        TR_CUDA(cudaGetLastError());
+        TR_TRY(read_counters(w));
+        if (!c->use_cub && c->h_counters[C_MAXOCC] > OCC_LIMIT) {
+            // a cell holds more bodies than the quadratic rank step accepts: redo this step (and
+            // all later ones) through the radix-sort fallback
+            c->use_cub = true;
+            continue;
+        }
+        if (!CANDIDATES && !side_launched && c->h_counters[C_SIDE] > 0) {
+            // bodies left the grid domain at run time: test them now (rare path, one more read-back)
+            c->may_have_side = true;
+            TR_TRY(launch_side(w, out, cap, counter));
+            TR_TRY(read_counters(w));
+        }
+        break;
     }
-    if (side && !CANDIDATES) {
-        dim3 grid((uint32_t)((w->n + 255) / 256), side < 64 ? side : 64);
-        side_kernel<<<grid, 256, 0, w->stream>>>(c->side_list, side, w->center_r, w->half_ext, w->flags, c->klass,
-                                                 (uint32_t)w->n, out, cap, counter);
-        w->stats.kernel_launches += 1;
-    }
-    timer_end(w, &t);
-    TR_CUDA(cudaGetLastError());
-    TR_TRY(read_counters(w));
-    *count = ((uint64_t)c->h_counters[CANDIDATES ? 5 : 3] << 32) | c->h_counters[CANDIDATES ? 4 : 2];
+    c->last_side = c->h_counters[C_SIDE];
+    c->last_grid = c->h_counters[C_GRID];
+    const int k = CANDIDATES ? C_CAND : C_CONTACTS;
+    *count = ((uint64_t)c->h_counters[k + 1] << 32) | c->h_counters[k];
     return TR_OK;
+}
+
+void collide_poll_stats(tr_world* w) {
+    Collide* c = w->col;
+    if (c && c->rounds_pending) {
+        w->stats.last_response_rounds = *c->h_rounds;
+        c->rounds_pending = false;
+    }
 }
 
 int collide_step(tr_world* w, bool /*emit_candidates*/) {
@@ -621,6 +899,7 @@ int collide_step(tr_world* w, bool /*emit_candidates*/) {
                   (unsigned long long)count, (unsigned long long)c->cap_contacts);
         return TR_ERR_CAPACITY;
     }
+    c->rounds_pending = false;
     w->stats.last_response_rounds = 0;
     if (count == 0) return TR_OK;
     const uint32_t cn = (uint32_t)count;
@@ -645,8 +924,7 @@ int collide_step(tr_world* w, bool /*emit_candidates*/) {
         int per_sm = 0;
         TR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, response_kernel, 256, 0));
         if (per_sm < 1) per_sm = 1;
-        if (per_sm > 2) per_sm = 2;
-        c->coop_blocks = per_sm * w->num_sms;
+        c->coop_blocks = w->num_sms;   // one CTA per SM: the grid barrier cost grows with the CTA count
     }
     RespArgs ra{w->pos_m[w->cur], w->vel_rest, w->center_r, w->half_ext, w->flags};
     const unsigned long long* ck = c->ckeys;
@@ -664,9 +942,9 @@ int collide_step(tr_world* w, bool /*emit_candidates*/) {
     timer_end(w, &t);
     w->stats.kernel_launches += 4;   // colkeys, colpos, deps, response
     c->last_contacts = count;
-    // rounds are read lazily with the next counter read-back; fetch now (cheap, one sync per step already paid)
-    TR_TRY(read_counters(w));
-    w->stats.last_response_rounds = c->h_counters[11];
+    // wavefront count: copied to pinned memory asynchronously, picked up at the next sync (no extra stall)
+    TR_CUDA(cudaMemcpyAsync(c->h_rounds, c->counters + C_ROUNDS, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+    c->rounds_pending = true;
     return TR_OK;
 }
 
@@ -695,9 +973,16 @@ int collide_debug_grid(tr_world* w, uint32_t* keys, uint32_t* sorted_ids, uint64
     if (!w->classified) TR_TRY(collide_classify(w));
     TR_TRY(ensure_buffers(w));
     Collide* c = state(w);
-    TR_TRY(broad_phase(w));
-    TR_TRY(read_counters(w));
-    const uint32_t gm = c->h_counters[1];
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        TR_TRY(broad_phase(w));
+        TR_TRY(read_counters(w));
+        if (!c->use_cub && c->h_counters[C_MAXOCC] > OCC_LIMIT) {
+            c->use_cub = true;
+            continue;
+        }
+        break;
+    }
+    const uint32_t gm = c->h_counters[C_GRID];
     if (m) *m = gm;
     if (cell) *cell = c->cell;
     if (inv_cell) *inv_cell = c->inv_cell;
@@ -749,14 +1034,17 @@ int collide_debug_candidates(tr_world* w, int32_t* pairs, uint64_t cap, uint64_t
 int collide_free(tr_world* w) {
     Collide* c = w->col;
     if (!c) return TR_OK;
-    cudaFree(c->keys); cudaFree(c->keys_sorted); cudaFree(c->vals); cudaFree(c->vals_sorted);
-    cudaFree(c->sorted_center_r); cudaFree(c->cell_start); cudaFree(c->side_list); cudaFree(c->klass);
+    cudaFree(c->keys); cudaFree(c->keys_sorted); cudaFree(c->vals); cudaFree(c->vals_sorted); cudaFree(c->tmp_ids);
+    cudaFree(c->sorted_center_r); cudaFree(c->cell_start); cudaFree(c->cell_count); cudaFree(c->tile_sum);
+    cudaFree(c->side_list); cudaFree(c->klass);
     cudaFree(c->row_start); cudaFree(c->col_last); cudaFree(c->counters);
     if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->h_rounds) cudaFreeHost(c->h_rounds);
     cudaFree(c->ckeys); cudaFree(c->ckeys_alt); cudaFree(c->colkeys); cudaFree(c->colkeys_alt);
     cudaFree(c->colc); cudaFree(c->colc_alt); cudaFree(c->col_pos); cudaFree(c->dep);
     cudaFree(c->succ_i); cudaFree(c->succ_j); cudaFree(c->frontier[0]); cudaFree(c->frontier[1]);
     cudaFree(c->cub_tmp);
+    if (c->bp_graph) cudaGraphExecDestroy(c->bp_graph);
     delete c;
     w->col = nullptr;
     return TR_OK;

@@ -33,7 +33,7 @@ enum : uint8_t {
     F_STATIONARY = 1,  // object::stationary      reference src/main.cpp:98
     F_STATIC = 2,      // collider::isStatic      reference src/main.cpp:84
     F_SPHERE = 4,      // collider::isSphere      reference src/main.cpp:83
-    F_GRID = 8         // lives in the uniform grid this step (else: side list)
+    F_LIVE = 8         // !(mass <= 0): can take part in collisions (reference src/main.cpp:696)
 };
 
 // ---- gravity tiling constants (see DESIGN.md "K1") -------------------------------------
@@ -152,6 +152,7 @@ int collide_debug_grid(tr_world* w, uint32_t* keys, uint32_t* sorted_ids, uint64
                        int32_t* bits);
 int collide_debug_candidates(tr_world* w, int32_t* pairs, uint64_t cap, uint64_t* n);
 int collide_classify(tr_world* w);
+void collide_poll_stats(tr_world* w);
 
 // nccl_dyn.cu
 int nccl_unique_id(void* out128);
