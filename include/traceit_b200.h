@@ -142,7 +142,11 @@ float tr_area_from_size(float size);
 int tr_step(tr_world* w, int nsteps);            /* asynchronous on the world's stream    */
 int tr_sync(tr_world* w);                        /* wait; reports deferred device errors  */
 /* Host-buffer round trip used by the C++ shim: upload bodies[0..n) (AoS), run nsteps,
- * read them back.  n must equal the world size (bodies are created on first use).      */
+ * read them back.  n must equal the world size (bodies are created on first use); on a
+ * sharded world n is this rank's owned count.  When the SAME buffer is passed on
+ * consecutive calls (the per-frame pattern) the library page-locks it in place from the
+ * second call on, until another buffer is passed or the world is destroyed: keep it
+ * allocated for that long.                                                              */
 int tr_step_host(tr_world* w, uint64_t n, tr_body_desc* bodies_inout, int nsteps);
 
 /* ---- state access: replaces direct reads/writes of w.objects[i] -------------------- */

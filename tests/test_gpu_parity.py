@@ -388,3 +388,56 @@ def test_crowded_cell_falls_back_to_radix_sort(tr, oracle):
     assert len(oc) > 1_000_000
     assert np.array_equal(contacts, oc)
     check_state(got, want, "crowded cell")
+
+
+def test_full_size_dense_1m_bit_exact(tr, oracle):
+    """Config 5 at N = 1,048,576 packed spheres (~3.1M contacts per step, ~800 response
+    wavefronts): two full steps must equal the oracle (CPU grid contact set + ordered replay of
+    the reference's impulse code) bit for bit."""
+    n = 1 << 20
+    b = scenes.cfg5_dense(n)
+    want = b.copy()
+    op = oracle.default_params(g=(0, 0, 0))
+    with tr.World(tr.default_params(g=(0, 0, 0))) as w:
+        w.add(b)
+        for _ in range(2):
+            w.step(1)
+            got = w.read_bodies()
+            contacts = w.contacts()
+            g = w.debug_grid()
+            oracle.integrate(want, op)
+            _, oc, _, nk = oracle.grid_pairs(want, np.ones(n, np.uint8), (0, 0, 0), g["inv_cell"], g["bits"],
+                                             want_candidates=False)
+            oracle.resolve_list(want, oc)
+            assert nk > 2_000_000
+            assert np.array_equal(contacts, oc)
+            check_state(got, want, "dense 1M")
+
+
+def test_legacy_default_stream(tr, oracle):
+    """tr_world_set_stream(NULL) = the legacy default stream (cannot be graph-captured)."""
+    b = scenes.random_cloud(5000, 12, spheres=True, density_l=0.6)
+    want = b.copy()
+    oracle.step(want, oracle.default_params(), 2)
+    with tr.World(tr.default_params()) as w:
+        w.set_stream(None)
+        w.add(b)
+        w.step(2)
+        got = w.read_bodies()
+    check_state(got, want, "legacy stream")
+
+
+def test_full_size_4m_sampled_forces(tr, oracle):
+    """Config 4's body count on ONE GPU: sampled targets of a 4,194,304-body gravity pass vs fp64."""
+    n = 1 << 22
+    b = scenes.cfg4_cloud(n)
+    p = tr.default_params(flags=tr.PAIR_GRAVITY, G=np.float32(1.0), g=(0, 0, 0))
+    with tr.World(p) as w:
+        w.add(b)
+        f = w.debug_gravity().astype(np.float64)
+    idx = np.random.RandomState(4).choice(n, 64, replace=False).astype(np.int32)
+    f64 = oracle.pair_gravity_f64_subset(b, 1.0, idx)
+    rel = np.linalg.norm(f[idx] - f64) / np.linalg.norm(f64)
+    print(f"4M sampled-force rel L2 vs fp64: {rel:.3e}")
+    assert rel <= FORCE_REL_L2_TOL
+    assert np.isfinite(f).all()

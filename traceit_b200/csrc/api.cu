@@ -232,13 +232,46 @@ static void set_owned_range(tr_world* w) {
     w->own_count = hi - lo;
 }
 
+// Is [host, host+bytes) the buffer this world page-locked for the per-frame host path?
+static bool is_registered(const tr_world* w, const void* host, size_t bytes) {
+    return w->reg_ptr && host == w->reg_ptr && bytes <= w->reg_bytes;
+}
+
+static void unregister_host(tr_world* w) {
+    if (w->reg_ptr) cudaHostUnregister(w->reg_ptr);
+    w->reg_ptr = nullptr;
+    w->reg_bytes = 0;
+}
+
+// tr_step_host is called once per frame with the SAME caller buffer (the shim's staging vector,
+// bench.py's array): from its second consecutive use on, that buffer is page-locked in place so
+// the transfers DMA straight from/to it and the two host-side staging copies disappear.
+static void note_host_buffer(tr_world* w, void* host, size_t bytes) {
+    if (is_registered(w, host, bytes)) return;
+    if (host == w->last_host_ptr && bytes == w->last_host_bytes && bytes >= (1u << 20)) {
+        unregister_host(w);
+        if (cudaHostRegister(host, bytes, cudaHostRegisterDefault) == cudaSuccess) {
+            w->reg_ptr = host;
+            w->reg_bytes = bytes;
+        } else {
+            cudaGetLastError();   // not fatal: keep staging through the world's own pinned buffer
+        }
+    } else if (w->reg_ptr && host != w->reg_ptr) {
+        unregister_host(w);
+    }
+    w->last_host_ptr = host;
+    w->last_host_bytes = bytes;
+}
+
 // device <- bodies[first .. first+count) given as host AoS
 static int upload_range(tr_world* w, uint64_t first, uint64_t count, const tr_body_desc* host) {
     if (count == 0) return TR_OK;
     TR_TRY(ensure_capacity(w, first + count));
     TR_TRY(ensure_staging(w, count));
-    memcpy(w->pinned, host, count * sizeof(tr_body_desc));
-    TR_CUDA(cudaMemcpyAsync(w->aos, w->pinned, count * sizeof(tr_body_desc), cudaMemcpyHostToDevice, w->stream));
+    const void* src = w->pinned;
+    if (is_registered(w, host, count * sizeof(tr_body_desc))) src = host;
+    else memcpy(w->pinned, host, count * sizeof(tr_body_desc));
+    TR_CUDA(cudaMemcpyAsync(w->aos, src, count * sizeof(tr_body_desc), cudaMemcpyHostToDevice, w->stream));
     unsigned blocks = (unsigned)((count + 255) / 256);
     unpack_kernel<<<blocks, 256, 0, w->stream>>>(w->aos, (uint32_t)first, (uint32_t)count, soa_of(w));
     TR_CUDA(cudaGetLastError());
@@ -268,9 +301,11 @@ static int download_range(tr_world* w, uint64_t first, uint64_t count, tr_body_d
     pack_kernel<<<blocks, 256, 0, w->stream>>>(w->aos, (uint32_t)first, (uint32_t)count, soa_of(w));
     TR_CUDA(cudaGetLastError());
     w->stats.kernel_launches += 1;
-    TR_CUDA(cudaMemcpyAsync(w->pinned, w->aos, count * sizeof(tr_body_desc), cudaMemcpyDeviceToHost, w->stream));
+    const bool direct = is_registered(w, host, count * sizeof(tr_body_desc));
+    TR_CUDA(cudaMemcpyAsync(direct ? (void*)host : (void*)w->pinned, w->aos, count * sizeof(tr_body_desc),
+                            cudaMemcpyDeviceToHost, w->stream));
     TR_CUDA(cudaStreamSynchronize(w->stream));
-    memcpy(host, w->pinned, count * sizeof(tr_body_desc));
+    if (!direct) memcpy(host, w->pinned, count * sizeof(tr_body_desc));
     return TR_OK;
 }
 
@@ -451,6 +486,7 @@ int tr_world_destroy(tr_world* w) {
     cudaSetDevice(w->device);
     cudaStreamSynchronize(w->stream);
     timers_collect(w);
+    unregister_host(w);
     nccl_destroy(w);
     collide_free(w);
     for (cudaEvent_t e : w->event_pool) cudaEventDestroy(e);
@@ -581,6 +617,7 @@ int tr_sync(tr_world* w) {
 int tr_step_host(tr_world* w, uint64_t n, tr_body_desc* bodies, int nsteps) {
     TR_TRY(check_world(w));
     if (!bodies && n) return TR_ERR_INVALID_ARG;
+    note_host_buffer(w, bodies, n * sizeof(tr_body_desc));
     if (w->nranks > 1) {
         // sharded: `bodies` is this rank's owned block; positions are re-gathered so that
         // every rank sees every other rank's freshly uploaded sources

@@ -772,7 +772,13 @@ static int broad_phase(tr_world* w) {
     const uint32_t blocks = (n + 255) / 256;
     const uint32_t ncell = 1u << (3 * c->bits);
     PendingTimer t;
-    if (!c->use_cub) {
+    if (!c->use_cub && w->stream == nullptr) {
+        // the legacy default stream cannot be captured: plain launches
+        timer_begin(w, T_BROAD, &t);
+        TR_TRY(launch_fast_broad(w, w->stream));
+        timer_end(w, &t);
+        w->stats.kernel_launches += 5;
+    } else if (!c->use_cub) {
         // signature of everything the captured launches depend on
         uint64_t sig[8] = {(uint64_t)(uintptr_t)w->center_r, (uint64_t)(uintptr_t)w->flags, (uint64_t)(uintptr_t)c->keys,
                            (uint64_t)(uintptr_t)c->cell_count, (uint64_t)(uintptr_t)c->ckeys ^ (uint64_t)(uintptr_t)c->tmp_ids,

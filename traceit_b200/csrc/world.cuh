@@ -112,6 +112,10 @@ struct tr_world {
     uint64_t aos_cap = 0;
     tr_body_desc* pinned = nullptr;         // pinned host staging
     uint64_t pinned_cap = 0;
+    void* reg_ptr = nullptr;                // caller buffer page-locked for tr_step_host
+    size_t reg_bytes = 0;
+    void* last_host_ptr = nullptr;
+    size_t last_host_bytes = 0;
 
     // gravity scratch
     float4* grav_partial = nullptr;         // [chunks][own_padded]
