@@ -83,3 +83,18 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"\bpyoracle\b|liboracle|oracle/|import oracle|from oracle", text):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_header_is_plain_c99_and_links(tmp_path):
+    """include/traceit_b200.h compiles as C99 and every entry point links against the .so."""
+    import subprocess
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    src = os.path.join(ROOT, "tests", "c_abi_check.c")
+    out = tmp_path / "c_abi_check.so"
+    cmd = [cc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"), src,
+           "-L", os.path.dirname(tr.lib_path()), "-ltraceit_b200", "-Wl,--no-undefined", "-Wl,--allow-shlib-undefined",
+           "-o", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    used = set(re.findall(r"\b(tr_[a-z0-9_]+)\s*\(", open(src).read()))
+    assert set(_declared_symbols()) <= used, sorted(set(_declared_symbols()) - used)
