@@ -441,3 +441,25 @@ def test_full_size_4m_sampled_forces(tr, oracle):
     print(f"4M sampled-force rel L2 vs fp64: {rel:.3e}")
     assert rel <= FORCE_REL_L2_TOL
     assert np.isfinite(f).all()
+
+
+def test_step_host_reclassifies_when_colliders_change(tr, oracle):
+    """The per-frame host path skips the grid classification unless radii / shapes / live-ness
+    changed; changing them between frames (as a UI edit of w.objects would) must take effect."""
+    b = scenes.random_cloud(3000, 31, spheres=True, density_l=0.6)
+    want = b.copy()
+    cur = b.copy()
+    op = oracle.default_params()
+    with tr.World(tr.default_params()) as w:
+        for frame in range(4):
+            if frame == 2:
+                for arr in (cur, want):
+                    arr["radius"][5] = 30.0      # becomes an oversize sphere: side list
+                    arr["isSphere"][9] = 0       # becomes a box
+                    arr["size"][9] = (2.0, 0.3, 2.0)
+                    arr["mass"][11] = 0.0        # drops out of every pair
+            w.step_host(cur, 1)
+            oracle.step(want, op, 1)
+            check_state(cur, want, f"frame {frame}")
+            assert np.array_equal(w.contacts(), oracle.contacts(want))
+        assert w.stats().side_list_size >= 2   # + bodies the reference's blow-up turned into NaN

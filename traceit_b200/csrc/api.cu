@@ -85,9 +85,24 @@ struct SoA {
     uint8_t* flags;
 };
 
+// sig (optional): order-independent 64-bit hash of the fields the host-side grid classification
+// depends on (radius, isSphere, mass<=0), so a per-frame re-upload can tell whether it must redo it
 __global__ void __launch_bounds__(256) unpack_kernel(const tr_body_desc* __restrict__ in, uint32_t first,
-                                                     uint32_t count, SoA s) {
+                                                     uint32_t count, SoA s, unsigned long long* sig) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long h = 0;
+    if (t < count && sig) {
+        const tr_body_desc& q = in[t];
+        unsigned long long x = ((unsigned long long)(first + t) << 32) ^ __float_as_uint(q.radius) ^
+                               ((q.isSphere ? 1ull : 0ull) << 62) ^ ((q.mass <= 0 ? 1ull : 0ull) << 61);
+        x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+        h = x;
+    }
+    if (sig) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xFFFFFFFFu, h, o);
+        if ((threadIdx.x & 31) == 0 && h) atomicAdd(sig, h);
+    }
     if (t >= count) return;
     const tr_body_desc b = in[t];
     uint32_t i = first + t;
@@ -263,9 +278,14 @@ static void note_host_buffer(tr_world* w, void* host, size_t bytes) {
     w->last_host_bytes = bytes;
 }
 
-// device <- bodies[first .. first+count) given as host AoS
-static int upload_range(tr_world* w, uint64_t first, uint64_t count, const tr_body_desc* host) {
+// device <- bodies[first .. first+count) given as host AoS.  sig_out: hash of the
+// classification-relevant fields of the uploaded range (see unpack_kernel).
+static int upload_range(tr_world* w, uint64_t first, uint64_t count, const tr_body_desc* host,
+                        unsigned long long* sig_out = nullptr) {
+    if (sig_out) *sig_out = 0;
     if (count == 0) return TR_OK;
+    if (sig_out && !w->d_sig) TR_CUDA(cudaMalloc(&w->d_sig, sizeof(unsigned long long)));
+    if (sig_out) TR_CUDA(cudaMemsetAsync(w->d_sig, 0, sizeof(unsigned long long), w->stream));
     TR_TRY(ensure_capacity(w, first + count));
     TR_TRY(ensure_staging(w, count));
     const void* src = w->pinned;
@@ -273,9 +293,11 @@ static int upload_range(tr_world* w, uint64_t first, uint64_t count, const tr_bo
     else memcpy(w->pinned, host, count * sizeof(tr_body_desc));
     TR_CUDA(cudaMemcpyAsync(w->aos, src, count * sizeof(tr_body_desc), cudaMemcpyHostToDevice, w->stream));
     unsigned blocks = (unsigned)((count + 255) / 256);
-    unpack_kernel<<<blocks, 256, 0, w->stream>>>(w->aos, (uint32_t)first, (uint32_t)count, soa_of(w));
+    unpack_kernel<<<blocks, 256, 0, w->stream>>>(w->aos, (uint32_t)first, (uint32_t)count, soa_of(w),
+                                                 sig_out ? w->d_sig : nullptr);
     TR_CUDA(cudaGetLastError());
     w->stats.kernel_launches += 1;
+    if (sig_out) TR_CUDA(cudaMemcpyAsync(sig_out, w->d_sig, sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream));
     // the pinned buffer is reused by the next call: wait for the copy
     TR_CUDA(cudaStreamSynchronize(w->stream));
     return TR_OK;
@@ -503,6 +525,7 @@ int tr_world_destroy(tr_world* w) {
     cudaFree(w->grav_partial);
     cudaFree(w->grav_ctrl);
     cudaFree(w->grav_force_dbg);
+    cudaFree(w->d_sig);
     if (w->own_stream && w->stream) cudaStreamDestroy(w->stream);
     delete w;
     return TR_OK;
@@ -643,8 +666,20 @@ int tr_step_host(tr_world* w, uint64_t n, tr_body_desc* bodies, int nsteps) {
                       (unsigned long long)w->n);
             return TR_ERR_INVALID_ARG;
         }
-        TR_TRY(upload_range(w, 0, n, bodies));
-        w->classified = false;
+        unsigned long long sig = 0;
+        TR_TRY(upload_range(w, 0, n, bodies, &sig));
+        if (!w->have_sig || sig != w->host_sig) {
+            // radii / shapes / live-ness changed since the last frame: refresh the host copy the
+            // grid classification reads, and redo it (otherwise the per-frame path skips it)
+            for (uint64_t i = 0; i < n; ++i) {
+                w->host_bodies[i].radius = bodies[i].radius;
+                w->host_bodies[i].isSphere = bodies[i].isSphere;
+                w->host_bodies[i].mass = bodies[i].mass;
+            }
+            w->classified = false;
+            w->host_sig = sig;
+            w->have_sig = true;
+        }
     }
     TR_TRY(tr_step(w, nsteps));
     TR_TRY(download_range(w, 0, n, bodies));

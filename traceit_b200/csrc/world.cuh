@@ -112,6 +112,9 @@ struct tr_world {
     uint64_t aos_cap = 0;
     tr_body_desc* pinned = nullptr;         // pinned host staging
     uint64_t pinned_cap = 0;
+    unsigned long long* d_sig = nullptr;    // classification hash of the last per-frame upload
+    unsigned long long host_sig = 0;
+    bool have_sig = false;
     void* reg_ptr = nullptr;                // caller buffer page-locked for tr_step_host
     size_t reg_bytes = 0;
     void* last_host_ptr = nullptr;
