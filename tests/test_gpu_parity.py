@@ -463,3 +463,52 @@ def test_step_host_reclassifies_when_colliders_change(tr, oracle):
             check_state(cur, want, f"frame {frame}")
             assert np.array_equal(w.contacts(), oracle.contacts(want))
         assert w.stats().side_list_size >= 2   # + bodies the reference's blow-up turned into NaN
+
+
+def test_bodies_added_between_steps_and_external_forces(tr, oracle):
+    """World growth (push_back between frames), tr_set_force (obj.force = ...) and
+    tr_write_bodies (direct edits of w.objects[i]) against the oracle doing the same."""
+    a = scenes.random_cloud(1500, 41, spheres=True, density_l=0.6)
+    extra = scenes.random_cloud(700, 42, spheres=True, density_l=0.5)
+    op = oracle.default_params()
+    with tr.World(tr.default_params()) as w:
+        first = w.add(a)
+        assert first == 0
+        w.step(2)
+        want = a.copy()
+        oracle.step(want, op, 2)
+        # grow the world past its initial capacity
+        assert w.add(extra) == 1500
+        want = np.concatenate([want, extra])
+        w.set_force(3, (50.0, -20.0, 5.0))
+        want["force"][3] = (50.0, -20.0, 5.0)
+        w.step(2)
+        oracle.step(want, op, 2)
+        got = w.read_bodies()
+        check_state(got, want, "after growth")
+        assert np.array_equal(w.contacts(), oracle.contacts(want))
+        # edit a few bodies in place
+        edit = got[100:110].copy()
+        edit["vel"] = (1.0, 2.0, 3.0)
+        edit["radius"] = 0.9
+        w.write_bodies(edit, first=100)
+        want[100:110] = edit
+        w.step(1)
+        oracle.step(want, op, 1)
+        check_state(w.read_bodies(), want, "after edit")
+        assert len(w) == 2200
+
+
+def test_degenerate_radii_and_infinite_positions(tr, oracle):
+    b = scenes.random_cloud(2000, 43, spheres=True, density_l=0.6)
+    b["radius"][::9] = 0.0
+    b["radius"][4] = -0.5          # (ra+rb)^2 is still a valid square in the reference predicate
+    b["radius"][5] = np.inf
+    b["pos"][6] = (np.inf, 0, 0)
+    b["pos"][7] = (-np.inf, np.inf, 1e30)
+    b["center"] = b["pos"]
+    want = b.copy()
+    oracle.step(want, oracle.default_params(), 2)
+    got, contacts, _ = gpu_run(tr, b, 2)
+    check_state(got, want, "degenerate")
+    assert np.array_equal(contacts, oracle.contacts(want))
