@@ -155,6 +155,14 @@ int tr_read_bodies(tr_world* w, uint64_t first, uint64_t count, tr_body_desc* ou
 int tr_write_bodies(tr_world* w, uint64_t first, uint64_t count, const tr_body_desc* in);
 int tr_set_force(tr_world* w, uint32_t id, float fx, float fy, float fz); /* obj.force = */
 
+/* ---- trajectory history: replaces object::trajectory (src/main.cpp:101-103,793-808) ------- */
+/* Keep the last max_points post-integration positions of every non-stationary body in a
+ * device ring (the reference keeps maxTrajectoryPoints = 300 and pushes obj.pos right after
+ * integration, before the collision nudges).  0 disables and frees the ring.  Costs
+ * 12*max_points bytes per body.  tr_read_trajectory returns the points oldest first.      */
+int tr_world_enable_trajectory(tr_world* w, uint32_t max_points);
+int tr_read_trajectory(tr_world* w, uint32_t id, float* xyz, uint64_t cap_points, uint64_t* n_points);
+
 /* ---- parity / observability --------------------------------------------------------- */
 /* Contact set of the last step in lexicographic (i,j) order, i<j: the pairs for which
  * the reference's guards + predicate (src/main.cpp:695-707) hold.  pairs may be NULL.  */

@@ -37,6 +37,8 @@ int use_every_entry_point(void) {
     (void)tr_read_bodies(w, 0, 1, &b);
     (void)tr_write_bodies(w, 0, 1, &b);
     (void)tr_set_force(w, 0, 0.f, 0.f, 0.f);
+    (void)tr_world_enable_trajectory(w, 300);
+    (void)tr_read_trajectory(w, 0, v, 1, &n);
     (void)tr_read_contacts(w, pairs, 1, &n);
     (void)tr_debug_grid(w, keys, ids, &n, &cell, &inv, &bits);
     (void)tr_debug_candidates(w, pairs, 1, &n);

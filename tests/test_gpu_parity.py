@@ -512,3 +512,37 @@ def test_degenerate_radii_and_infinite_positions(tr, oracle):
     got, contacts, _ = gpu_run(tr, b, 2)
     check_state(got, want, "degenerate")
     assert np.array_equal(contacts, oracle.contacts(want))
+
+
+def test_trajectory_ring_matches_reference_history(tr, oracle):
+    """object::trajectory (src/main.cpp:793-808): the last maxTrajectoryPoints post-integration
+    positions of every non-stationary body, kept on the device across steps, ring wrap included,
+    surviving a capacity growth."""
+    b = scenes.random_cloud(1200, 51, spheres=True, density_l=0.6)
+    b["stationary"][3] = 1
+    extra = scenes.random_cloud(600, 52, spheres=True, density_l=0.5)
+    op = oracle.default_params()
+    hist = {i: [] for i in (0, 3, 7, 1199, 1300)}
+    want = b.copy()
+    with tr.World(tr.default_params()) as w:
+        w.enable_trajectory(5)
+        w.add(b)
+        assert len(w.trajectory(0)) == 0
+        for s in range(12):
+            if s == 6:
+                w.add(extra)                       # grows past the initial capacity of 1024 -> 2048
+                want = np.concatenate([want, extra])
+            w.step(1)
+            oracle.step(want, op, 1)
+            for i in hist:
+                if i < len(want) and not want["stationary"][i]:
+                    hist[i].append(want["center"][i].copy())   # pos right after integration
+        for i, pts in hist.items():
+            got = w.trajectory(i)
+            exp = np.array(pts[-5:], dtype=np.float32).reshape(-1, 3)
+            assert got.shape == exp.shape, (i, got.shape, exp.shape)
+            assert_bits_equal(got, exp, f"trajectory of body {i}")
+        assert len(w.trajectory(3)) == 0 and len(w.trajectory(1300)) == 5
+        w.enable_trajectory(0)
+        with pytest.raises(tr.TraceItError):
+            w.trajectory(0)

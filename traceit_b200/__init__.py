@@ -81,7 +81,7 @@ ABI_SYMBOLS = [
     "tr_world_owned_range", "tr_to_spherical", "tr_area_from_size", "tr_step", "tr_sync", "tr_step_host",
     "tr_read_state", "tr_read_bodies", "tr_write_bodies", "tr_set_force", "tr_read_contacts", "tr_debug_grid",
     "tr_debug_candidates", "tr_debug_gravity", "tr_get_stats", "tr_reset_stats", "tr_enable_timing",
-    "tr_measure_fma_peak",
+    "tr_measure_fma_peak", "tr_world_enable_trajectory", "tr_read_trajectory",
 ]
 
 
@@ -133,6 +133,8 @@ def lib():
         L.tr_read_bodies.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
         L.tr_write_bodies.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
         L.tr_set_force.argtypes = [vp, C.c_uint32, C.c_float, C.c_float, C.c_float]
+        L.tr_world_enable_trajectory.argtypes = [vp, C.c_uint32]
+        L.tr_read_trajectory.argtypes = [vp, C.c_uint32, vp, C.c_uint64, u64p]
         L.tr_read_contacts.argtypes = [vp, vp, C.c_uint64, u64p]
         L.tr_debug_grid.argtypes = [vp, vp, vp, u64p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32)]
         L.tr_debug_candidates.argtypes = [vp, vp, C.c_uint64, u64p]
@@ -303,6 +305,18 @@ class World:
 
     def set_force(self, idx: int, f) -> None:
         _check(self._L.tr_set_force(self._h, idx, float(f[0]), float(f[1]), float(f[2])))
+
+    # -- trajectory history (object::trajectory)
+    def enable_trajectory(self, max_points: int = 300) -> None:
+        _check(self._L.tr_world_enable_trajectory(self._h, max_points))
+
+    def trajectory(self, idx: int) -> np.ndarray:
+        n = C.c_uint64(0)
+        _check(self._L.tr_read_trajectory(self._h, idx, None, 0, C.byref(n)))
+        out = np.empty((n.value, 3), dtype=np.float32)
+        if n.value:
+            _check(self._L.tr_read_trajectory(self._h, idx, _ptr(out), n.value, C.byref(n)))
+        return out
 
     # -- parity / observability
     def contacts(self) -> np.ndarray:

@@ -173,6 +173,59 @@ __global__ void __launch_bounds__(256) refresh_remote_centers(const float4* __re
     center_r[i] = make_float4(p.x, p.y, p.z, c.w);
 }
 
+// trajectory.push_back(obj.pos) of main.cpp:794 for the bodies this rank integrates: the
+// post-integration position is the refreshed collider centre
+__global__ void __launch_bounds__(256) traj_record_kernel(const float4* __restrict__ center_r, const uint8_t* __restrict__ flags,
+                                                          uint32_t first, uint32_t count, float* traj, uint32_t* traj_cnt,
+                                                          uint32_t max_points, uint64_t stride) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const uint32_t i = first + t;
+    if (flags[i] & F_STATIONARY) return;
+    const float4 c = center_r[i];
+    const uint32_t k = traj_cnt[i];
+    const uint64_t slot = k % max_points;
+    traj[(slot * 3 + 0) * stride + i] = c.x;
+    traj[(slot * 3 + 1) * stride + i] = c.y;
+    traj[(slot * 3 + 2) * stride + i] = c.z;
+    traj_cnt[i] = k + 1;
+}
+
+// (re)allocate the ring for the current capacity, carrying recorded points over
+static int ensure_traj(tr_world* w) {
+    if (w->traj_max == 0 || w->cap == 0 || (w->traj && w->traj_stride == w->cap)) return TR_OK;
+    float* nt = nullptr;
+    uint32_t* nc = nullptr;
+    const uint64_t rows = 3ull * w->traj_max;
+    TR_CUDA(cudaMalloc(&nt, rows * w->cap * sizeof(float)));
+    TR_CUDA(cudaMalloc(&nc, w->cap * sizeof(uint32_t)));
+    TR_CUDA(cudaMemsetAsync(nc, 0, w->cap * sizeof(uint32_t), w->stream));
+    if (w->traj && w->n) {
+        uint64_t keep = w->n < w->traj_stride ? w->n : w->traj_stride;
+        TR_CUDA(cudaMemcpy2DAsync(nt, w->cap * sizeof(float), w->traj, w->traj_stride * sizeof(float), keep * sizeof(float), rows,
+                                  cudaMemcpyDeviceToDevice, w->stream));
+        TR_CUDA(cudaMemcpyAsync(nc, w->traj_cnt, keep * sizeof(uint32_t), cudaMemcpyDeviceToDevice, w->stream));
+    }
+    TR_CUDA(cudaStreamSynchronize(w->stream));
+    cudaFree(w->traj);
+    cudaFree(w->traj_cnt);
+    w->traj = nt;
+    w->traj_cnt = nc;
+    w->traj_stride = w->cap;
+    return TR_OK;
+}
+
+static int record_trajectory(tr_world* w) {
+    if (w->traj_max == 0 || w->own_count == 0) return TR_OK;
+    TR_TRY(ensure_traj(w));
+    unsigned blocks = (unsigned)((w->own_count + 255) / 256);
+    traj_record_kernel<<<blocks, 256, 0, w->stream>>>(w->center_r, w->flags, (uint32_t)w->own_first, (uint32_t)w->own_count,
+                                                      w->traj, w->traj_cnt, w->traj_max, w->traj_stride);
+    TR_CUDA(cudaGetLastError());
+    w->stats.kernel_launches += 1;
+    return TR_OK;
+}
+
 static SoA soa_of(tr_world* w) {
     SoA s;
     s.pos_m = w->pos_m[w->cur];
@@ -428,6 +481,7 @@ static int step_once(tr_world* w) {
         TR_TRY(integrate_only(w, c));
         if (w->nranks > 1) TR_TRY(nccl_allgather_pos(w, w->pos_m[w->cur]));
     }
+    TR_TRY(record_trajectory(w));
     if (coll && w->nranks > 1) {
         // Sharded collisions: the collision pipeline is cheap next to
         // gravity (~140 B/body vs N interactions/body), so it is REPLICATED: gather the freshly
@@ -526,6 +580,8 @@ int tr_world_destroy(tr_world* w) {
     cudaFree(w->grav_ctrl);
     cudaFree(w->grav_force_dbg);
     cudaFree(w->d_sig);
+    cudaFree(w->traj);
+    cudaFree(w->traj_cnt);
     if (w->own_stream && w->stream) cudaStreamDestroy(w->stream);
     delete w;
     return TR_OK;
@@ -752,6 +808,55 @@ int tr_set_force(tr_world* w, uint32_t id, float fx, float fy, float fz) {
     float4 f = make_float4(fx, fy, fz, 0.f);
     TR_CUDA(cudaMemcpyAsync(w->force + id, &f, sizeof(f), cudaMemcpyHostToDevice, w->stream));
     TR_CUDA(cudaStreamSynchronize(w->stream));
+    return TR_OK;
+}
+
+int tr_world_enable_trajectory(tr_world* w, uint32_t max_points) {
+    TR_TRY(check_world(w));
+    TR_CUDA(cudaStreamSynchronize(w->stream));
+    if (max_points != w->traj_max) {
+        cudaFree(w->traj);
+        cudaFree(w->traj_cnt);
+        w->traj = nullptr;
+        w->traj_cnt = nullptr;
+        w->traj_stride = 0;
+        w->traj_max = max_points;
+    }
+    return TR_OK;
+}
+
+int tr_read_trajectory(tr_world* w, uint32_t id, float* xyz, uint64_t cap_points, uint64_t* n_points) {
+    TR_TRY(check_world(w));
+    TR_TRY(flush_created(w));
+    if (id >= w->n) {
+        set_error("tr_read_trajectory: id %u out of range", id);
+        return TR_ERR_INVALID_ARG;
+    }
+    if (w->traj_max == 0) {
+        set_error("tr_read_trajectory: history is off (tr_world_enable_trajectory)");
+        return TR_ERR_STATE;
+    }
+    if (n_points) *n_points = 0;
+    if (!w->traj) return TR_OK;   // enabled but no step recorded yet
+    uint32_t cnt = 0;
+    TR_CUDA(cudaMemcpyAsync(&cnt, w->traj_cnt + id, sizeof(cnt), cudaMemcpyDeviceToHost, w->stream));
+    TR_CUDA(cudaStreamSynchronize(w->stream));
+    const uint32_t have = cnt < w->traj_max ? cnt : w->traj_max;
+    if (n_points) *n_points = have;
+    if (!xyz || have == 0) return TR_OK;
+    // one strided gather of the body's column: rows = slot*3+c, pitch = stride floats
+    std::vector<float> col(3ull * w->traj_max);
+    TR_CUDA(cudaMemcpy2DAsync(col.data(), sizeof(float), w->traj + id, w->traj_stride * sizeof(float), sizeof(float),
+                              3ull * w->traj_max, cudaMemcpyDeviceToHost, w->stream));
+    TR_CUDA(cudaStreamSynchronize(w->stream));
+    const uint32_t start = cnt > w->traj_max ? cnt % w->traj_max : 0;   // oldest point
+    const uint64_t take = have < cap_points ? have : cap_points;
+    for (uint64_t k = 0; k < take; ++k) {
+        const uint32_t slot = (start + (uint32_t)k) % w->traj_max;
+        xyz[3 * k + 0] = col[3ull * slot + 0];
+        xyz[3 * k + 1] = col[3ull * slot + 1];
+        xyz[3 * k + 2] = col[3ull * slot + 2];
+    }
     return TR_OK;
 }
 

@@ -120,6 +120,12 @@ struct tr_world {
     void* last_host_ptr = nullptr;
     size_t last_host_bytes = 0;
 
+    // optional trajectory ring: traj[(slot*3 + c) * traj_stride + body], traj_cnt[body] = points pushed
+    float* traj = nullptr;
+    uint32_t* traj_cnt = nullptr;
+    uint32_t traj_max = 0;
+    uint64_t traj_stride = 0;
+
     // gravity scratch
     float4* grav_partial = nullptr;         // [chunks][own_padded]
     uint64_t grav_partial_elems = 0;
