@@ -66,7 +66,11 @@ typedef struct tr_world_params {
     uint64_t max_contacts;       /* 0 = 8*N + 4096 */
     /* Largest radius admitted to the grid; 0 = automatic.              */
     float grid_max_radius;
-    uint32_t reserved[3];
+    /* Ordered collision response: 0 = dataflow (barrier-free, default), 1 = level-synchronous
+     * wavefronts (one grid barrier per wavefront).  Both replay the reference's Gauss-Seidel
+     * order exactly and give identical bits; see DESIGN.md K6.                            */
+    uint32_t response_mode;
+    uint32_t reserved[2];
 } tr_world_params;
 
 /* Body descriptor = hot fields of the reference's `object` + `collider`

@@ -149,28 +149,31 @@ def test_out_of_domain_bodies_use_side_list(tr, oracle):
 
 
 # ---------------------------------------------------------------- response order
-def test_dense_lattice_response_bit_exact(tr, oracle):
-    """Config 5 (small): ~3 contacts per body, lattice-ordered ids = long Gauss-Seidel chains."""
+@pytest.mark.parametrize("mode", [0, 1])
+def test_dense_lattice_response_bit_exact(tr, oracle, mode):
+    """Config 5 (small): ~3 contacts per body, lattice-ordered ids = long Gauss-Seidel chains.
+    mode 0 = dataflow response (default), mode 1 = level-synchronous wavefronts."""
     b = scenes.dense_lattice(20)           # 8000 bodies
     p = oracle.default_params(g=(0, 0, 0))
     want = b.copy()
     for _ in range(10):
         oracle.integrate(want, p)
         oracle.resolve_list(want, oracle.contacts(want))
-    got, contacts, st = gpu_run(tr, b, 10, g=(0, 0, 0))
+    got, contacts, st = gpu_run(tr, b, 10, g=(0, 0, 0), response_mode=mode)
     check_state(got, want, "dense lattice")
     assert np.array_equal(contacts, oracle.contacts(want))
-    assert st.last_response_rounds >= 1
+    assert (st.last_response_rounds >= 10) == (mode == 1)
 
 
-def test_shuffled_ids_response_bit_exact(tr, oracle):
+@pytest.mark.parametrize("mode", [0, 1])
+def test_shuffled_ids_response_bit_exact(tr, oracle, mode):
     b = scenes.dense_lattice(16, shuffle_ids=True)
     p = oracle.default_params(g=(0, 0, 0))
     want = b.copy()
     for _ in range(6):
         oracle.integrate(want, p)
         oracle.resolve_list(want, oracle.contacts(want))
-    got, _, _ = gpu_run(tr, b, 6, g=(0, 0, 0))
+    got, _, _ = gpu_run(tr, b, 6, g=(0, 0, 0), response_mode=mode)
     check_state(got, want, "shuffled lattice")
 
 

@@ -53,7 +53,7 @@ class Params(C.Structure):
         ("g", C.c_float * 3), ("G", C.c_float), ("dt", C.c_float), ("atm_density", C.c_float),
         ("flags", C.c_uint32), ("grid_origin", C.c_float * 3), ("grid_cell", C.c_float),
         ("grid_bits", C.c_int32), ("max_contacts", C.c_uint64), ("grid_max_radius", C.c_float),
-        ("reserved", C.c_uint32 * 3),
+        ("response_mode", C.c_uint32), ("reserved", C.c_uint32 * 2),
     ]
 
 

@@ -48,7 +48,7 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 // counters[] slots
 enum { C_SIDE = 0, C_GRID = 1, C_CONTACTS = 2 /*u64*/, C_CAND = 4 /*u64*/, C_MAXOCC = 6, C_FRONT = 8 /*3*/, C_ROUNDS = 11,
-       C_NCOUNTERS = 16 };
+       C_QHEAD = 12, C_QTAIL = 13, C_DONE = 14, C_ABORT = 15, C_NCOUNTERS = 16 };
 
 }  // namespace tr
 
@@ -82,6 +82,7 @@ struct Collide {
     uint32_t* h_counters = nullptr;  // pinned mirror (detection read-back)
     uint32_t* h_rounds = nullptr;    // pinned: response wavefront count, fetched lazily
     bool rounds_pending = false;
+    bool flow_pending = false;       // h_rounds holds the dataflow kernel's watchdog flag, not a round count
 
     // per contact
     unsigned long long* ckeys = nullptr;      // (i<<32)|j, unsorted then sorted
@@ -481,7 +482,7 @@ __global__ void __launch_bounds__(256) deps_kernel(const unsigned long long* __r
                                                    const uint32_t* __restrict__ col_last, uint32_t c_n,
                                                    uint32_t* __restrict__ dep, uint32_t* __restrict__ succ_i,
                                                    uint32_t* __restrict__ succ_j, uint32_t* __restrict__ frontier0,
-                                                   uint32_t* counters) {
+                                                   uint32_t* counters, int ready_counter) {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= c_n) return;
     unsigned long long k = ckeys[c];
@@ -497,7 +498,7 @@ __global__ void __launch_bounds__(256) deps_kernel(const unsigned long long* __r
     if (t + 1 < c_n && (uint32_t)(colkeys_sorted[t + 1] >> 32) == j) sj = colc_sorted[t + 1];
     else sj = row_start[j];
     succ_j[c] = sj;
-    if (d == 0) frontier0[atomicAdd(&counters[8], 1u)] = c;
+    if (d == 0) frontier0[atomicAdd(&counters[ready_counter], 1u)] = c;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -538,12 +539,14 @@ __device__ __forceinline__ void respond(const RespArgs& a, uint32_t i, uint32_t 
         else if (oy < oz) ny = dy > 0 ? 1.0f : -1.0f;
         else nz = dz > 0 ? 1.0f : -1.0f;
     }
-    // L2 loads: these were written by other SMs in earlier wavefronts
+    // L2 loads: these were written by other SMs in earlier wavefronts.  Positions are fetched in
+    // the same round trip (needed only when the pair is not skipped, but a second dependent trip
+    // would sit on the critical path of the ordered replay).
     float4 vi = __ldcg(a.vel_rest + i), vj = __ldcg(a.vel_rest + j);
+    float4 pi = __ldcg(a.pos_m + i), pj = __ldcg(a.pos_m + j);
     float rvx = __fsub_rn(vi.x, vj.x), rvy = __fsub_rn(vi.y, vj.y), rvz = __fsub_rn(vi.z, vj.z);
     float vn = dot3_rn(rvx, rvy, rvz, nx, ny, nz);
     if (vn > 0) return;                                  // main.cpp:714 (as written)
-    float4 pi = __ldcg(a.pos_m + i), pj = __ldcg(a.pos_m + j);
     float e = (vj.w < vi.w) ? vj.w : vi.w;               // std::min(a.rest, b.rest)
     float jimp = __fmul_rn(-__fadd_rn(1.0f, e), vn);     // -(1 + e) * vn
     float ima = __fdiv_rn(1.0f, pi.w), imb = __fdiv_rn(1.0f, pj.w);
@@ -604,6 +607,93 @@ __global__ void __launch_bounds__(256) response_kernel(RespArgs a, const unsigne
         ++round;
     }
     if (gtid == 0) counters[11] = round;
+}
+
+// Barrier-free variant of K6 ("dataflow"): the same dependency graph, but instead of one grid-wide
+// barrier per wavefront a thread that finishes a contact releases its (at most two) successors
+// and CONTINUES with one that became ready; a second one goes to a global FIFO that idle threads
+// drain.  A contact still runs only after the previous contact of both its bodies, and never
+// concurrently with another contact of the same body, so the result is the sequential sweep's,
+// bit for bit - but the critical path costs one L2 hand-off per contact (~3 us) instead of a
+// barrier round (~9 us).  Message passing: writes -> __threadfence -> atomicSub(dep) on the
+// releasing side; atomicSub returns 1 (or the queue slot fills) -> __threadfence -> L2 loads on
+// the acquiring side.  A spin budget (C_ABORT) guarantees termination even if the graph were broken.
+constexpr uint32_t FLOW_SPIN_LIMIT = 1u << 21;
+
+__global__ void __launch_bounds__(128) response_flow_kernel(RespArgs a, const unsigned long long* __restrict__ ckeys,
+                                                            uint32_t* dep, const uint32_t* __restrict__ succ_i,
+                                                            const uint32_t* __restrict__ succ_j, uint32_t* q, uint32_t c_n,
+                                                            uint32_t* counters) {
+    volatile uint32_t* vq = q;
+    volatile uint32_t* vc = counters;
+    uint32_t cur = EMPTY, slot = EMPTY, spins = 0, mine = 0;
+    bool alive = true;
+    // One lock-step iteration per warp: [lanes without work try to acquire] -> vote -> [lanes with
+    // work process one contact] -> release.  Lanes never wait inside the iteration, so the warp
+    // stays converged (a lane-divergent formulation serialises the lanes and is no faster than the
+    // barrier version); the fences execute once per warp-iteration.
+    while (true) {
+        if (alive && cur == EMPTY) {
+            if (mine) {                           // publish finished work only when a chain ends:
+                atomicAdd(&counters[C_DONE], mine);   // one hot-address atomic per chain, not per contact
+                mine = 0;
+            }
+            if (slot == EMPTY) {
+                const uint32_t h = atomicAdd(&counters[C_QHEAD], 1u);
+                if (h >= c_n) alive = false;      // every slot that can ever fill is already claimed
+                else slot = h;
+            }
+            if (alive) {
+                const uint32_t c = vq[slot];
+                if (c != EMPTY) {
+                    cur = c;
+                    slot = EMPTY;
+                    spins = 0;
+                } else if ((++spins & 15u) == 0 && (vc[C_DONE] >= c_n || vc[C_ABORT])) {
+                    alive = false;                // termination is polled every 16th idle iteration
+                } else if (spins > FLOW_SPIN_LIMIT) {
+                    atomicExch(&counters[C_ABORT], 1u);
+                    alive = false;
+                }
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, alive)) break;   // the warp leaves together (and reconverges here)
+        // (no acquire fence: everything another thread may have written is read with ld.cg / atomics
+        //  issued after the queue slot or the dependency counter was observed)
+        uint32_t s1 = EMPTY, s2 = EMPTY;
+        if (cur != EMPTY) {
+            s1 = succ_i[cur];
+            s2 = succ_j[cur];
+            // the successors' records are needed one iteration from now: start pulling them into L2
+            if (s1 != EMPTY) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ckeys + s1));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(succ_i + s1));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(succ_j + s1));
+            }
+            if (s2 != EMPTY) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ckeys + s2));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(succ_i + s2));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(succ_j + s2));
+            }
+            const unsigned long long k = ckeys[cur];
+            respond(a, (uint32_t)(k >> 32), (uint32_t)k);
+        }
+        __threadfence();                          // release: impulses/nudges are visible before the hand-off
+        if (cur != EMPTY) {
+            // both releases are issued back to back; mutable state is only ever read with L2 loads
+            // (ld.cg) issued after these atomics return
+            const uint32_t r1 = (s1 != EMPTY) ? atomicSub(&dep[s1], 1u) : 0u;
+            const uint32_t r2 = (s2 != EMPTY) ? atomicSub(&dep[s2], 1u) : 0u;
+            ++mine;
+            uint32_t next = EMPTY;
+            if (r1 == 1u) next = s1;
+            if (r2 == 1u) {
+                if (next == EMPTY) next = s2;
+                else vq[atomicAdd(&counters[C_QTAIL], 1u)] = s2;
+            }
+            cur = next;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -885,7 +975,16 @@ static int detect(tr_world* w, unsigned long long* out, uint64_t cap, uint64_t* 
 void collide_poll_stats(tr_world* w) {
     Collide* c = w->col;
     if (c && c->rounds_pending) {
-        w->stats.last_response_rounds = *c->h_rounds;
+        if (c->flow_pending) {
+            w->stats.last_response_rounds = 0;    // no rounds in dataflow mode
+            if (*c->h_rounds != 0 && w->deferred_error == TR_OK) {
+                w->deferred_error = TR_ERR_CUDA;
+                w->deferred_msg = "ordered response: dataflow watchdog fired (dependency graph did not drain)";
+            }
+            c->flow_pending = false;
+        } else {
+            w->stats.last_response_rounds = *c->h_rounds;
+        }
         c->rounds_pending = false;
     }
 }
@@ -924,8 +1023,28 @@ int collide_step(tr_world* w, bool /*emit_candidates*/) {
     TR_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, c->colkeys, c->colkeys_alt, c->colc, c->colc_alt, cn, 0,
                                             32 + idbits, w->stream));
     colpos_kernel<<<cblocks, 256, 0, w->stream>>>(c->colkeys_alt, c->colc_alt, cn, c->col_pos, c->col_last);
+    const bool flow = w->params.response_mode != 1;   // 1 selects the level-synchronous kernel
+    if (flow) TR_CUDA(cudaMemsetAsync(c->frontier[0], 0xFF, (size_t)cn * sizeof(uint32_t), w->stream));   // queue = all EMPTY
     deps_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, c->colkeys_alt, c->colc_alt, c->col_pos, c->row_start, c->col_last,
-                                                cn, c->dep, c->succ_i, c->succ_j, c->frontier[0], c->counters);
+                                                cn, c->dep, c->succ_i, c->succ_j, c->frontier[0], c->counters,
+                                                flow ? C_QTAIL : C_FRONT);
+    if (flow) {
+        RespArgs ra{w->pos_m[w->cur], w->vel_rest, w->center_r, w->half_ext, w->flags};
+        int fblocks = w->num_sms;                     // resident by construction: 128 threads per SM
+        int fwant = (int)((cn + 127) / 128);
+        if (fwant < fblocks) fblocks = fwant < 1 ? 1 : fwant;
+        response_flow_kernel<<<fblocks, 128, 0, w->stream>>>(ra, c->ckeys, c->dep, c->succ_i, c->succ_j, c->frontier[0], cn,
+                                                             c->counters);
+        TR_CUDA(cudaGetLastError());
+        timer_end(w, &t);
+        w->stats.kernel_launches += 4;
+        c->last_contacts = count;
+        // watchdog flag + (unused) round counter come back with the next sync
+        TR_CUDA(cudaMemcpyAsync(c->h_rounds, c->counters + C_ABORT, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+        c->rounds_pending = true;
+        c->flow_pending = true;
+        return TR_OK;
+    }
     if (c->coop_blocks == 0) {
         int per_sm = 0;
         TR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, response_kernel, 256, 0));
