@@ -156,11 +156,6 @@ __global__ void __launch_bounds__(256) read_state_kernel(const float4* __restric
     }
 }
 
-__global__ void copy_pos_kernel(const float4* __restrict__ a, float4* __restrict__ b, uint32_t n) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) b[t] = a[t];
-}
-
 // sharded collisions: collider centres of bodies integrated by OTHER ranks
 __global__ void __launch_bounds__(256) refresh_remote_centers(const float4* __restrict__ pos_m, float4* center_r,
                                                               const uint8_t* __restrict__ flags, uint32_t n,
@@ -495,7 +490,7 @@ static int step_once(tr_world* w) {
         TR_CUDA(cudaGetLastError());
         w->stats.kernel_launches += 1;
     }
-    if (coll) TR_TRY(collide_step(w, false));
+    if (coll) TR_TRY(collide_step(w));
     w->stats.steps += 1;
     return TR_OK;
 }
@@ -578,7 +573,6 @@ int tr_world_destroy(tr_world* w) {
     if (w->pinned) cudaFreeHost(w->pinned);
     cudaFree(w->grav_partial);
     cudaFree(w->grav_ctrl);
-    cudaFree(w->grav_force_dbg);
     cudaFree(w->d_sig);
     cudaFree(w->traj);
     cudaFree(w->traj_cnt);

@@ -989,7 +989,7 @@ void collide_poll_stats(tr_world* w) {
     }
 }
 
-int collide_step(tr_world* w, bool /*emit_candidates*/) {
+int collide_step(tr_world* w) {
     if (w->n == 0) return TR_OK;
     if (!w->classified) TR_TRY(collide_classify(w));
     TR_TRY(ensure_buffers(w));

@@ -75,8 +75,6 @@ struct PendingTimer {
     int cat;
 };
 
-struct NcclApi;  // nccl_dyn.cu
-
 }  // namespace tr
 
 // The opaque world.  Device buffers are plain SoA fp32 arrays sized to `cap` bodies.
@@ -131,7 +129,6 @@ struct tr_world {
     uint64_t grav_partial_elems = 0;
     uint32_t* grav_ctrl = nullptr;          // [0]=work counter, [1..]=per-tile arrival counters
     uint64_t grav_ctrl_elems = 0;
-    float4* grav_force_dbg = nullptr;
 
     // collision scratch (collide.cu)
     struct Collide* col = nullptr;
@@ -158,7 +155,7 @@ int integrate_only(tr_world* w, const StepConsts& c);
 int measure_fma_peak(int device, double* lane_ops_per_s, double* sm_clock_mhz);
 
 // collide.cu
-int collide_step(tr_world* w, bool emit_candidates);
+int collide_step(tr_world* w);
 int collide_free(tr_world* w);
 int collide_read_contacts(tr_world* w, int32_t* pairs, uint64_t cap, uint64_t* n);
 int collide_debug_grid(tr_world* w, uint32_t* keys, uint32_t* sorted_ids, uint64_t* m, float* cell, float* inv_cell,
