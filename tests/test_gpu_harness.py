@@ -31,3 +31,16 @@ def test_headless_harness_cloud_with_gravity(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     assert "bodies 20000 steps 5 hash 0x" in r.stdout
     assert not (tmp_path / "Координаты.txt").exists()
+
+
+def test_shim_on_the_reference_own_types_equals_reference(tmp_path):
+    """oracle/_ref/shim_vs_ref contains the UNMODIFIED reference TU and traceit_b200::updatePhysics
+    instantiated on the reference's own world/object structs (INTEGRATION.md's three-line change).
+    400 frames of the seeded world + projectiles + 300 sphere colliders through both: every body,
+    every trajectory point, every transform and the Координаты.txt dumps must be identical."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "shim_vs_ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/shim_vs_ref not built (needs /root/reference at build time)")
+    r = subprocess.run([exe, "400", "300", str(tmp_path)], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "SHIM_EQUALS_REFERENCE" in r.stdout and "mismatching_bodies 0" in r.stdout
