@@ -98,3 +98,18 @@ def test_header_is_plain_c99_and_links(tmp_path):
     assert r.returncode == 0, r.stderr
     used = set(re.findall(r"\b(tr_[a-z0-9_]+)\s*\(", open(src).read()))
     assert set(_declared_symbols()) <= used, sorted(set(_declared_symbols()) - used)
+
+
+def test_minimal_c_example_builds(tmp_path):
+    import subprocess
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    out = tmp_path / "minimal"
+    libdir = os.path.dirname(tr.lib_path())
+    cmd = [cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "minimal.c"),
+           "-L", libdir, "-ltraceit_b200", f"-Wl,-rpath,{libdir}", "-Wl,-rpath-link,/usr/local/cuda/lib64", "-o", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    n = C.c_int(0)
+    if tr.lib().tr_device_count(C.byref(n)) != 0 or n.value == 0:
+        run = subprocess.run([str(out)], capture_output=True, text=True)
+        assert run.returncode == 1 and "no CPU fallback" in run.stderr      # loud failure without a GPU
