@@ -98,7 +98,8 @@ typedef struct tr_stats {
     uint64_t kernel_launches;    /* launches of THIS library's kernels                   */
     uint64_t last_contacts;      /* contacts found by the last step                      */
     uint64_t last_candidates;    /* candidate pairs tested by the last step (debug mode) */
-    uint32_t last_response_rounds; /* wavefront depth of the last ordered response      */
+    uint32_t last_response_rounds; /* last ordered response: wavefronts (level-synchronous)
+                                      or lock-step iterations of the longest warp (dataflow) */
     uint32_t side_list_size;     /* bodies outside the grid at the last step             */
     double gravity_ms;           /* accumulated device time of the gravity kernel        */
     uint64_t gravity_launches;

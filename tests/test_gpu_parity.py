@@ -162,7 +162,7 @@ def test_dense_lattice_response_bit_exact(tr, oracle, mode):
     got, contacts, st = gpu_run(tr, b, 10, g=(0, 0, 0), response_mode=mode)
     check_state(got, want, "dense lattice")
     assert np.array_equal(contacts, oracle.contacts(want))
-    assert (st.last_response_rounds >= 10) == (mode == 1)
+    assert st.last_response_rounds >= 10   # wavefronts (mode 1) / lock-step iterations of the longest warp (mode 0)
 
 
 @pytest.mark.parametrize("mode", [0, 1])

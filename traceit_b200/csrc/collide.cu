@@ -95,6 +95,7 @@ struct Collide {
     uint32_t* dep = nullptr;
     uint32_t* succ_i = nullptr;
     uint32_t* succ_j = nullptr;
+    uint4* crec = nullptr;                    // packed {i, j, succ_i, succ_j} per contact (dataflow executor)
     uint32_t* frontier[2] = {nullptr, nullptr};
 
     void* cub_tmp = nullptr;
@@ -481,8 +482,8 @@ __global__ void __launch_bounds__(256) deps_kernel(const unsigned long long* __r
                                                    const uint32_t* __restrict__ row_start,
                                                    const uint32_t* __restrict__ col_last, uint32_t c_n,
                                                    uint32_t* __restrict__ dep, uint32_t* __restrict__ succ_i,
-                                                   uint32_t* __restrict__ succ_j, uint32_t* __restrict__ frontier0,
-                                                   uint32_t* counters, int ready_counter) {
+                                                   uint32_t* __restrict__ succ_j, uint4* __restrict__ crec,
+                                                   uint32_t* __restrict__ frontier0, uint32_t* counters, int ready_counter) {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= c_n) return;
     unsigned long long k = ckeys[c];
@@ -498,6 +499,7 @@ __global__ void __launch_bounds__(256) deps_kernel(const unsigned long long* __r
     if (t + 1 < c_n && (uint32_t)(colkeys_sorted[t + 1] >> 32) == j) sj = colc_sorted[t + 1];
     else sj = row_start[j];
     succ_j[c] = sj;
+    crec[c] = make_uint4(i, j, succ_i[c], sj);
     if (d == 0) frontier0[atomicAdd(&counters[ready_counter], 1u)] = c;
 }
 
@@ -620,21 +622,69 @@ __global__ void __launch_bounds__(256) response_kernel(RespArgs a, const unsigne
 // the acquiring side.  A spin budget (C_ABORT) guarantees termination even if the graph were broken.
 constexpr uint32_t FLOW_SPIN_LIMIT = 1u << 21;
 
-__global__ void __launch_bounds__(128) response_flow_kernel(RespArgs a, const unsigned long long* __restrict__ ckeys,
-                                                            uint32_t* dep, const uint32_t* __restrict__ succ_i,
-                                                            const uint32_t* __restrict__ succ_j, uint32_t* q, uint32_t c_n,
-                                                            uint32_t* counters) {
+__global__ void __launch_bounds__(128) response_flow_kernel(RespArgs a, const uint4* __restrict__ crec, uint32_t* dep,
+                                                            uint32_t* q, uint32_t c_n, uint32_t* counters) {
     volatile uint32_t* vq = q;
     volatile uint32_t* vc = counters;
     uint32_t cur = EMPTY, slot = EMPTY, spins = 0, mine = 0;
+    uint4 rec = make_uint4(0, 0, EMPTY, EMPTY);    // {i, j, succ_i, succ_j} of `cur`, loaded one iteration early
     bool alive = true;
-    // One lock-step iteration per warp: [lanes without work try to acquire] -> vote -> [lanes with
-    // work process one contact] -> release.  Lanes never wait inside the iteration, so the warp
-    // stays converged (a lane-divergent formulation serialises the lanes and is no faster than the
-    // barrier version); the fences execute once per warp-iteration.
+    uint32_t iters = 0;
+    // One lock-step iteration per warp, two memory phases: (1) lanes with work resolve one contact,
+    // (2) they release its successors while idle lanes try to acquire from the queue.  Lanes never
+    // wait inside the iteration, so the warp stays converged (a lane-divergent formulation
+    // serialises the lanes and is no faster than the barrier version) and each phase costs one
+    // memory round trip; the fence executes once per warp-iteration.  Software pipelining: the
+    // records of both successors are loaded while the current contact is being resolved, and the
+    // bodies they touch are prefetched to L2, so the dependent chain of a hand-off is
+    // body loads -> fence -> dependency atomics.
     while (true) {
-        if (alive && cur == EMPTY) {
-            if (mine) {                           // publish finished work only when a chain ends:
+        if (!__any_sync(0xFFFFFFFFu, alive)) break;   // the warp leaves together (and reconverges here)
+        ++iters;
+        // ---- phase 1 (loads): successors' records + this contact's bodies, all in flight together
+        const bool work = cur != EMPTY;
+        const uint32_t s1 = work ? rec.z : EMPTY, s2 = work ? rec.w : EMPTY;
+        uint4 n1 = make_uint4(0, 0, EMPTY, EMPTY), n2 = make_uint4(0, 0, EMPTY, EMPTY);
+        if (s1 != EMPTY) n1 = crec[s1];
+        if (s2 != EMPTY) n2 = crec[s2];
+        if (work) respond(a, rec.x, rec.y);
+        if (s1 != EMPTY) {                        // the next hand-off will touch these bodies
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vel_rest + n1.x));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vel_rest + n1.y));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pos_m + n1.x));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pos_m + n1.y));
+        }
+        if (s2 != EMPTY) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vel_rest + n2.x));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vel_rest + n2.y));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pos_m + n2.x));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pos_m + n2.y));
+        }
+        // release: impulses/nudges are visible device-wide before the hand-off below.  No acquire
+        // fence is needed on the other side: everything another thread may have written is read
+        // with ld.cg / atomics issued after the queue slot or the dependency counter was observed.
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        // ---- phase 2 (atomics): working lanes release their successors, idle lanes try to acquire
+        if (work) {
+            const uint32_t r1 = (s1 != EMPTY) ? atomicSub(&dep[s1], 1u) : 0u;
+            const uint32_t r2 = (s2 != EMPTY) ? atomicSub(&dep[s2], 1u) : 0u;
+            ++mine;
+            uint32_t next = EMPTY;
+            if (r1 == 1u) {
+                next = s1;
+                rec = n1;
+            }
+            if (r2 == 1u) {
+                if (next == EMPTY) {
+                    next = s2;
+                    rec = n2;
+                } else {
+                    vq[atomicAdd(&counters[C_QTAIL], 1u)] = s2;   // second ready successor: to the global queue
+                }
+            }
+            cur = next;
+        } else if (alive) {
+            if (mine) {                           // publish finished work only when a chain has ended:
                 atomicAdd(&counters[C_DONE], mine);   // one hot-address atomic per chain, not per contact
                 mine = 0;
             }
@@ -647,6 +697,7 @@ __global__ void __launch_bounds__(128) response_flow_kernel(RespArgs a, const un
                 const uint32_t c = vq[slot];
                 if (c != EMPTY) {
                     cur = c;
+                    rec = crec[c];
                     slot = EMPTY;
                     spins = 0;
                 } else if ((++spins & 15u) == 0 && (vc[C_DONE] >= c_n || vc[C_ABORT])) {
@@ -657,43 +708,8 @@ __global__ void __launch_bounds__(128) response_flow_kernel(RespArgs a, const un
                 }
             }
         }
-        if (!__any_sync(0xFFFFFFFFu, alive)) break;   // the warp leaves together (and reconverges here)
-        // (no acquire fence: everything another thread may have written is read with ld.cg / atomics
-        //  issued after the queue slot or the dependency counter was observed)
-        uint32_t s1 = EMPTY, s2 = EMPTY;
-        if (cur != EMPTY) {
-            s1 = succ_i[cur];
-            s2 = succ_j[cur];
-            // the successors' records are needed one iteration from now: start pulling them into L2
-            if (s1 != EMPTY) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(ckeys + s1));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(succ_i + s1));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(succ_j + s1));
-            }
-            if (s2 != EMPTY) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(ckeys + s2));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(succ_i + s2));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(succ_j + s2));
-            }
-            const unsigned long long k = ckeys[cur];
-            respond(a, (uint32_t)(k >> 32), (uint32_t)k);
-        }
-        __threadfence();                          // release: impulses/nudges are visible before the hand-off
-        if (cur != EMPTY) {
-            // both releases are issued back to back; mutable state is only ever read with L2 loads
-            // (ld.cg) issued after these atomics return
-            const uint32_t r1 = (s1 != EMPTY) ? atomicSub(&dep[s1], 1u) : 0u;
-            const uint32_t r2 = (s2 != EMPTY) ? atomicSub(&dep[s2], 1u) : 0u;
-            ++mine;
-            uint32_t next = EMPTY;
-            if (r1 == 1u) next = s1;
-            if (r2 == 1u) {
-                if (next == EMPTY) next = s2;
-                else vq[atomicAdd(&counters[C_QTAIL], 1u)] = s2;
-            }
-            cur = next;
-        }
     }
+    if ((threadIdx.x & 31) == 0) atomicMax(&counters[C_ROUNDS], iters);   // observability: longest warp
 }
 
 // ---------------------------------------------------------------------------------------
@@ -803,6 +819,7 @@ static int ensure_buffers(tr_world* w) {
         TR_TRY(realloc_dev(&c->dep, want_c));
         TR_TRY(realloc_dev(&c->succ_i, want_c));
         TR_TRY(realloc_dev(&c->succ_j, want_c));
+        TR_TRY(realloc_dev(&c->crec, want_c));
         TR_TRY(realloc_dev(&c->frontier[0], want_c));
         TR_TRY(realloc_dev(&c->frontier[1], want_c));
         c->cap_contacts = want_c;
@@ -810,8 +827,8 @@ static int ensure_buffers(tr_world* w) {
     if (!c->counters) {
         TR_CUDA(cudaMalloc(&c->counters, C_NCOUNTERS * sizeof(uint32_t)));
         TR_CUDA(cudaMallocHost(&c->h_counters, C_NCOUNTERS * sizeof(uint32_t)));
-        TR_CUDA(cudaMallocHost(&c->h_rounds, sizeof(uint32_t)));
-        *c->h_rounds = 0;
+        TR_CUDA(cudaMallocHost(&c->h_rounds, 8 * sizeof(uint32_t)));
+        memset(c->h_rounds, 0, 8 * sizeof(uint32_t));
     }
     // CUB scratch sized for the largest of the three sorts
     size_t need = 0, b = 0;
@@ -976,8 +993,8 @@ void collide_poll_stats(tr_world* w) {
     Collide* c = w->col;
     if (c && c->rounds_pending) {
         if (c->flow_pending) {
-            w->stats.last_response_rounds = 0;    // no rounds in dataflow mode
-            if (*c->h_rounds != 0 && w->deferred_error == TR_OK) {
+            w->stats.last_response_rounds = c->h_rounds[0];   // dataflow: lock-step iterations of the longest warp
+            if (c->h_rounds[C_ABORT - C_ROUNDS] != 0 && w->deferred_error == TR_OK) {
                 w->deferred_error = TR_ERR_CUDA;
                 w->deferred_msg = "ordered response: dataflow watchdog fired (dependency graph did not drain)";
             }
@@ -1026,21 +1043,20 @@ int collide_step(tr_world* w) {
     const bool flow = w->params.response_mode != 1;   // 1 selects the level-synchronous kernel
     if (flow) TR_CUDA(cudaMemsetAsync(c->frontier[0], 0xFF, (size_t)cn * sizeof(uint32_t), w->stream));   // queue = all EMPTY
     deps_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, c->colkeys_alt, c->colc_alt, c->col_pos, c->row_start, c->col_last,
-                                                cn, c->dep, c->succ_i, c->succ_j, c->frontier[0], c->counters,
+                                                cn, c->dep, c->succ_i, c->succ_j, c->crec, c->frontier[0], c->counters,
                                                 flow ? C_QTAIL : C_FRONT);
     if (flow) {
         RespArgs ra{w->pos_m[w->cur], w->vel_rest, w->center_r, w->half_ext, w->flags};
         int fblocks = w->num_sms;                     // resident by construction: 128 threads per SM
         int fwant = (int)((cn + 127) / 128);
         if (fwant < fblocks) fblocks = fwant < 1 ? 1 : fwant;
-        response_flow_kernel<<<fblocks, 128, 0, w->stream>>>(ra, c->ckeys, c->dep, c->succ_i, c->succ_j, c->frontier[0], cn,
-                                                             c->counters);
+        response_flow_kernel<<<fblocks, 128, 0, w->stream>>>(ra, c->crec, c->dep, c->frontier[0], cn, c->counters);
         TR_CUDA(cudaGetLastError());
         timer_end(w, &t);
         w->stats.kernel_launches += 4;
         c->last_contacts = count;
         // watchdog flag + (unused) round counter come back with the next sync
-        TR_CUDA(cudaMemcpyAsync(c->h_rounds, c->counters + C_ABORT, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+        TR_CUDA(cudaMemcpyAsync(c->h_rounds, c->counters + C_ROUNDS, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
         c->rounds_pending = true;
         c->flow_pending = true;
         return TR_OK;
@@ -1167,7 +1183,7 @@ int collide_free(tr_world* w) {
     if (c->h_rounds) cudaFreeHost(c->h_rounds);
     cudaFree(c->ckeys); cudaFree(c->ckeys_alt); cudaFree(c->colkeys); cudaFree(c->colkeys_alt);
     cudaFree(c->colc); cudaFree(c->colc_alt); cudaFree(c->col_pos); cudaFree(c->dep);
-    cudaFree(c->succ_i); cudaFree(c->succ_j); cudaFree(c->frontier[0]); cudaFree(c->frontier[1]);
+    cudaFree(c->succ_i); cudaFree(c->succ_j); cudaFree(c->crec); cudaFree(c->frontier[0]); cudaFree(c->frontier[1]);
     cudaFree(c->cub_tmp);
     if (c->bp_graph) cudaGraphExecDestroy(c->bp_graph);
     delete c;
