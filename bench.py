@@ -169,6 +169,20 @@ def cpu_reference_step_rate(name: str, steps: int, warmup: int, n: int = CPU_SAM
         "sample": f"{steps} steps of the {name} cloud cut to N={n} ({what}); {pairs / dt:.3e} unordered pair visits/s x2",
         "pair_visits_per_s": pairs / dt, "ms_per_step": dt / steps * 1e3, "n_bodies": n,
     }
+    # the reference as shipped: its CMakeLists.txt sets no build type, i.e. -O0 (same bits, ~5x slower)
+    if po.ref_available(o0=True):
+        n0 = 8192
+        w0 = po.RefWorld(1.2, o0=True)
+        w0.add(make_scene(name, n0))
+        w0.step(1)
+        t0 = time.perf_counter()
+        w0.step(2)
+        dt0 = time.perf_counter() - t0
+        out["as_shipped_O0"] = {"value": n0 * (n0 - 1) * 2 / dt0, "unit": "interactions/s", "cores": 1, "kind": "reference",
+                                "sample": f"2 steps at N={n0}, verbatim reference built -O0 as its CMakeLists.txt does"}
+        w0.close()
+    # O(N^2) sweep: extrapolated (NOT measured) time of one reference step at the workload's size
+    out["extrapolated_s_per_step_at_workload_n"] = cfg["n"] * (cfg["n"] - 1) / 2 / (pairs / dt)
     if cfg["gravity"]:
         # second line: the restated pair-gravity term (dead code in the reference) on all host cores
         threads = os.cpu_count() or 1
