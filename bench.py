@@ -403,7 +403,10 @@ def main():
         "config": {"workload": f"{name}: {cfg['desc']}", "n_bodies": n, "G": GRAVITY_G, "g": [0, 0, 0],
                    "parallelism": f"targets sharded over {world_size} GPU(s), sources replicated",
                    "l2": "flushed between timed steps (256 MB memset, outside the per-step events)" if flush_buf is not None else "not flushed",
-                   "timing": "sum of per-step CUDA-event intervals on the launching stream, max over ranks"},
+                   "timing": "sum of per-step CUDA-event intervals on the launching stream, max over ranks",
+                   "interaction": ("ordered (target, source) gravity evaluations, N^2 per step" if cfg["gravity"] else
+                                   "ordered pair visits the reference's O(N^2) sweep would make, N^2 per step "
+                                   "(the grid broad phase prunes them; see collision_ms / steps_per_s for the physical cost)")},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
     }
