@@ -18,7 +18,8 @@
 //   K5  narrow_kernel        27-cell stencil as 9 contiguous key ranges, exact reference
 //                            predicate (no FMA contraction), emits (i<j) contacts.
 //   K5b side_kernel          every side-list body against every live body.
-//   K6  ordered response     contacts sorted by (i,j); a dependency wavefront replays the
+//   K6  ordered response     contacts counting-sorted into (i,j) and (j,i) order give each contact
+//                            its two predecessors / successors; the executor replays the
 //                            reference's Gauss-Seidel order exactly: a contact runs when
 //                            the previous contact of BOTH its bodies has run, so results
 //                            are bit-identical to the sequential sweep.
@@ -70,13 +71,15 @@ struct Collide {
     uint32_t* vals_sorted = nullptr; // id | static<<31 in (key,id) order
     uint2* tmp_ids = nullptr;        // K3b out: (id|static, key) grouped by cell, arrival order
     uint32_t* tile_sum = nullptr;    // scan: per-tile histogram sums
+    uint64_t tile_sum_cap = 0;
     float4* sorted_center_r = nullptr;
     uint32_t* cell_count = nullptr;  // [ncell] histogram; self-cleaning (K3b counts it back to zero)
     uint32_t* cell_start = nullptr;  // [ncell+1] dense exclusive prefix
     uint32_t* side_list = nullptr;   // ids of side-list bodies
     uint8_t* klass = nullptr;        // 0 dropped, 1 grid, 2 side
-    uint32_t* row_start = nullptr;   // per body: first contact with i == body
-    uint32_t* col_last = nullptr;    // per body: last column-order slot with j == body
+    uint32_t* row_start = nullptr;   // [N+1] dense: contacts with i == body are [row_start[b], row_start[b+1])
+    uint32_t* col_start = nullptr;   // [N+1] dense: column-order slots with j == body
+    uint32_t* body_cnt = nullptr;    // [N] per-body histogram scratch (self-cleaning)
 
     uint32_t* counters = nullptr;
     uint32_t* h_counters = nullptr;  // pinned mirror (detection read-back)
@@ -87,10 +90,8 @@ struct Collide {
     // per contact
     unsigned long long* ckeys = nullptr;      // (i<<32)|j, unsorted then sorted
     unsigned long long* ckeys_alt = nullptr;
-    unsigned long long* colkeys = nullptr;    // (j<<32)|i
-    unsigned long long* colkeys_alt = nullptr;
+    unsigned long long* colkeys = nullptr;    // column scatter scratch: (i<<32)|c in arrival order
     uint32_t* colc = nullptr;                 // contact index per column slot
-    uint32_t* colc_alt = nullptr;
     uint32_t* col_pos = nullptr;              // inverse of colc
     uint32_t* dep = nullptr;
     uint32_t* succ_i = nullptr;
@@ -210,7 +211,8 @@ __device__ __forceinline__ void load_tile_items(const uint32_t* __restrict__ cel
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) tile_sums_kernel(const uint32_t* __restrict__ cell_count, uint32_t ncell,
-                                                                 uint32_t* __restrict__ tile_sum, uint32_t* counters) {
+                                                                 uint32_t* __restrict__ tile_sum, uint32_t* counters,
+                                                                 uint32_t occ_limit) {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     uint32_t v[SCAN_ITEMS];
     load_tile_items(cell_count, blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS, ncell, v);
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_sums_kernel(const uint32_t*
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // largest cell population guards the O(occ^2) rank step; almost never above a handful
     vmax = __reduce_max_sync(0xFFFFFFFFu, vmax);
-    if (lane == 0 && vmax > OCC_LIMIT) atomicMax(&counters[C_MAXOCC], vmax);
+    if (lane == 0 && vmax > occ_limit) atomicMax(&counters[C_MAXOCC], vmax);
     tsum = __reduce_add_sync(0xFFFFFFFFu, tsum);
     if (lane == 0) s_warp[wid] = tsum;
     __syncthreads();
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_sums_kernel(const uint32_t*
 __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const uint32_t* __restrict__ cell_count,
                                                             const uint32_t* __restrict__ tile_sum,
                                                             uint32_t* __restrict__ cell_start, uint32_t ncell,
-                                                            uint32_t* counters) {
+                                                            uint32_t* counters, int total_slot) {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32], s_red[SCAN_THREADS / 32], s_prefix;
     const uint32_t tile = blockIdx.x;
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const uint32_t* __re
             s_prefix = r;
             if ((tile + 1) * (uint32_t)SCAN_TILE >= ncell) {   // last tile: grand total = number of grid bodies
                 cell_start[ncell] = r + total;
-                counters[C_GRID] = r + total;
+                if (total_slot >= 0) counters[total_slot] = r + total;
             }
         }
     }
@@ -450,37 +452,75 @@ __global__ void __launch_bounds__(256) side_kernel(const uint32_t* __restrict__ 
 // ---------------------------------------------------------------------------------------
 // K6 preparation: dependency structure of the lexicographic Gauss-Seidel order
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) colkeys_kernel(const unsigned long long* __restrict__ ckeys, uint32_t c_n,
-                                                      unsigned long long* __restrict__ colkeys, uint32_t* __restrict__ colc,
-                                                      uint32_t* __restrict__ row_start) {
+// The contact list is put into the reference's visiting order - lexicographic (i,j) - and into
+// "column" order (j, then i) with the same counting-sort machinery as the broad phase, keyed by
+// body id: histogram (RED) -> two-kernel scan -> scatter into the body's segment (atomicSub counts
+// the histogram back to zero) -> rank inside the segment.  The scans leave DENSE tables
+// row_start[N+1] / col_start[N+1], so "first / last contact of body b" is a lookup.
+__global__ void __launch_bounds__(256) chist_kernel(const unsigned long long* __restrict__ ckeys, uint32_t c_n, int shift,
+                                                    uint32_t* __restrict__ cnt) {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= c_n) return;
-    unsigned long long k = ckeys[c];
-    uint32_t i = (uint32_t)(k >> 32), j = (uint32_t)k;
-    colkeys[c] = ((unsigned long long)j << 32) | i;
-    colc[c] = c;
-    if (c == 0 || (uint32_t)(ckeys[c - 1] >> 32) != i) row_start[i] = c;
+    if (c < c_n) atomicAdd(&cnt[(uint32_t)(ckeys[c] >> shift)], 1u);
 }
 
-__global__ void __launch_bounds__(256) colpos_kernel(const unsigned long long* __restrict__ colkeys_sorted,
-                                                     const uint32_t* __restrict__ colc_sorted, uint32_t c_n,
-                                                     uint32_t* __restrict__ col_pos, uint32_t* __restrict__ col_last) {
+__global__ void __launch_bounds__(256) cscatter_row_kernel(const unsigned long long* __restrict__ ckeys, uint32_t c_n,
+                                                           const uint32_t* __restrict__ row_start, uint32_t* __restrict__ cnt,
+                                                           unsigned long long* __restrict__ tmp) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c_n) return;
+    const unsigned long long k = ckeys[c];
+    const uint32_t i = (uint32_t)(k >> 32);
+    tmp[row_start[i] + atomicSub(&cnt[i], 1u) - 1u] = k;
+}
+
+// rows: ascending j inside body i's segment (j is unique inside a row)
+__global__ void __launch_bounds__(256) crank_row_kernel(const unsigned long long* __restrict__ tmp,
+                                                        const uint32_t* __restrict__ row_start, uint32_t c_n,
+                                                        unsigned long long* __restrict__ sorted) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= c_n) return;
-    col_pos[colc_sorted[t]] = t;
-    uint32_t j = (uint32_t)(colkeys_sorted[t] >> 32);
-    if (t == c_n - 1 || (uint32_t)(colkeys_sorted[t + 1] >> 32) != j) col_last[j] = t;
+    const unsigned long long k = tmp[t];
+    const uint32_t i = (uint32_t)(k >> 32);
+    const uint32_t s = row_start[i], e = row_start[i + 1];
+    uint32_t rank = 0;
+    for (uint32_t u = s; u < e; ++u) rank += (tmp[u] < k) ? 1u : 0u;
+    sorted[s + rank] = k;
+}
+
+// columns: entry = (i << 32 | c) of the contact c = (i,j) in row order, scattered to body j's segment
+__global__ void __launch_bounds__(256) cscatter_col_kernel(const unsigned long long* __restrict__ ckeys, uint32_t c_n,
+                                                           const uint32_t* __restrict__ col_start, uint32_t* __restrict__ cnt,
+                                                           unsigned long long* __restrict__ tmp) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c_n) return;
+    const unsigned long long k = ckeys[c];
+    const uint32_t j = (uint32_t)k;
+    tmp[col_start[j] + atomicSub(&cnt[j], 1u) - 1u] = (k & 0xFFFFFFFF00000000ull) | c;
+}
+
+__global__ void __launch_bounds__(256) crank_col_kernel(const unsigned long long* __restrict__ tmp,
+                                                        const unsigned long long* __restrict__ ckeys,
+                                                        const uint32_t* __restrict__ col_start, uint32_t c_n,
+                                                        uint32_t* __restrict__ colc, uint32_t* __restrict__ col_pos) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= c_n) return;
+    const unsigned long long e = tmp[t];
+    const uint32_t c = (uint32_t)e;
+    const uint32_t j = (uint32_t)ckeys[c];
+    const uint32_t s = col_start[j], en = col_start[j + 1];
+    uint32_t rank = 0;
+    for (uint32_t u = s; u < en; ++u) rank += (tmp[u] < e) ? 1u : 0u;   // ascending i (unique inside a column)
+    colc[s + rank] = c;
+    col_pos[c] = s + rank;
 }
 
 // Body b's contacts in sweep order are: its column entries (k,b) by ascending k, then its
 // row entries (b,j) by ascending j.  pred/succ below are the neighbours of contact c in the
 // lists of its two bodies.
 __global__ void __launch_bounds__(256) deps_kernel(const unsigned long long* __restrict__ ckeys,
-                                                   const unsigned long long* __restrict__ colkeys_sorted,
-                                                   const uint32_t* __restrict__ colc_sorted,
-                                                   const uint32_t* __restrict__ col_pos,
+                                                   const uint32_t* __restrict__ colc, const uint32_t* __restrict__ col_pos,
                                                    const uint32_t* __restrict__ row_start,
-                                                   const uint32_t* __restrict__ col_last, uint32_t c_n,
+                                                   const uint32_t* __restrict__ col_start, uint32_t c_n,
                                                    uint32_t* __restrict__ dep, uint32_t* __restrict__ succ_i,
                                                    uint32_t* __restrict__ succ_j, uint4* __restrict__ crec,
                                                    uint32_t* __restrict__ frontier0, uint32_t* counters, int ready_counter) {
@@ -489,17 +529,17 @@ __global__ void __launch_bounds__(256) deps_kernel(const unsigned long long* __r
     unsigned long long k = ckeys[c];
     uint32_t i = (uint32_t)(k >> 32), j = (uint32_t)k;
     uint32_t t = col_pos[c];
-    bool row_prev = c > 0 && (uint32_t)(ckeys[c - 1] >> 32) == i;
-    bool pred_i = row_prev || col_last[i] != EMPTY;
-    bool pred_j = t > 0 && (uint32_t)(colkeys_sorted[t - 1] >> 32) == j;
+    bool pred_i = c > row_start[i] || col_start[i + 1] > col_start[i];   // an earlier row entry, or any column entry of i
+    bool pred_j = t > col_start[j];                                      // an earlier column entry of j
     uint32_t d = (pred_i ? 1u : 0u) + (pred_j ? 1u : 0u);
     dep[c] = d;
-    succ_i[c] = (c + 1 < c_n && (uint32_t)(ckeys[c + 1] >> 32) == i) ? c + 1 : EMPTY;
-    uint32_t sj = EMPTY;
-    if (t + 1 < c_n && (uint32_t)(colkeys_sorted[t + 1] >> 32) == j) sj = colc_sorted[t + 1];
-    else sj = row_start[j];
+    const uint32_t si = (c + 1 < row_start[i + 1]) ? c + 1 : EMPTY;
+    uint32_t sj;
+    if (t + 1 < col_start[j + 1]) sj = colc[t + 1];
+    else sj = (row_start[j + 1] > row_start[j]) ? row_start[j] : EMPTY;  // j's first row entry follows its last column entry
+    succ_i[c] = si;
     succ_j[c] = sj;
-    crec[c] = make_uint4(i, j, succ_i[c], sj);
+    crec[c] = make_uint4(i, j, si, sj);
     if (d == 0) frontier0[atomicAdd(&counters[ready_counter], 1u)] = c;
 }
 
@@ -793,18 +833,27 @@ static int ensure_buffers(tr_world* w) {
         TR_TRY(realloc_dev(&c->sorted_center_r, cap));
         TR_TRY(realloc_dev(&c->side_list, cap));
         TR_TRY(realloc_dev(&c->klass, cap));
-        TR_TRY(realloc_dev(&c->row_start, cap));
-        TR_TRY(realloc_dev(&c->col_last, cap));
+        TR_TRY(realloc_dev(&c->row_start, cap + 1));
+        TR_TRY(realloc_dev(&c->col_start, cap + 1));
+        TR_TRY(realloc_dev(&c->body_cnt, cap));
+        TR_CUDA(cudaMemsetAsync(c->body_cnt, 0, cap * sizeof(uint32_t), w->stream));
         c->cap_bodies = cap;
     }
     const uint64_t ncell = 1ull << (3 * c->bits);
     if (ncell > c->ncell_alloc) {
         TR_TRY(realloc_dev(&c->cell_start, ncell + 1));
         TR_TRY(realloc_dev(&c->cell_count, ncell));
-        TR_TRY(realloc_dev(&c->tile_sum, (ncell + SCAN_TILE - 1) / SCAN_TILE));
         // zeroed ONCE: the histogram counts itself back to zero every step (scatter_kernel)
         TR_CUDA(cudaMemsetAsync(c->cell_count, 0, ncell * sizeof(uint32_t), w->stream));
         c->ncell_alloc = ncell;
+    }
+    {
+        const uint64_t longest = ncell > c->cap_bodies + 1 ? ncell : c->cap_bodies + 1;
+        const uint64_t tiles = (longest + SCAN_TILE - 1) / SCAN_TILE;
+        if (tiles > c->tile_sum_cap) {
+            TR_TRY(realloc_dev(&c->tile_sum, tiles));
+            c->tile_sum_cap = tiles;
+        }
     }
     uint64_t want_c = w->params.max_contacts ? w->params.max_contacts : 8 * n + 4096;
     if (want_c > 0xFFFFFFF0ull) want_c = 0xFFFFFFF0ull;
@@ -812,9 +861,7 @@ static int ensure_buffers(tr_world* w) {
         TR_TRY(realloc_dev(&c->ckeys, want_c));
         TR_TRY(realloc_dev(&c->ckeys_alt, want_c));
         TR_TRY(realloc_dev(&c->colkeys, want_c));
-        TR_TRY(realloc_dev(&c->colkeys_alt, want_c));
         TR_TRY(realloc_dev(&c->colc, want_c));
-        TR_TRY(realloc_dev(&c->colc_alt, want_c));
         TR_TRY(realloc_dev(&c->col_pos, want_c));
         TR_TRY(realloc_dev(&c->dep, want_c));
         TR_TRY(realloc_dev(&c->succ_i, want_c));
@@ -830,14 +877,9 @@ static int ensure_buffers(tr_world* w) {
         TR_CUDA(cudaMallocHost(&c->h_rounds, 8 * sizeof(uint32_t)));
         memset(c->h_rounds, 0, 8 * sizeof(uint32_t));
     }
-    // CUB scratch sized for the largest of the three sorts
-    size_t need = 0, b = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, b, c->keys, c->keys_sorted, c->vals, c->vals_sorted, (uint32_t)c->cap_bodies);
-    need = b;
-    cub::DeviceRadixSort::SortKeys(nullptr, b, c->ckeys, c->ckeys_alt, (uint32_t)c->cap_contacts);
-    need = b > need ? b : need;
-    cub::DeviceRadixSort::SortPairs(nullptr, b, c->colkeys, c->colkeys_alt, c->colc, c->colc_alt, (uint32_t)c->cap_contacts);
-    need = b > need ? b : need;
+    // CUB scratch: only the crowded-cell fallback of the broad phase sorts with CUB
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, c->keys, c->keys_sorted, c->vals, c->vals_sorted, (uint32_t)c->cap_bodies);
     if (need > c->cub_tmp_bytes) {
         if (c->cub_tmp) cudaFree(c->cub_tmp);
         c->cub_tmp = nullptr;
@@ -845,12 +887,6 @@ static int ensure_buffers(tr_world* w) {
         c->cub_tmp_bytes = need;
     }
     return TR_OK;
-}
-
-static int bits_for(uint64_t max_value) {
-    int b = 1;
-    while (b < 32 && (max_value >> b) != 0) ++b;
-    return b;
 }
 
 static int launch_fast_broad(tr_world* w, cudaStream_t st) {
@@ -863,8 +899,8 @@ static int launch_fast_broad(tr_world* w, cudaStream_t st) {
     TR_CUDA(cudaMemsetAsync(c->counters, 0, C_NCOUNTERS * sizeof(uint32_t), st));
     keys_kernel<true><<<blocks, 256, 0, st>>>(w->center_r, w->flags, n, g, c->keys, c->vals, c->klass, c->side_list,
                                               c->cell_count, c->counters);
-    tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, ncell, c->tile_sum, c->counters);
-    scan_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, c->tile_sum, c->cell_start, ncell, c->counters);
+    tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, ncell, c->tile_sum, c->counters, OCC_LIMIT);
+    scan_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, c->tile_sum, c->cell_start, ncell, c->counters, C_GRID);
     scatter_kernel<<<blocks, 256, 0, st>>>(c->keys, ncell, w->flags, n, c->cell_start, c->cell_count, c->tmp_ids);
     rank_gather_kernel<<<blocks, 256, 0, st>>>(c->tmp_ids, c->cell_start, w->center_r, c->counters, c->keys_sorted,
                                                c->vals_sorted, c->sorted_center_r);
@@ -1026,25 +1062,26 @@ int collide_step(tr_world* w) {
     if (count == 0) return TR_OK;
     const uint32_t cn = (uint32_t)count;
     const uint32_t cblocks = (cn + 255) / 256;
-    const int idbits = bits_for(w->n - 1);
     PendingTimer t;
     timer_begin(w, T_RESPONSE, &t);
-    // lexicographic (i,j) order == the reference's visiting order
-    size_t tmp = c->cub_tmp_bytes;
-    TR_CUDA(cub::DeviceRadixSort::SortKeys(c->cub_tmp, tmp, c->ckeys, c->ckeys_alt, cn, 0, 32 + idbits, w->stream));
-    std::swap(c->ckeys, c->ckeys_alt);
-    TR_CUDA(cudaMemsetAsync(c->row_start, 0xFF, w->n * sizeof(uint32_t), w->stream));
-    TR_CUDA(cudaMemsetAsync(c->col_last, 0xFF, w->n * sizeof(uint32_t), w->stream));
-    colkeys_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, cn, c->colkeys, c->colc, c->row_start);
-    tmp = c->cub_tmp_bytes;
-    TR_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, c->colkeys, c->colkeys_alt, c->colc, c->colc_alt, cn, 0,
-                                            32 + idbits, w->stream));
-    colpos_kernel<<<cblocks, 256, 0, w->stream>>>(c->colkeys_alt, c->colc_alt, cn, c->col_pos, c->col_last);
+    const uint32_t nb = (uint32_t)w->n;
+    const uint32_t btiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
+    // lexicographic (i,j) order == the reference's visiting order: counting sort by i, rank by j
+    chist_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, cn, 32, c->body_cnt);
+    tile_sums_kernel<<<btiles, SCAN_THREADS, 0, w->stream>>>(c->body_cnt, nb, c->tile_sum, c->counters, 0xFFFFFFFFu);
+    scan_kernel<<<btiles, SCAN_THREADS, 0, w->stream>>>(c->body_cnt, c->tile_sum, c->row_start, nb, c->counters, -1);
+    cscatter_row_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, cn, c->row_start, c->body_cnt, c->ckeys_alt);
+    crank_row_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys_alt, c->row_start, cn, c->ckeys);
+    // column order (j, then i): the same, keyed by j
+    chist_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, cn, 0, c->body_cnt);
+    tile_sums_kernel<<<btiles, SCAN_THREADS, 0, w->stream>>>(c->body_cnt, nb, c->tile_sum, c->counters, 0xFFFFFFFFu);
+    scan_kernel<<<btiles, SCAN_THREADS, 0, w->stream>>>(c->body_cnt, c->tile_sum, c->col_start, nb, c->counters, -1);
+    cscatter_col_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, cn, c->col_start, c->body_cnt, c->colkeys);
+    crank_col_kernel<<<cblocks, 256, 0, w->stream>>>(c->colkeys, c->ckeys, c->col_start, cn, c->colc, c->col_pos);
     const bool flow = w->params.response_mode != 1;   // 1 selects the level-synchronous kernel
     if (flow) TR_CUDA(cudaMemsetAsync(c->frontier[0], 0xFF, (size_t)cn * sizeof(uint32_t), w->stream));   // queue = all EMPTY
-    deps_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, c->colkeys_alt, c->colc_alt, c->col_pos, c->row_start, c->col_last,
-                                                cn, c->dep, c->succ_i, c->succ_j, c->crec, c->frontier[0], c->counters,
-                                                flow ? C_QTAIL : C_FRONT);
+    deps_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, c->colc, c->col_pos, c->row_start, c->col_start, cn, c->dep, c->succ_i,
+                                                c->succ_j, c->crec, c->frontier[0], c->counters, flow ? C_QTAIL : C_FRONT);
     if (flow) {
         RespArgs ra{w->pos_m[w->cur], w->vel_rest, w->center_r, w->half_ext, w->flags};
         int fblocks = w->num_sms;                     // resident by construction: 128 threads per SM
@@ -1053,7 +1090,7 @@ int collide_step(tr_world* w) {
         response_flow_kernel<<<fblocks, 128, 0, w->stream>>>(ra, c->crec, c->dep, c->frontier[0], cn, c->counters);
         TR_CUDA(cudaGetLastError());
         timer_end(w, &t);
-        w->stats.kernel_launches += 4;
+        w->stats.kernel_launches += 12;   // 2 x (hist, tile sums, scan, scatter, rank) + deps + response
         c->last_contacts = count;
         // watchdog flag + (unused) round counter come back with the next sync
         TR_CUDA(cudaMemcpyAsync(c->h_rounds, c->counters + C_ROUNDS, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
@@ -1081,7 +1118,7 @@ int collide_step(tr_world* w) {
     if (want < blocks) blocks = want < 1 ? 1 : want;
     TR_CUDA(cudaLaunchCooperativeKernel((void*)response_kernel, dim3(blocks), dim3(256), args, 0, w->stream));
     timer_end(w, &t);
-    w->stats.kernel_launches += 4;   // colkeys, colpos, deps, response
+    w->stats.kernel_launches += 12;   // 2 x (hist, tile sums, scan, scatter, rank) + deps + response
     c->last_contacts = count;
     // wavefront count: copied to pinned memory asynchronously, picked up at the next sync (no extra stall)
     TR_CUDA(cudaMemcpyAsync(c->h_rounds, c->counters + C_ROUNDS, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
@@ -1178,11 +1215,11 @@ int collide_free(tr_world* w) {
     cudaFree(c->keys); cudaFree(c->keys_sorted); cudaFree(c->vals); cudaFree(c->vals_sorted); cudaFree(c->tmp_ids);
     cudaFree(c->sorted_center_r); cudaFree(c->cell_start); cudaFree(c->cell_count); cudaFree(c->tile_sum);
     cudaFree(c->side_list); cudaFree(c->klass);
-    cudaFree(c->row_start); cudaFree(c->col_last); cudaFree(c->counters);
+    cudaFree(c->row_start); cudaFree(c->col_start); cudaFree(c->body_cnt); cudaFree(c->counters);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_rounds) cudaFreeHost(c->h_rounds);
-    cudaFree(c->ckeys); cudaFree(c->ckeys_alt); cudaFree(c->colkeys); cudaFree(c->colkeys_alt);
-    cudaFree(c->colc); cudaFree(c->colc_alt); cudaFree(c->col_pos); cudaFree(c->dep);
+    cudaFree(c->ckeys); cudaFree(c->ckeys_alt); cudaFree(c->colkeys);
+    cudaFree(c->colc); cudaFree(c->col_pos); cudaFree(c->dep);
     cudaFree(c->succ_i); cudaFree(c->succ_j); cudaFree(c->crec); cudaFree(c->frontier[0]); cudaFree(c->frontier[1]);
     cudaFree(c->cub_tmp);
     if (c->bp_graph) cudaGraphExecDestroy(c->bp_graph);
