@@ -56,7 +56,7 @@ constexpr int GRAV_MAX_CHUNKS = 64;                    // partial sums per targe
 inline uint32_t grav_chunk_len(uint64_t n) {
     uint64_t c = (n + GRAV_MAX_CHUNKS - 1) / GRAV_MAX_CHUNKS;
     c = (c + GRAV_SUB - 1) / GRAV_SUB * GRAV_SUB;
-    if (c < 1024) c = 1024;
+    if (c < (uint64_t)GRAV_SUB) c = GRAV_SUB;   // at least one full TMA stage per chunk
     return (uint32_t)c;
 }
 
