@@ -313,7 +313,7 @@ def main():
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     total_ms_max = float(tm.item())
     ms_per_step = total_ms_max / args.steps
-    interactions_per_step = float(n) * float(n) if cfg["gravity"] else float(n) * float(n)
+    interactions_per_step = float(n) * float(n)     # ordered pairs, self pair included
     value = interactions_per_step * args.steps / (total_ms_max * 1e-3)
 
     # ---- per-kernel numbers (library-side CUDA events around each launch, same timed region)

@@ -549,3 +549,26 @@ def test_trajectory_ring_matches_reference_history(tr, oracle):
         w.enable_trajectory(0)
         with pytest.raises(tr.TraceItError):
             w.trajectory(0)
+
+
+def test_gravity_survey_parameterisation_huge_masses(tr, oracle):
+    """SURVEY.md 8d, config 2 alternative: masses uniform in [1,10]*1e9 with the reference's own
+    G = 6.6743e-11f (G*m ~ 0.07..0.7).  Intermediate products reach ~1e20: no overflow, same
+    accuracy as the G = 1 form."""
+    n = 8192
+    b = scenes.random_cloud(n, scenes.SEED_CFG2, spheres=True, mass_scale=1e9)
+    p = tr.default_params(flags=tr.PAIR_GRAVITY, g=(0, 0, 0))      # G stays the reference constant
+    with tr.World(p) as w:
+        w.add(b)
+        f = w.debug_gravity().astype(np.float64)
+        w.step(3)
+        got = w.read_bodies()
+    assert np.isfinite(f).all() and np.isfinite(got["pos"]).all()
+    f64 = oracle.pair_gravity_f64(b, float(np.float32(6.6743e-11)))
+    rel = np.linalg.norm(f - f64) / np.linalg.norm(f64)
+    print(f"huge masses: rel L2 vs fp64 {rel:.3e}")
+    assert rel <= FORCE_REL_L2_TOL
+    want = b.copy()
+    oracle.step(want, oracle.default_params(flags=oracle.PAIR_GRAVITY, g=(0, 0, 0)), 3)
+    epos, evel = _traj_errors(got, want)
+    assert epos <= TRAJ_REL_TOL and evel <= TRAJ_REL_TOL

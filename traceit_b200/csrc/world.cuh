@@ -47,8 +47,14 @@ constexpr int GRAV_THREADS = 256;
 constexpr int GRAV_PAIRS = TR_GRAV_PAIRS;             // packed f32x2 target pairs per thread
 constexpr int GRAV_T = 2 * GRAV_PAIRS;                 // targets per thread
 constexpr int GRAV_TILE = GRAV_THREADS * GRAV_T;       // 2048 targets per tile
-constexpr int GRAV_SUB = 512;                          // sources per TMA stage (8 KB)
-constexpr int GRAV_STAGES = 3;
+#ifndef TR_GRAV_SUB
+#define TR_GRAV_SUB 512
+#endif
+#ifndef TR_GRAV_STAGES
+#define TR_GRAV_STAGES 3
+#endif
+constexpr int GRAV_SUB = TR_GRAV_SUB;                  // sources per TMA stage (16 B each)
+constexpr int GRAV_STAGES = TR_GRAV_STAGES;
 constexpr int GRAV_MAX_CHUNKS = 64;                    // partial sums per target
 
 // chunk length is a function of N only, so a sharded run adds the same partial sums in
