@@ -15,8 +15,8 @@
 //   K4  rank_gather_kernel   rank of each id inside its cell (ascending id) -> the stable
 //                            (key,id) order; collider centres gathered into that order.
 //   (fallback for pathological occupancy: CUB radix sort + binary-search cell table.)
-//   K5  narrow_kernel        27-cell stencil as 9 contiguous key ranges, exact reference
-//                            predicate (no FMA contraction), emits (i<j) contacts.
+//   K5  narrow_kernel        half of the 27-cell stencil (each pair reached once) as 5 contiguous
+//                            key ranges, exact reference predicate (no FMA contraction).
 //   K5b side_kernel          every side-list body against every live body.
 //   K6  ordered response     contacts counting-sorted into (i,j) and (j,i) order give each contact
 //                            its two predecessors / successors; the executor replays the
@@ -373,16 +373,23 @@ __device__ __forceinline__ void test_range(uint32_t s, uint32_t e, uint32_t va, 
     for (uint32_t u = s; u < e; ++u) {
         const uint32_t vb = vals_sorted[u];
         const uint32_t idb = vb & ID_MASK;
-        if (idb <= ida) continue;
+        const uint32_t lo = min(ida, idb), hi = max(ida, idb);       // pairs are reported as (i < j)
         if (CANDIDATES) {
-            emit_pair(out, cap, counter, ida, idb);
+            emit_pair(out, cap, counter, lo, hi);
         } else {
             if (va & vb & STATIC_BIT) continue;                      // main.cpp:695
-            if (sphere_hit(ca, sorted_center_r[u])) emit_pair(out, cap, counter, ida, idb);
+            if (sphere_hit(ca, sorted_center_r[u])) emit_pair(out, cap, counter, lo, hi);
         }
     }
 }
 
+// The candidate relation "cell(b) is in the 27-cell stencil of cell(a)" is symmetric, so every
+// unordered pair is reached from exactly one side by a HALF stencil: the later slots of a's own
+// cell, and the 13 cells at "forward" offsets (dz,dy,dx) > (0,0,0) lexicographically (an offset o
+// and its opposite -o are distinct modulo 2^bits >= 4, and exactly one of them is forward).
+// With x as the fastest key digit those are 5 contiguous slot ranges for an interior cell:
+//   [t+1, end of cell cx+1]  in the own row, and cells cx-1..cx+1 of the rows (dz,dy) =
+//   (0,+1), (+1,-1), (+1,0), (+1,+1).
 template <bool CANDIDATES>
 __global__ void __launch_bounds__(128) narrow_kernel(const uint32_t* __restrict__ keys_sorted,
                                                      const uint32_t* __restrict__ vals_sorted,
@@ -400,22 +407,30 @@ __global__ void __launch_bounds__(128) narrow_kernel(const uint32_t* __restrict_
     const uint32_t msk = (1u << bits) - 1u;
     const uint32_t cx = key & msk, cy = (key >> bits) & msk, cz = (key >> (2 * bits)) & msk;
     const bool interior = cx > 0 && cx < msk;
+    // own row: the rest of the own cell, then cell cx+1
+    if (cx < msk) {
+        test_range<CANDIDATES>(t + 1, cell_start[key + 2], va, ida, ca, vals_sorted, sorted_center_r, out, cap, counter);
+    } else {
+        test_range<CANDIDATES>(t + 1, cell_start[key + 1], va, ida, ca, vals_sorted, sorted_center_r, out, cap, counter);
+        const uint32_t nk = key & ~msk;                            // x wraps to cell 0 of the same row
+        test_range<CANDIDATES>(cell_start[nk], cell_start[nk + 1], va, ida, ca, vals_sorted, sorted_center_r, out, cap, counter);
+    }
+    // the four forward rows
 #pragma unroll 1
-    for (int dz = -1; dz <= 1; ++dz) {
+    for (int r = 0; r < 4; ++r) {
+        const int dz = r == 0 ? 0 : 1;
+        const int dy = r == 0 ? 1 : r - 2;
+        const uint32_t row = (((cy + dy) & msk) << bits) | (((cz + dz) & msk) << (2 * bits));
+        if (interior) {
+            // cells (cx-1, cx, cx+1) of this row are consecutive keys: one contiguous slot range
+            test_range<CANDIDATES>(cell_start[row + cx - 1], cell_start[row + cx + 2], va, ida, ca, vals_sorted, sorted_center_r,
+                                   out, cap, counter);
+        } else {
 #pragma unroll 1
-        for (int dy = -1; dy <= 1; ++dy) {
-            const uint32_t row = (((cy + dy) & msk) << bits) | (((cz + dz) & msk) << (2 * bits));
-            if (interior) {
-                // cells (cx-1, cx, cx+1) of this row are consecutive keys: one contiguous slot range
-                test_range<CANDIDATES>(cell_start[row + cx - 1], cell_start[row + cx + 2], va, ida, ca, vals_sorted,
-                                       sorted_center_r, out, cap, counter);
-            } else {
-#pragma unroll 1
-                for (int dx = -1; dx <= 1; ++dx) {
-                    const uint32_t nk = row | ((cx + dx) & msk);
-                    test_range<CANDIDATES>(cell_start[nk], cell_start[nk + 1], va, ida, ca, vals_sorted, sorted_center_r, out,
-                                           cap, counter);
-                }
+            for (int dx = -1; dx <= 1; ++dx) {
+                const uint32_t nk = row | ((cx + dx) & msk);
+                test_range<CANDIDATES>(cell_start[nk], cell_start[nk + 1], va, ida, ca, vals_sorted, sorted_center_r, out, cap,
+                                       counter);
             }
         }
     }
