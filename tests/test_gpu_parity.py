@@ -603,3 +603,32 @@ def test_dense_lattice_long_horizon_drift(tr, oracle):
     drift = np.abs(got["pos"][finite].astype(np.float64) - want["pos"][finite]).max() if finite.any() else 0.0
     print(f"K=50 drift on {finite.sum()} finite bodies: {drift}")
     assert drift == 0.0
+
+
+def test_parameter_changes_mid_run(tr, oracle):
+    """tr_world_set_params between frames: grid geometry (re-allocation of the cell tables and
+    re-capture of the broad-phase graph), collisions off/on, response executor, atmosphere and dt.
+    The physics must follow the oracle driven with the same schedule."""
+    b = scenes.random_cloud(6000, 61, spheres=True, density_l=0.6)
+    want = b.copy()
+    schedule = [
+        dict(),                                            # defaults
+        dict(grid_bits=3),                                 # coarser wrap: more aliasing, same contacts
+        dict(grid_bits=8, grid_origin=(-3.5, 2.25, 0.75)), # bigger table, shifted origin
+        dict(flags=0),                                     # collisions off
+        dict(response_mode=1, atm_density=np.float32(0.4), dt=np.float32(0.01)),
+        dict(grid_cell=np.float32(2.5)),                   # explicit (oversized) cell edge
+    ]
+    with tr.World(tr.default_params()) as w:
+        w.add(b)
+        for over in schedule:
+            p = tr.default_params(**over)
+            w.params = p
+            w.step(2)
+            op = oracle.default_params(flags=(oracle.COLLISIONS if p.flags & tr.COLLISIONS else 0),
+                                       atm_density=p.atm_density, dt=p.dt)
+            oracle.step(want, op, 2)
+            got = w.read_bodies()
+            check_state(got, want, f"after {over}")
+            if p.flags & tr.COLLISIONS:
+                assert np.array_equal(w.contacts(), oracle.contacts(want)), over
