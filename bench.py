@@ -348,8 +348,15 @@ def main():
         except Exception:
             pass
         ach = BROADPHASE_BYTES_PER_BODY * n / (broad_ms * 1e-3) / 1e9
-        bp = {"bound": "hbm", "kernel": "broad phase K2-K4 (keys, radix sort, cell ranges + gather)", "achieved": ach,
-              "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None, "peak_source": src,
+        bp_traffic = None
+        prof = os.path.join(ROOT, "profiles", "broadphase_traffic.json")
+        if os.path.exists(prof):
+            try:
+                bp_traffic = json.load(open(prof)).get(str(n))
+            except Exception:
+                bp_traffic = None
+        bp = {"bound": "hbm", "kernel": "broad phase K2-K4 (keys, one-digit radix sort, cell table, gather)", "achieved": ach,
+              "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": bp_traffic, "peak_source": src,
               "algorithmic": f"{BROADPHASE_BYTES_PER_BODY} B/body x {n} bodies", "kernel_ms": broad_ms}
         if roofline is None:
             roofline = bp
