@@ -58,13 +58,15 @@ typedef struct tr_world_params {
     /* Uniform-grid broad phase (no reference counterpart; the reference is brute force).
      * 0 / zeros = automatic.  cell edge defaults to 2*rmax*(1+2^-7) where rmax is the
      * largest radius among grid bodies; grid_bits is bits per axis of the wrapped key
-     * (2..10).  Bodies that cannot live in the grid (boxes, oversize or out-of-domain
-     * spheres) go to a side list that is tested against every body.                    */
+     * (2..10).  Spheres and boxes share the grid (a body's extent is |radius|, and
+     * max|size| as soon as boxes exist); oversize or out-of-domain bodies go to a side
+     * list that is tested against every body.                                            */
     float grid_origin[3];
     float grid_cell;
     int32_t grid_bits;
     uint64_t max_contacts;       /* 0 = 8*N + 4096 */
-    /* Largest radius admitted to the grid; 0 = automatic.              */
+    /* Largest extent admitted to the grid; 0 = automatic: the largest extent that is
+     * <= 8x the median extent.                                           */
     float grid_max_radius;
     /* Ordered collision response: 0 = dataflow (barrier-free, default), 1 = level-synchronous
      * wavefronts (one grid barrier per wavefront).  Both replay the reference's Gauss-Seidel

@@ -68,12 +68,13 @@ def test_step_host_round_trip_equals_step(tr, oracle):
 
 # ---------------------------------------------------------------- goldens from the verbatim reference
 def test_default_scene_golden_gpu(tr):
-    """Config 1 on the GPU: boxes + the 10000x5x10000 slab (side list), 1000 steps."""
+    """Config 1 on the GPU: the two box projectiles live in the grid (AABB predicate), the
+    10000x5x10000 slab is oversize and sits in the side list; 1000 steps."""
     g = load_golden("default_scene.npz")
     got, contacts, st = gpu_run(tr, g["initial"].copy(), 1000)
     check_state(got, g["final"], "default scene")
     assert np.array_equal(contacts, g["contacts"])
-    assert st.side_list_size == 3
+    assert st.side_list_size == 1
 
 
 @pytest.mark.parametrize("name,steps", [("sphere_cloud_2048_s1.npz", 1), ("sphere_cloud_2048_s50.npz", 50),
@@ -91,14 +92,14 @@ def test_grid_keys_sort_candidates_bit_exact(tr, oracle, n, dens, bits):
     b = scenes.random_cloud(n, 100 + bits, spheres=True, density_l=dens)
     b["radius"] = np.random.RandomState(bits).uniform(0.2, 0.5, n).astype(np.float32)
     b["mass"][::17] = 0          # dropped from the grid
-    b["isSphere"][::29] = 0      # boxes -> side list
+    b["isSphere"][::29] = 0      # boxes (size 0.5): share the grid, candidates are shape independent
     p = tr.default_params(flags=tr.COLLISIONS, grid_bits=bits)
     with tr.World(p) as w:
         w.add(b)
         g = w.debug_grid()
         ncand, cand = w.debug_candidates()
     gb = g["bits"]
-    in_grid = (b["isSphere"] != 0) & ~(b["mass"] <= 0)
+    in_grid = ~(b["mass"] <= 0)
     keys = oracle.grid_keys(b, (0, 0, 0), g["inv_cell"], gb)
     assert np.array_equal(g["keys"][in_grid], keys[in_grid])
     assert (g["keys"][~in_grid] == 0xFFFFFFFF).all()
@@ -107,8 +108,8 @@ def test_grid_keys_sort_candidates_bit_exact(tr, oracle, n, dens, bits):
     ocand, _, nc, _ = oracle.grid_pairs(b, in_grid.astype(np.uint8), (0, 0, 0), g["inv_cell"], gb, want_contacts=False)
     assert ncand == nc
     assert np.array_equal(cand, ocand)
-    # the grid actually used is the documented one
-    rmax = float(b["radius"][in_grid].max())
+    # the grid actually used is the documented one: extent = max(|radius| if sphere, |size|) in a mixed world
+    rmax = max(float(b["radius"][in_grid & (b["isSphere"] != 0)].max()), float(np.abs(b["size"][in_grid]).max()))
     assert g["cell"] == np.float32(np.float32(2.0 * rmax) * np.float32(1.0078125))
 
 
@@ -129,7 +130,7 @@ def test_contact_set_equals_brute_force(tr, oracle, n, dens):
         got = w.contacts()
         st = w.stats()
     assert np.array_equal(got, brute)
-    assert st.side_list_size == len(range(0, n, 1000)) + (0 if 5 % 1000 == 0 else 1)
+    assert st.side_list_size == 1          # only the oversize sphere; the 3.0 x 0.2 x 3.0 boxes share the grid
     assert st.last_contacts == len(brute)
 
 
@@ -465,7 +466,7 @@ def test_step_host_reclassifies_when_colliders_change(tr, oracle):
             oracle.step(want, op, 1)
             check_state(cur, want, f"frame {frame}")
             assert np.array_equal(w.contacts(), oracle.contacts(want))
-        assert w.stats().side_list_size >= 2   # + bodies the reference's blow-up turned into NaN
+        assert w.stats().side_list_size >= 1   # the oversize sphere (+ bodies the reference's blow-up turned into NaN)
 
 
 def test_bodies_added_between_steps_and_external_forces(tr, oracle):
@@ -632,3 +633,20 @@ def test_parameter_changes_mid_run(tr, oracle):
             check_state(got, want, f"after {over}")
             if p.flags & tr.COLLISIONS:
                 assert np.array_equal(w.contacts(), oracle.contacts(want)), over
+
+
+def test_all_box_world_uses_the_grid(tr, oracle):
+    """The reference's creation form only ever builds AABB bodies (src/main.cpp:1302-1306): a world
+    of 20,000 boxes of mixed sizes must go through the grid (empty side list), with the reference's
+    AABB predicate and normal, bit for bit."""
+    n = 20000
+    b = scenes.random_cloud(n, 71, spheres=False, density_l=0.9)
+    rs = np.random.RandomState(71)
+    b["size"] = rs.uniform(0.2, 1.0, size=(n, 3)).astype(np.float32)
+    b["isStatic"][::13] = 1
+    want = b.copy()
+    oracle.step(want, oracle.default_params(), 3)
+    got, contacts, st = gpu_run(tr, b, 3)
+    check_state(got, want, "box world")
+    assert np.array_equal(contacts, oracle.contacts(want)) and len(contacts) > 1000
+    assert st.side_list_size == 0

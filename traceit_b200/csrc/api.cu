@@ -250,8 +250,8 @@ static int ensure_capacity(tr_world* w, uint64_t need) {
     if (need <= w->cap) return TR_OK;
     uint64_t nc = w->cap ? w->cap : 1024;
     while (nc < need) nc *= 2;
-    if (need > (1ull << 31)) {
-        set_error("world too large: %llu bodies (limit 2^31)", (unsigned long long)need);
+    if (need > (1ull << 30)) {
+        set_error("world too large: %llu bodies (limit 2^30)", (unsigned long long)need);
         return TR_ERR_INVALID_ARG;
     }
     TR_TRY(grow(&w->pos_m[0], w->n, nc, w->stream));
@@ -618,7 +618,7 @@ int tr_bodies_add(tr_world* w, uint64_t n, const tr_body_desc* b, uint32_t* firs
         set_error("null argument");
         return TR_ERR_INVALID_ARG;
     }
-    if (w->host_bodies.size() + n > (1ull << 31)) {
+    if (w->host_bodies.size() + n > (1ull << 30)) {
         set_error("too many bodies");
         return TR_ERR_INVALID_ARG;
     }

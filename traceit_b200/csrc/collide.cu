@@ -40,8 +40,9 @@ namespace cg = cooperative_groups;
 namespace tr {
 
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;
-constexpr uint32_t ID_MASK = 0x7FFFFFFFu;
-constexpr uint32_t STATIC_BIT = 0x80000000u;
+constexpr uint32_t ID_MASK = 0x3FFFFFFFu;      // body ids fit 30 bits (tr_bodies_add enforces it)
+constexpr uint32_t STATIC_BIT = 0x80000000u;   // collider::isStatic
+constexpr uint32_t BOX_BIT = 0x40000000u;      // !collider::isSphere: pairs with it use the AABB predicate
 constexpr uint32_t OCC_LIMIT = 1024;      // bodies per cell above which the O(occ^2) rank step is refused
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
@@ -58,7 +59,8 @@ struct Collide {
     float cell = 1.f, inv_cell = 1.f, rmax_grid = 0.f;
     float origin[3] = {0, 0, 0};
     int bits = 2;
-    bool may_have_side = true;    // some body is statically outside the grid (box / oversize / NaN radius)
+    bool may_have_side = true;    // some body is statically outside the grid (oversize / NaN extent)
+    bool mixed = false;           // live boxes exist: they share the grid, extents include collider::size
     bool use_cub = false;         // occupancy fallback engaged
     uint64_t cap_bodies = 0;      // arrays below sized for this many bodies
     uint64_t ncell_alloc = 0;
@@ -73,6 +75,7 @@ struct Collide {
     uint32_t* tile_sum = nullptr;    // scan: per-tile histogram sums
     uint64_t tile_sum_cap = 0;
     float4* sorted_center_r = nullptr;
+    float4* sorted_half_ext = nullptr;   // gathered only in mixed worlds
     uint32_t* cell_count = nullptr;  // [ncell] histogram; self-cleaning (K3b counts it back to zero)
     uint32_t* cell_start = nullptr;  // [ncell+1] dense exclusive prefix
     uint32_t* side_list = nullptr;   // ids of side-list bodies
@@ -145,13 +148,18 @@ __device__ __forceinline__ uint32_t pack_key(int cx, int cy, int cz, int bits) {
 struct GridParams {
     float ox, oy, oz, inv_cell, rmax_grid;
     int bits;
+    int mixed;   // boxes live in the grid too: a body's extent is max(|radius| if sphere, |size.xyz|)
 };
+
+__device__ __forceinline__ uint32_t pack_val(uint32_t id, uint8_t f) {
+    return id | ((f & F_STATIC) ? STATIC_BIT : 0u) | ((f & F_SPHERE) ? 0u : BOX_BIT);
+}
 
 // ---------------------------------------------------------------------------------------
 // K2: keys + classification (+ per-cell histogram on the fast path)
 // ---------------------------------------------------------------------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ center_r,
+__global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ center_r, const float4* __restrict__ half_ext,
                                                    const uint8_t* __restrict__ flags, uint32_t n, GridParams g,
                                                    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                                    uint8_t* __restrict__ klass, uint32_t* __restrict__ side_list,
@@ -174,7 +182,17 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ ce
             float uy = __fmul_rn(__fsub_rn(c.y, g.oy), g.inv_cell);
             float uz = __fmul_rn(__fsub_rn(c.z, g.oz), g.inv_cell);
             bool in_domain = fabsf(ux) < 32768.0f && fabsf(uy) < 32768.0f && fabsf(uz) < 32768.0f;
-            bool grid_ok = (f & F_SPHERE) && in_domain && fabsf(c.w) <= g.rmax_grid;
+            bool grid_ok;
+            if (g.mixed) {
+                // any body may meet a box, and box pairs use collider::size of BOTH bodies (main.cpp:704-705)
+                const float4 h = half_ext[i];
+                float ext = fmaxf(fmaxf(fabsf(h.x), fabsf(h.y)), fabsf(h.z));
+                const bool finite = fabsf(h.x) <= 3.0e38f && fabsf(h.y) <= 3.0e38f && fabsf(h.z) <= 3.0e38f;   // rejects NaN/inf
+                if (f & F_SPHERE) ext = fmaxf(ext, fabsf(c.w));
+                grid_ok = in_domain && finite && ext <= g.rmax_grid && (!(f & F_SPHERE) || fabsf(c.w) <= g.rmax_grid);
+            } else {
+                grid_ok = (f & F_SPHERE) && in_domain && fabsf(c.w) <= g.rmax_grid;
+            }
             if (grid_ok) {
                 key = pack_key(__float2int_rd(ux), __float2int_rd(uy), __float2int_rd(uz), g.bits);
                 k = 1;
@@ -186,7 +204,7 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ ce
             }
         }
         keys[i] = key;
-        if (!COUNT) vals[i] = i | ((f & F_STATIC) ? STATIC_BIT : 0u);
+        if (!COUNT) vals[i] = pack_val(i, f);
         klass[i] = k;
     }
 }
@@ -312,15 +330,17 @@ __global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict
     const uint32_t key = keys[i];
     if (key >= sentinel) return;          // side-list or dropped body
     const uint32_t old = atomicSub(&cell_count[key], 1u);
-    tmp[cell_start[key] + old - 1u] = make_uint2(i | ((flags[i] & F_STATIC) ? STATIC_BIT : 0u), key);
+    tmp[cell_start[key] + old - 1u] = make_uint2(pack_val(i, flags[i]), key);
 }
 
 // K4: deterministic order inside each cell (ascending id) + gather to sorted order.
 __global__ void __launch_bounds__(256) rank_gather_kernel(const uint2* __restrict__ tmp, const uint32_t* __restrict__ cell_start,
                                                           const float4* __restrict__ center_r,
+                                                          const float4* __restrict__ half_ext,   // NULL unless boxes are in the grid
                                                           const uint32_t* __restrict__ counters,
                                                           uint32_t* __restrict__ keys_sorted, uint32_t* __restrict__ vals_sorted,
-                                                          float4* __restrict__ sorted_center_r) {
+                                                          float4* __restrict__ sorted_center_r,
+                                                          float4* __restrict__ sorted_half_ext) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= counters[C_GRID] || counters[C_MAXOCC] > OCC_LIMIT) return;
     const uint2 me = tmp[t];
@@ -333,6 +353,7 @@ __global__ void __launch_bounds__(256) rank_gather_kernel(const uint2* __restric
     keys_sorted[f] = me.y;
     vals_sorted[f] = me.x;
     sorted_center_r[f] = c;
+    if (half_ext) sorted_half_ext[f] = half_ext[id];
 }
 
 // ---- fallback path (cell population above OCC_LIMIT): CUB radix sort, then the same tables ----
@@ -350,10 +371,13 @@ __global__ void __launch_bounds__(256) dense_start_kernel(const uint32_t* __rest
 }
 
 __global__ void __launch_bounds__(256) gather_kernel(const uint32_t* __restrict__ vals_sorted, const float4* __restrict__ center_r,
-                                                     const uint32_t* __restrict__ counters, float4* __restrict__ sorted_center_r) {
+                                                     const float4* __restrict__ half_ext, const uint32_t* __restrict__ counters,
+                                                     float4* __restrict__ sorted_center_r, float4* __restrict__ sorted_half_ext) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= counters[C_GRID]) return;
-    sorted_center_r[t] = center_r[vals_sorted[t] & ID_MASK];
+    const uint32_t id = vals_sorted[t] & ID_MASK;
+    sorted_center_r[t] = center_r[id];
+    if (half_ext) sorted_half_ext[t] = half_ext[id];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -365,10 +389,11 @@ __device__ __forceinline__ void emit_pair(unsigned long long* out, unsigned long
     if (slot < cap) out[slot] = ((unsigned long long)i << 32) | j;
 }
 
-template <bool CANDIDATES>
-__device__ __forceinline__ void test_range(uint32_t s, uint32_t e, uint32_t va, uint32_t ida, const float4 ca,
+template <bool CANDIDATES, bool MIXED>
+__device__ __forceinline__ void test_range(uint32_t s, uint32_t e, uint32_t va, uint32_t ida, const float4 ca, const float4 ha,
                                            const uint32_t* __restrict__ vals_sorted,
-                                           const float4* __restrict__ sorted_center_r, unsigned long long* out,
+                                           const float4* __restrict__ sorted_center_r,
+                                           const float4* __restrict__ sorted_half_ext, unsigned long long* out,
                                            unsigned long long cap, unsigned long long* counter) {
     for (uint32_t u = s; u < e; ++u) {
         const uint32_t vb = vals_sorted[u];
@@ -378,7 +403,10 @@ __device__ __forceinline__ void test_range(uint32_t s, uint32_t e, uint32_t va, 
             emit_pair(out, cap, counter, lo, hi);
         } else {
             if (va & vb & STATIC_BIT) continue;                      // main.cpp:695
-            if (sphere_hit(ca, sorted_center_r[u])) emit_pair(out, cap, counter, lo, hi);
+            bool hit;
+            if (MIXED && ((va | vb) & BOX_BIT)) hit = aabb_hit(ca, ha, sorted_center_r[u], sorted_half_ext[u]);   // main.cpp:704
+            else hit = sphere_hit(ca, sorted_center_r[u]);                                                       // main.cpp:702
+            if (hit) emit_pair(out, cap, counter, lo, hi);
         }
     }
 }
@@ -390,10 +418,13 @@ __device__ __forceinline__ void test_range(uint32_t s, uint32_t e, uint32_t va, 
 // With x as the fastest key digit those are 5 contiguous slot ranges for an interior cell:
 //   [t+1, end of cell cx+1]  in the own row, and cells cx-1..cx+1 of the rows (dz,dy) =
 //   (0,+1), (+1,-1), (+1,0), (+1,+1).
-template <bool CANDIDATES>
+// MIXED: boxes live in the grid; a pair with at least one box uses the AABB predicate on the
+// collider sizes of both bodies, exactly as the reference dispatches (main.cpp:701-706).
+template <bool CANDIDATES, bool MIXED>
 __global__ void __launch_bounds__(128) narrow_kernel(const uint32_t* __restrict__ keys_sorted,
                                                      const uint32_t* __restrict__ vals_sorted,
                                                      const float4* __restrict__ sorted_center_r,
+                                                     const float4* __restrict__ sorted_half_ext,
                                                      const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ counters,
                                                      int bits, bool check_occ, unsigned long long* out, unsigned long long cap,
                                                      unsigned long long* counter) {
@@ -404,16 +435,19 @@ __global__ void __launch_bounds__(128) narrow_kernel(const uint32_t* __restrict_
     const uint32_t va = vals_sorted[t];
     const uint32_t ida = va & ID_MASK;
     const float4 ca = sorted_center_r[t];
+    float4 ha = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MIXED) ha = sorted_half_ext[t];
     const uint32_t msk = (1u << bits) - 1u;
     const uint32_t cx = key & msk, cy = (key >> bits) & msk, cz = (key >> (2 * bits)) & msk;
     const bool interior = cx > 0 && cx < msk;
+#define TR_RANGE(S, E) test_range<CANDIDATES, MIXED>((S), (E), va, ida, ca, ha, vals_sorted, sorted_center_r, sorted_half_ext, out, cap, counter)
     // own row: the rest of the own cell, then cell cx+1
     if (cx < msk) {
-        test_range<CANDIDATES>(t + 1, cell_start[key + 2], va, ida, ca, vals_sorted, sorted_center_r, out, cap, counter);
+        TR_RANGE(t + 1, cell_start[key + 2]);
     } else {
-        test_range<CANDIDATES>(t + 1, cell_start[key + 1], va, ida, ca, vals_sorted, sorted_center_r, out, cap, counter);
+        TR_RANGE(t + 1, cell_start[key + 1]);
         const uint32_t nk = key & ~msk;                            // x wraps to cell 0 of the same row
-        test_range<CANDIDATES>(cell_start[nk], cell_start[nk + 1], va, ida, ca, vals_sorted, sorted_center_r, out, cap, counter);
+        TR_RANGE(cell_start[nk], cell_start[nk + 1]);
     }
     // the four forward rows
 #pragma unroll 1
@@ -423,17 +457,16 @@ __global__ void __launch_bounds__(128) narrow_kernel(const uint32_t* __restrict_
         const uint32_t row = (((cy + dy) & msk) << bits) | (((cz + dz) & msk) << (2 * bits));
         if (interior) {
             // cells (cx-1, cx, cx+1) of this row are consecutive keys: one contiguous slot range
-            test_range<CANDIDATES>(cell_start[row + cx - 1], cell_start[row + cx + 2], va, ida, ca, vals_sorted, sorted_center_r,
-                                   out, cap, counter);
+            TR_RANGE(cell_start[row + cx - 1], cell_start[row + cx + 2]);
         } else {
 #pragma unroll 1
             for (int dx = -1; dx <= 1; ++dx) {
                 const uint32_t nk = row | ((cx + dx) & msk);
-                test_range<CANDIDATES>(cell_start[nk], cell_start[nk + 1], va, ida, ca, vals_sorted, sorted_center_r, out, cap,
-                                       counter);
+                TR_RANGE(cell_start[nk], cell_start[nk + 1]);
             }
         }
     }
+#undef TR_RANGE
 }
 
 // K5b: side-list bodies against every live body.  grid = (ceil(n/256), up to 64).
@@ -784,17 +817,36 @@ static Collide* state(tr_world* w) {
     return w->col;
 }
 
-// Host-side choice of the grid: which radii are admitted, the cell edge, bits per axis.
+// Host-side choice of the grid: which bodies are admitted, the cell edge, bits per axis.
+// A body's extent is |radius| for a sphere in an all-sphere world; as soon as one live box with
+// finite size exists ("mixed" world) any body may meet a box, box pairs use collider::size of both
+// bodies, and the extent becomes max(|radius| if sphere, |size.x|, |size.y|, |size.z|).
+static float body_extent(const tr_body_desc& b, bool mixed) {
+    float e = b.isSphere ? std::fabs(b.radius) : 0.f;
+    if (mixed || !b.isSphere) e = std::max(e, std::max(std::fabs(b.size[0]), std::max(std::fabs(b.size[1]), std::fabs(b.size[2]))));
+    return e;
+}
+
 int collide_classify(tr_world* w) {
     Collide* c = state(w);
     const tr_world_params& p = w->params;
-    // admitted radius: user value, else max |r| over spheres with |r| <= 8 * median |r|
+    bool mixed = false;
+    for (const tr_body_desc& b : w->host_bodies)
+        if (!(b.mass <= 0) && !b.isSphere && std::isfinite(b.size[0]) && std::isfinite(b.size[1]) && std::isfinite(b.size[2])) {
+            mixed = true;
+            break;
+        }
+    c->mixed = mixed;
+    // admitted extent: user value, else the largest extent <= 8 * median extent
     float rmax = p.grid_max_radius;
     if (rmax <= 0.f) {
         std::vector<float> r;
         r.reserve(w->host_bodies.size());
-        for (const tr_body_desc& b : w->host_bodies)
-            if (b.isSphere && !(b.mass <= 0) && std::isfinite(b.radius)) r.push_back(std::fabs(b.radius));
+        for (const tr_body_desc& b : w->host_bodies) {
+            if (b.mass <= 0 || (!mixed && !b.isSphere)) continue;
+            float e = body_extent(b, mixed);
+            if (std::isfinite(e)) r.push_back(e);
+        }
         rmax = 0.f;
         if (!r.empty()) {
             std::vector<float> s = r;
@@ -810,7 +862,7 @@ int collide_classify(tr_world* w) {
     c->may_have_side = false;
     for (const tr_body_desc& b : w->host_bodies) {
         if (b.mass <= 0) continue;
-        if (!b.isSphere || !(std::fabs(b.radius) <= rmax)) {
+        if ((!mixed && !b.isSphere) || !(body_extent(b, mixed) <= rmax)) {
             c->may_have_side = true;
             break;
         }
@@ -846,6 +898,7 @@ static int ensure_buffers(tr_world* w) {
         TR_TRY(realloc_dev(&c->vals_sorted, cap));
         TR_TRY(realloc_dev(&c->tmp_ids, cap));
         TR_TRY(realloc_dev(&c->sorted_center_r, cap));
+        TR_TRY(realloc_dev(&c->sorted_half_ext, cap));
         TR_TRY(realloc_dev(&c->side_list, cap));
         TR_TRY(realloc_dev(&c->klass, cap));
         TR_TRY(realloc_dev(&c->row_start, cap + 1));
@@ -910,15 +963,15 @@ static int launch_fast_broad(tr_world* w, cudaStream_t st) {
     const uint32_t blocks = (n + 255) / 256;
     const uint32_t ncell = 1u << (3 * c->bits);
     const uint32_t ntiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
-    GridParams g{c->origin[0], c->origin[1], c->origin[2], c->inv_cell, c->rmax_grid, c->bits};
+    GridParams g{c->origin[0], c->origin[1], c->origin[2], c->inv_cell, c->rmax_grid, c->bits, c->mixed ? 1 : 0};
     TR_CUDA(cudaMemsetAsync(c->counters, 0, C_NCOUNTERS * sizeof(uint32_t), st));
-    keys_kernel<true><<<blocks, 256, 0, st>>>(w->center_r, w->flags, n, g, c->keys, c->vals, c->klass, c->side_list,
+    keys_kernel<true><<<blocks, 256, 0, st>>>(w->center_r, w->half_ext, w->flags, n, g, c->keys, c->vals, c->klass, c->side_list,
                                               c->cell_count, c->counters);
     tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, ncell, c->tile_sum, c->counters, OCC_LIMIT);
     scan_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, c->tile_sum, c->cell_start, ncell, c->counters, C_GRID);
     scatter_kernel<<<blocks, 256, 0, st>>>(c->keys, ncell, w->flags, n, c->cell_start, c->cell_count, c->tmp_ids);
-    rank_gather_kernel<<<blocks, 256, 0, st>>>(c->tmp_ids, c->cell_start, w->center_r, c->counters, c->keys_sorted,
-                                               c->vals_sorted, c->sorted_center_r);
+    rank_gather_kernel<<<blocks, 256, 0, st>>>(c->tmp_ids, c->cell_start, w->center_r, c->mixed ? w->half_ext : nullptr,
+                                               c->counters, c->keys_sorted, c->vals_sorted, c->sorted_center_r, c->sorted_half_ext);
     TR_CUDA(cudaGetLastError());
     return TR_OK;
 }
@@ -940,7 +993,7 @@ static int broad_phase(tr_world* w) {
         // signature of everything the captured launches depend on
         uint64_t sig[8] = {(uint64_t)(uintptr_t)w->center_r, (uint64_t)(uintptr_t)w->flags, (uint64_t)(uintptr_t)c->keys,
                            (uint64_t)(uintptr_t)c->cell_count, (uint64_t)(uintptr_t)c->ckeys ^ (uint64_t)(uintptr_t)c->tmp_ids,
-                           ((uint64_t)n << 8) | (uint64_t)c->bits, 0, 0};
+                           ((uint64_t)n << 9) | ((uint64_t)(c->mixed ? 1 : 0) << 8) | (uint64_t)c->bits, 0, 0};
         memcpy(&sig[6], &c->inv_cell, 4);
         memcpy((char*)&sig[6] + 4, &c->rmax_grid, 4);
         memcpy(&sig[7], &c->origin[0], 8);
@@ -966,16 +1019,17 @@ static int broad_phase(tr_world* w) {
         timer_end(w, &t);
         w->stats.kernel_launches += 5;
     } else {
-        GridParams g{c->origin[0], c->origin[1], c->origin[2], c->inv_cell, c->rmax_grid, c->bits};
+        GridParams g{c->origin[0], c->origin[1], c->origin[2], c->inv_cell, c->rmax_grid, c->bits, c->mixed ? 1 : 0};
         timer_begin(w, T_BROAD, &t);
         TR_CUDA(cudaMemsetAsync(c->counters, 0, C_NCOUNTERS * sizeof(uint32_t), w->stream));
-        keys_kernel<false><<<blocks, 256, 0, w->stream>>>(w->center_r, w->flags, n, g, c->keys, c->vals, c->klass, c->side_list,
+        keys_kernel<false><<<blocks, 256, 0, w->stream>>>(w->center_r, w->half_ext, w->flags, n, g, c->keys, c->vals, c->klass, c->side_list,
                                                           c->cell_count, c->counters);
         size_t tmp = c->cub_tmp_bytes;
         TR_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, c->keys, c->keys_sorted, c->vals, c->vals_sorted, n, 0,
                                                 3 * c->bits + 1, w->stream));
         dense_start_kernel<<<(ncell + 1 + 255) / 256, 256, 0, w->stream>>>(c->keys_sorted, n, ncell, c->cell_start, c->counters);
-        gather_kernel<<<blocks, 256, 0, w->stream>>>(c->vals_sorted, w->center_r, c->counters, c->sorted_center_r);
+        gather_kernel<<<blocks, 256, 0, w->stream>>>(c->vals_sorted, w->center_r, c->mixed ? w->half_ext : nullptr, c->counters,
+                                                     c->sorted_center_r, c->sorted_half_ext);
         timer_end(w, &t);
         w->stats.kernel_launches += 3;
     }
@@ -1011,8 +1065,14 @@ static int detect(tr_world* w, unsigned long long* out, uint64_t cap, uint64_t* 
         PendingTimer t;
         timer_begin(w, T_NARROW, &t);
         const uint32_t nb = (uint32_t)((w->n + 127) / 128);
-        narrow_kernel<CANDIDATES><<<nb, 128, 0, w->stream>>>(c->keys_sorted, c->vals_sorted, c->sorted_center_r, c->cell_start,
-                                                             c->counters, c->bits, !c->use_cub, out, cap, counter);
+        if (c->mixed)
+            narrow_kernel<CANDIDATES, true><<<nb, 128, 0, w->stream>>>(c->keys_sorted, c->vals_sorted, c->sorted_center_r,
+                                                                       c->sorted_half_ext, c->cell_start, c->counters, c->bits,
+                                                                       !c->use_cub, out, cap, counter);
+        else
+            narrow_kernel<CANDIDATES, false><<<nb, 128, 0, w->stream>>>(c->keys_sorted, c->vals_sorted, c->sorted_center_r,
+                                                                        c->sorted_half_ext, c->cell_start, c->counters, c->bits,
+                                                                        !c->use_cub, out, cap, counter);
         w->stats.kernel_launches += 1;
         const bool side_launched = c->may_have_side && !CANDIDATES;
         if (side_launched) TR_TRY(launch_side(w, out, cap, counter));
@@ -1228,7 +1288,7 @@ int collide_free(tr_world* w) {
     Collide* c = w->col;
     if (!c) return TR_OK;
     cudaFree(c->keys); cudaFree(c->keys_sorted); cudaFree(c->vals); cudaFree(c->vals_sorted); cudaFree(c->tmp_ids);
-    cudaFree(c->sorted_center_r); cudaFree(c->cell_start); cudaFree(c->cell_count); cudaFree(c->tile_sum);
+    cudaFree(c->sorted_center_r); cudaFree(c->sorted_half_ext); cudaFree(c->cell_start); cudaFree(c->cell_count); cudaFree(c->tile_sum);
     cudaFree(c->side_list); cudaFree(c->klass);
     cudaFree(c->row_start); cudaFree(c->col_start); cudaFree(c->body_cnt); cudaFree(c->counters);
     if (c->h_counters) cudaFreeHost(c->h_counters);
