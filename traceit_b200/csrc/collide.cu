@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(256) side_kernel(const uint32_t* __restrict__ 
                                                    unsigned long long* counter) {
     const uint32_t side_count = counters[C_SIDE];
     uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= n || blockIdx.y >= side_count) return;
+    if (x >= n) return;
     const uint8_t kx = klass[x];
     if (kx == 0) return;
     const float4 cx = center_r[x], hx = half_ext[x];
@@ -1046,7 +1046,11 @@ static int read_counters(tr_world* w) {
 
 static int launch_side(tr_world* w, unsigned long long* out, uint64_t cap, unsigned long long* counter) {
     Collide* c = state(w);
-    dim3 grid((uint32_t)((w->n + 255) / 256), 64);
+    // rows of the launch loop over the side list with stride gridDim.y, so any row count is correct;
+    // last step's side count is the best guess for this one
+    uint32_t rows = c->last_side ? c->last_side : 1;
+    if (rows > 64) rows = 64;
+    dim3 grid((uint32_t)((w->n + 255) / 256), rows);
     side_kernel<<<grid, 256, 0, w->stream>>>(c->side_list, c->counters, w->center_r, w->half_ext, w->flags, c->klass,
                                              (uint32_t)w->n, out, cap, counter);
     TR_CUDA(cudaGetLastError());
