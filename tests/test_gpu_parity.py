@@ -143,7 +143,7 @@ def test_out_of_domain_bodies_use_side_list(tr, oracle):
     want = b.copy()
     oracle.step(want, oracle.default_params(), 2)
     got, contacts, st = gpu_run(tr, b, 2)
-    assert st.side_list_size >= 3
+    assert st.side_list_size >= 2      # the two far bodies; the NaN body is 'lost' (can never touch anything finite)
     for f in FIELDS:
         assert_bits_equal(got[f], want[f], f"domain:{f}")
     assert np.array_equal(contacts, oracle.contacts(want))

@@ -79,7 +79,7 @@ struct Collide {
     uint32_t* cell_count = nullptr;  // [ncell] histogram; self-cleaning (K3b counts it back to zero)
     uint32_t* cell_start = nullptr;  // [ncell+1] dense exclusive prefix
     uint32_t* side_list = nullptr;   // ids of side-list bodies
-    uint8_t* klass = nullptr;        // 0 dropped, 1 grid, 2 side
+    uint8_t* klass = nullptr;        // 0 dropped (mass<=0), 1 grid, 2 side list, 3 lost (non-finite centre)
     uint32_t* row_start = nullptr;   // [N+1] dense: contacts with i == body are [row_start[b], row_start[b+1])
     uint32_t* col_start = nullptr;   // [N+1] dense: column-order slots with j == body
     uint32_t* body_cnt = nullptr;    // [N] per-body histogram scratch (self-cleaning)
@@ -181,22 +181,30 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ ce
             float ux = __fmul_rn(__fsub_rn(c.x, g.ox), g.inv_cell);
             float uy = __fmul_rn(__fsub_rn(c.y, g.oy), g.inv_cell);
             float uz = __fmul_rn(__fsub_rn(c.z, g.oz), g.inv_cell);
-            bool in_domain = fabsf(ux) < 32768.0f && fabsf(uy) < 32768.0f && fabsf(uz) < 32768.0f;
-            bool grid_ok;
+            const bool in_domain = fabsf(ux) < 32768.0f && fabsf(uy) < 32768.0f && fabsf(uz) < 32768.0f;
+            const bool finite_c = fabsf(c.x) <= 3.0e38f && fabsf(c.y) <= 3.0e38f && fabsf(c.z) <= 3.0e38f;   // false for NaN / inf
+            bool fits;   // extent admitted to the grid
             if (g.mixed) {
                 // any body may meet a box, and box pairs use collider::size of BOTH bodies (main.cpp:704-705)
                 const float4 h = half_ext[i];
                 float ext = fmaxf(fmaxf(fabsf(h.x), fabsf(h.y)), fabsf(h.z));
-                const bool finite = fabsf(h.x) <= 3.0e38f && fabsf(h.y) <= 3.0e38f && fabsf(h.z) <= 3.0e38f;   // rejects NaN/inf
+                const bool finite_h = fabsf(h.x) <= 3.0e38f && fabsf(h.y) <= 3.0e38f && fabsf(h.z) <= 3.0e38f;
                 if (f & F_SPHERE) ext = fmaxf(ext, fabsf(c.w));
-                grid_ok = in_domain && finite && ext <= g.rmax_grid && (!(f & F_SPHERE) || fabsf(c.w) <= g.rmax_grid);
+                fits = finite_h && ext <= g.rmax_grid && (!(f & F_SPHERE) || fabsf(c.w) <= g.rmax_grid);
             } else {
-                grid_ok = (f & F_SPHERE) && in_domain && fabsf(c.w) <= g.rmax_grid;
+                fits = (f & F_SPHERE) && fabsf(c.w) <= g.rmax_grid;
             }
-            if (grid_ok) {
+            if (fits && in_domain) {
                 key = pack_key(__float2int_rd(ux), __float2int_rd(uy), __float2int_rd(uz), g.bits);
                 k = 1;
                 if (COUNT) atomicAdd(&cell_count[key], 1u);   // result unused: a fire-and-forget RED
+            } else if (fits && !finite_c && g.rmax_grid < 1.0e18f) {
+                // "lost": a NaN / infinite centre makes both predicates false (delta is +-inf or NaN)
+                // unless the radius / size SUM is itself infinite, i.e. the partner is an oversize
+                // side-list body.  Not a grid body, not a side-list body; side_kernel still tests it
+                // against every side-list body.  (Bodies the reference's inverted approach test blows
+                // up end here instead of turning the side list into an O(N^2) sweep.)
+                k = 3;
             } else {
                 k = 2;
                 uint32_t slot = atomicAdd(&counters[C_SIDE], 1u);
