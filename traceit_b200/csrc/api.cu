@@ -86,7 +86,7 @@ struct SoA {
 };
 
 // sig (optional): order-independent 64-bit hash of the fields the host-side grid classification
-// depends on (radius, isSphere, mass<=0), so a per-frame re-upload can tell whether it must redo it
+// depends on (radius, size, isSphere, mass<=0), so a per-frame re-upload can tell whether it must redo it
 __global__ void __launch_bounds__(256) unpack_kernel(const tr_body_desc* __restrict__ in, uint32_t first,
                                                      uint32_t count, SoA s, unsigned long long* sig) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(256) unpack_kernel(const tr_body_desc* __restr
         const tr_body_desc& q = in[t];
         unsigned long long x = ((unsigned long long)(first + t) << 32) ^ __float_as_uint(q.radius) ^
                                ((q.isSphere ? 1ull : 0ull) << 62) ^ ((q.mass <= 0 ? 1ull : 0ull) << 61);
+        x ^= ((unsigned long long)__float_as_uint(q.size[0]) << 7) ^ ((unsigned long long)__float_as_uint(q.size[1]) << 19) ^
+             ((unsigned long long)__float_as_uint(q.size[2]) << 29);
         x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
         h = x;
     }
@@ -727,6 +729,7 @@ int tr_step_host(tr_world* w, uint64_t n, tr_body_desc* bodies, int nsteps) {
             // grid classification reads, and redo it (otherwise the per-frame path skips it)
             for (uint64_t i = 0; i < n; ++i) {
                 w->host_bodies[i].radius = bodies[i].radius;
+                memcpy(w->host_bodies[i].size, bodies[i].size, sizeof(bodies[i].size));
                 w->host_bodies[i].isSphere = bodies[i].isSphere;
                 w->host_bodies[i].mass = bodies[i].mass;
             }
