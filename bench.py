@@ -391,11 +391,41 @@ def main():
     cpu = None
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
         try:
-            cpu = cpu_reference_step_rate(name, steps=8, warmup=1)
+            cpu = cpu_reference_step_rate(name, steps=12, warmup=1)
         except Exception as e:  # the baseline is a reported figure, never a reason to lose the GPU number
             cpu = {"value": None, "unit": "interactions/s", "cores": 1, "kind": "port", "sample": f"failed: {e}"}
 
     world.close()
+
+    # ---- secondary line (1 GPU, default workload only): BASELINE.json configs[1], the 64K gravity-only cloud
+    secondary = None
+    if world_size == 1 and args.workload is None and args.bodies is None:
+        try:
+            scfg = WORKLOADS["cfg2"]
+            sb = make_scene("cfg2", scfg["n"])
+            sp = tr.default_params(flags=tr.PAIR_GRAVITY, G=np.float32(GRAVITY_G), g=(0, 0, 0))
+            with tr.World(sp, device=local_rank) as w2:
+                w2.set_stream(stream.cuda_stream)
+                w2.add(sb)
+                w2.step(5)
+                ssteps = 40
+                sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ssteps)]
+                for k in range(ssteps):
+                    if flush_buf is not None:
+                        flush_buf.zero_()
+                    sev[k][0].record(stream)
+                    w2.step(1, sync=False)
+                    sev[k][1].record(stream)
+                w2.sync()
+                sms = sum(a.elapsed_time(b) for a, b in sev) / ssteps
+            sn = float(scfg["n"])
+            peak_ops2, _ = tr.measure_fma_peak(local_rank)
+            secondary = {"workload": f"cfg2: {scfg['desc']}", "n_bodies": scfg["n"], "steps": ssteps, "ms_per_step": sms,
+                         "value": sn * sn / (sms * 1e-3), "unit": "interactions/s", "steps_per_s": 1e3 / sms,
+                         "roofline_frac": sn * sn * LANE_OPS_PER_INTERACTION / (sms * 1e-3) / peak_ops2}
+        except Exception as e:   # never lose the headline over the secondary line
+            secondary = {"error": str(e)}
+
     if world_size > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -415,7 +445,7 @@ def main():
                                    "ordered pair visits the reference's O(N^2) sweep would make, N^2 per step "
                                    "(the grid broad phase prunes them; see collision_ms / steps_per_s for the physical cost)")},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-        "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
+        "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3, "secondary": secondary,
     }
     line.update(extra)
     print(json.dumps(line))
