@@ -87,7 +87,8 @@ def test_cloud_goldens_gpu(tr, name, steps):
 
 
 # ---------------------------------------------------------------- broad phase: keys, order, candidates
-@pytest.mark.parametrize("n,dens,bits", [(20000, 0.7, 0), (20000, 0.7, 3), (5000, 3.0, 2), (4096, 0.5, 6)])
+@pytest.mark.parametrize("n,dens,bits", [(20000, 0.7, 0), (20000, 0.7, 3), (5000, 3.0, 2), (4096, 0.5, 6),
+                                         (20000, 0.7, 8)])  # bits 8: 16M cells, the streamed-span variant of the fused scan
 def test_grid_keys_sort_candidates_bit_exact(tr, oracle, n, dens, bits):
     b = scenes.random_cloud(n, 100 + bits, spheres=True, density_l=dens)
     b["radius"] = np.random.RandomState(bits).uniform(0.2, 0.5, n).astype(np.float32)

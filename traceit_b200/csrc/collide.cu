@@ -30,6 +30,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -965,7 +967,8 @@ static int ensure_buffers(tr_world* w) {
     return TR_OK;
 }
 
-static int launch_fast_broad(tr_world* w, cudaStream_t st) {
+// `ev` (debug, TR_BP_PROFILE=1): 6 events recorded around the five kernels
+static int launch_fast_broad(tr_world* w, cudaStream_t st, cudaEvent_t* ev = nullptr) {
     Collide* c = state(w);
     const uint32_t n = (uint32_t)w->n;
     const uint32_t blocks = (n + 255) / 256;
@@ -973,13 +976,19 @@ static int launch_fast_broad(tr_world* w, cudaStream_t st) {
     const uint32_t ntiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
     GridParams g{c->origin[0], c->origin[1], c->origin[2], c->inv_cell, c->rmax_grid, c->bits, c->mixed ? 1 : 0};
     TR_CUDA(cudaMemsetAsync(c->counters, 0, C_NCOUNTERS * sizeof(uint32_t), st));
+    if (ev) cudaEventRecord(ev[0], st);
     keys_kernel<true><<<blocks, 256, 0, st>>>(w->center_r, w->half_ext, w->flags, n, g, c->keys, c->vals, c->klass, c->side_list,
                                               c->cell_count, c->counters);
+    if (ev) cudaEventRecord(ev[1], st);
     tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, ncell, c->tile_sum, c->counters, OCC_LIMIT);
+    if (ev) cudaEventRecord(ev[2], st);
     scan_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, c->tile_sum, c->cell_start, ncell, c->counters, C_GRID);
+    if (ev) cudaEventRecord(ev[3], st);
     scatter_kernel<<<blocks, 256, 0, st>>>(c->keys, ncell, w->flags, n, c->cell_start, c->cell_count, c->tmp_ids);
+    if (ev) cudaEventRecord(ev[4], st);
     rank_gather_kernel<<<blocks, 256, 0, st>>>(c->tmp_ids, c->cell_start, w->center_r, c->mixed ? w->half_ext : nullptr,
                                                c->counters, c->keys_sorted, c->vals_sorted, c->sorted_center_r, c->sorted_half_ext);
+    if (ev) cudaEventRecord(ev[5], st);
     TR_CUDA(cudaGetLastError());
     return TR_OK;
 }
@@ -991,7 +1000,23 @@ static int broad_phase(tr_world* w) {
     const uint32_t blocks = (n + 255) / 256;
     const uint32_t ncell = 1u << (3 * c->bits);
     PendingTimer t;
-    if (!c->use_cub && w->stream == nullptr) {
+    static const bool bp_profile = getenv("TR_BP_PROFILE") != nullptr;
+    if (!c->use_cub && bp_profile) {
+        // debug: plain launches with an event between the kernels, per-kernel times to stderr
+        // (event gaps include the launch gap a graph does not have: ~2 us per kernel)
+        cudaEvent_t ev[6];
+        for (auto& e : ev) TR_CUDA(cudaEventCreate(&e));
+        timer_begin(w, T_BROAD, &t);
+        TR_TRY(launch_fast_broad(w, w->stream, ev));
+        timer_end(w, &t);
+        TR_CUDA(cudaEventSynchronize(ev[5]));
+        float ms[5];
+        for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
+        fprintf(stderr, "[TR_BP_PROFILE] n=%u keys %.1f us, tile sums %.1f us, scan %.1f us, scatter %.1f us, rank+gather %.1f us\n", n,
+                ms[0] * 1e3f, ms[1] * 1e3f, ms[2] * 1e3f, ms[3] * 1e3f, ms[4] * 1e3f);
+        for (auto& e : ev) cudaEventDestroy(e);
+        w->stats.kernel_launches += 5;
+    } else if (!c->use_cub && w->stream == nullptr) {
         // the legacy default stream cannot be captured: plain launches
         timer_begin(w, T_BROAD, &t);
         TR_TRY(launch_fast_broad(w, w->stream));
