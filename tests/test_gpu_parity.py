@@ -150,6 +150,40 @@ def test_out_of_domain_bodies_use_side_list(tr, oracle):
     assert np.array_equal(contacts, oracle.contacts(want))
 
 
+def test_far_bodies_meet_each_other_and_the_domain_boundary(tr, oracle):
+    """Bodies outside the grid domain (|centre - origin| / cell >= 32768) are tested against each
+    other and against the grid bodies next to the domain boundary only; the contact set and the
+    response must still equal the reference's O(N^2) sweep."""
+    b = scenes.random_cloud(3000, 78, spheres=True, density_l=0.6)
+    cell = np.float32(np.float32(2.0 * 0.5) * np.float32(1.0078125))
+    edge = float(cell) * 32768.0
+    k = 100
+    for axis, sign in ((0, 1), (1, -1), (2, 1)):
+        for d_in, d_out in ((0.45, 0.40), (0.2, 0.7), (1.6, 0.1)):   # touching, touching, apart
+            p_in = np.zeros(3, np.float32); p_out = np.zeros(3, np.float32)
+            p_in[axis] = sign * (edge - d_in); p_out[axis] = sign * (edge + d_out)
+            b["pos"][k] = p_in; b["pos"][k + 1] = p_out
+            k += 2
+    # a far cluster: chain of touching spheres, one static pair, one box
+    for q in range(12):
+        b["pos"][k + q] = (2.0e5 + 0.75 * q, -3.0e5, 0.5 * (q % 2))
+    b["isStatic"][k + 3] = 1; b["isStatic"][k + 4] = 1
+    b["isSphere"][k + 7] = 0
+    b["center"] = b["pos"]
+    for steps in (1, 3):
+        want = b.copy()
+        oracle.step(want, oracle.default_params(), steps)
+        got, contacts, st = gpu_run(tr, b.copy(), steps)
+        assert st.side_list_size == 9 + 12 if steps == 1 else st.side_list_size >= 12   # the response moves boundary bodies in and out
+        oc = oracle.contacts(want)
+        assert np.array_equal(contacts, oc)
+        if steps == 1:   # both kinds of pair are really there
+            assert any(100 <= i < 118 and 100 <= j < 118 for i, j in oc), "boundary pairs"
+            assert any(118 <= i < 130 and 118 <= j < 130 for i, j in oc), "far-far pairs"
+        for f in FIELDS:
+            assert_bits_equal(got[f], want[f], f"far:{f}")
+
+
 # ---------------------------------------------------------------- response order
 @pytest.mark.parametrize("mode", [0, 1])
 def test_dense_lattice_response_bit_exact(tr, oracle, mode):

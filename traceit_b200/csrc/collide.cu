@@ -17,7 +17,9 @@
 //   (fallback for pathological occupancy: CUB radix sort + binary-search cell table.)
 //   K5  narrow_kernel        half of the 27-cell stencil (each pair reached once) as 5 contiguous
 //                            key ranges, exact reference predicate (no FMA contraction).
-//   K5b side_kernel          every side-list body against every live body.
+//   K5b side_kernel          every side-list body (oversize / non-finite extent) against every live body.
+//   K5c far_kernel           bodies outside the grid domain against each other and against the
+//                            grid bodies next to the domain boundary.
 //   K6  ordered response     contacts counting-sorted into (i,j) and (j,i) order give each contact
 //                            its two predecessors / successors; the executor replays the
 //                            reference's Gauss-Seidel order exactly: a contact runs when
@@ -52,7 +54,7 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 // counters[] slots
 enum { C_SIDE = 0, C_GRID = 1, C_CONTACTS = 2 /*u64*/, C_CAND = 4 /*u64*/, C_MAXOCC = 6, C_FRONT = 8 /*3*/, C_ROUNDS = 11,
-       C_QHEAD = 12, C_QTAIL = 13, C_DONE = 14, C_ABORT = 15, C_NCOUNTERS = 16 };
+       C_QHEAD = 12, C_QTAIL = 13, C_DONE = 14, C_ABORT = 15, C_FAR = 16, C_BND = 17, C_NCOUNTERS = 24 };
 
 }  // namespace tr
 
@@ -80,8 +82,12 @@ struct Collide {
     float4* sorted_half_ext = nullptr;   // gathered only in mixed worlds
     uint32_t* cell_count = nullptr;  // [ncell] histogram; self-cleaning (K3b counts it back to zero)
     uint32_t* cell_start = nullptr;  // [ncell+1] dense exclusive prefix
-    uint32_t* side_list = nullptr;   // ids of side-list bodies
-    uint8_t* klass = nullptr;        // 0 dropped (mass<=0), 1 grid, 2 side list, 3 lost (non-finite centre)
+    uint32_t* side_list = nullptr;   // ids of side-list bodies (oversize / non-finite extent): tested against everyone
+    uint32_t* far_list = nullptr;    // id|flags of normal-extent bodies outside the grid domain (finite centre)
+    uint32_t* bnd_list = nullptr;    // id|flags of grid bodies within two cells of the domain boundary
+    float4* far_c = nullptr;         // their collider centres, same slots
+    float4* bnd_c = nullptr;
+    uint8_t* klass = nullptr;        // 0 dropped (mass<=0), 1 grid, 2 side list, 3 lost (non-finite centre), 4 far
     uint32_t* row_start = nullptr;   // [N+1] dense: contacts with i == body are [row_start[b], row_start[b+1])
     uint32_t* col_start = nullptr;   // [N+1] dense: column-order slots with j == body
     uint32_t* body_cnt = nullptr;    // [N] per-body histogram scratch (self-cleaning)
@@ -115,6 +121,8 @@ struct Collide {
     uint64_t last_contacts = 0;
     uint64_t last_grid = 0;
     uint32_t last_side = 0;
+    uint32_t last_far = 0;        // far / boundary list sizes of the previous step (launch sizing)
+    uint32_t last_bnd = 0;
     int coop_blocks = 0;
 };
 
@@ -165,6 +173,8 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ ce
                                                    const uint8_t* __restrict__ flags, uint32_t n, GridParams g,
                                                    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                                    uint8_t* __restrict__ klass, uint32_t* __restrict__ side_list,
+                                                   uint32_t* __restrict__ far_list, float4* __restrict__ far_c,
+                                                   uint32_t* __restrict__ bnd_list, float4* __restrict__ bnd_c,
                                                    uint32_t* __restrict__ cell_count, uint32_t* counters) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (COUNT) {
@@ -200,7 +210,21 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ ce
                 key = pack_key(__float2int_rd(ux), __float2int_rd(uy), __float2int_rd(uz), g.bits);
                 k = 1;
                 if (COUNT) atomicAdd(&cell_count[key], 1u);   // result unused: a fire-and-forget RED
-            } else if (fits && !finite_c && g.rmax_grid < 1.0e18f) {
+                // grid bodies within two cells of the domain boundary are the only ones a "far" body can touch
+                if (fmaxf(fmaxf(fabsf(ux), fabsf(uy)), fabsf(uz)) >= 32766.0f) {
+                    const uint32_t slot = atomicAdd(&counters[C_BND], 1u);
+                    bnd_list[slot] = pack_val(i, f);
+                    bnd_c[slot] = c;
+                }
+            } else if (fits && finite_c) {
+                // "far": normal extent, finite centre, outside the grid domain.  It can only touch other
+                // far bodies, boundary grid bodies (computed |u| differs by >= 2 cells from everyone else:
+                // more than the largest admitted reach) and oversize side-list bodies.
+                k = 4;
+                const uint32_t slot = atomicAdd(&counters[C_FAR], 1u);
+                far_list[slot] = pack_val(i, f);
+                far_c[slot] = c;
+            } else if (fits && g.rmax_grid < 1.0e18f) {
                 // "lost": a NaN / infinite centre makes both predicates false (delta is +-inf or NaN)
                 // unless the radius / size SUM is itself infinite, i.e. the partner is an oversize
                 // side-list body.  Not a grid body, not a side-list body; side_kernel still tests it
@@ -504,6 +528,38 @@ __global__ void __launch_bounds__(256) side_kernel(const uint32_t* __restrict__ 
         if ((fx & F_SPHERE) && (fs & F_SPHERE)) hit = sphere_hit(cx, cs);
         else hit = aabb_hit(cx, hx, cs, half_ext[s]);
         if (hit) emit_pair(out, cap, counter, min(x, s), max(x, s));
+    }
+}
+
+// K5c: "far" bodies (normal extent, finite centre, outside the grid domain |u| < 32768) against each
+// other and against the grid bodies within two cells of the domain boundary; side_kernel covers
+// far-vs-oversize.  A contact implies |delta u| < 1 per axis (cell = 2*rmax*(1+2^-7)) and computed
+// u carries < 0.01 of error at that magnitude, so a grid body that touches a far body has
+// |u| > 32766 on that axis: nobody else needs testing.  Thread = far body (grid-stride), rows
+// (gridDim.y) stride over the partner list, so any launch geometry is correct.
+// Both lists carry id|flags (pack_val) and a compact copy of the centres, so the partner loop
+// streams consecutive 16-byte entries instead of gathering by id.
+__global__ void __launch_bounds__(256) far_kernel(const uint32_t* __restrict__ far_list, const float4* __restrict__ far_c,
+                                                  const uint32_t* __restrict__ bnd_list, const float4* __restrict__ bnd_c,
+                                                  const uint32_t* __restrict__ counters, const float4* __restrict__ half_ext,
+                                                  unsigned long long* out, unsigned long long cap, unsigned long long* counter) {
+    const uint32_t nfar = counters[C_FAR], nbnd = counters[C_BND];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nfar; t += gridDim.x * blockDim.x) {
+        const uint32_t va = far_list[t];
+        const uint32_t a = va & ID_MASK;
+        const float4 ca = far_c[t];
+        // partners: far bodies later in the list, then every boundary grid body
+        for (uint32_t k = t + 1 + blockIdx.y; k < nfar + nbnd; k += gridDim.y) {
+            const bool kf = k < nfar;
+            const uint32_t vb = kf ? far_list[k] : bnd_list[k - nfar];
+            if (va & vb & STATIC_BIT) continue;                      // main.cpp:695
+            const float4 cb = kf ? far_c[k] : bnd_c[k - nfar];
+            const uint32_t b = vb & ID_MASK;
+            bool hit;
+            if ((va | vb) & BOX_BIT) hit = aabb_hit(ca, half_ext[a], cb, half_ext[b]);   // main.cpp:704
+            else hit = sphere_hit(ca, cb);                                               // main.cpp:702
+            if (hit) emit_pair(out, cap, counter, min(a, b), max(a, b));
+        }
     }
 }
 
@@ -910,6 +966,10 @@ static int ensure_buffers(tr_world* w) {
         TR_TRY(realloc_dev(&c->sorted_center_r, cap));
         TR_TRY(realloc_dev(&c->sorted_half_ext, cap));
         TR_TRY(realloc_dev(&c->side_list, cap));
+        TR_TRY(realloc_dev(&c->far_list, cap));
+        TR_TRY(realloc_dev(&c->bnd_list, cap));
+        TR_TRY(realloc_dev(&c->far_c, cap));
+        TR_TRY(realloc_dev(&c->bnd_c, cap));
         TR_TRY(realloc_dev(&c->klass, cap));
         TR_TRY(realloc_dev(&c->row_start, cap + 1));
         TR_TRY(realloc_dev(&c->col_start, cap + 1));
@@ -978,7 +1038,7 @@ static int launch_fast_broad(tr_world* w, cudaStream_t st, cudaEvent_t* ev = nul
     TR_CUDA(cudaMemsetAsync(c->counters, 0, C_NCOUNTERS * sizeof(uint32_t), st));
     if (ev) cudaEventRecord(ev[0], st);
     keys_kernel<true><<<blocks, 256, 0, st>>>(w->center_r, w->half_ext, w->flags, n, g, c->keys, c->vals, c->klass, c->side_list,
-                                              c->cell_count, c->counters);
+                                              c->far_list, c->far_c, c->bnd_list, c->bnd_c, c->cell_count, c->counters);
     if (ev) cudaEventRecord(ev[1], st);
     tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, ncell, c->tile_sum, c->counters, OCC_LIMIT);
     if (ev) cudaEventRecord(ev[2], st);
@@ -1056,7 +1116,7 @@ static int broad_phase(tr_world* w) {
         timer_begin(w, T_BROAD, &t);
         TR_CUDA(cudaMemsetAsync(c->counters, 0, C_NCOUNTERS * sizeof(uint32_t), w->stream));
         keys_kernel<false><<<blocks, 256, 0, w->stream>>>(w->center_r, w->half_ext, w->flags, n, g, c->keys, c->vals, c->klass, c->side_list,
-                                                          c->cell_count, c->counters);
+                                                          c->far_list, c->far_c, c->bnd_list, c->bnd_c, c->cell_count, c->counters);
         size_t tmp = c->cub_tmp_bytes;
         TR_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, c->keys, c->keys_sorted, c->vals, c->vals_sorted, n, 0,
                                                 3 * c->bits + 1, w->stream));
@@ -1091,6 +1151,22 @@ static int launch_side(tr_world* w, unsigned long long* out, uint64_t cap, unsig
     return TR_OK;
 }
 
+static int launch_far(tr_world* w, unsigned long long* out, uint64_t cap, unsigned long long* counter) {
+    Collide* c = state(w);
+    // sized from the previous step's counts; the kernel strides, so any geometry is correct
+    uint32_t gx = (c->last_far + 255) / 256;
+    if (gx < 1) gx = 1;
+    if (gx > 1024) gx = 1024;
+    uint32_t gy = (c->last_far + c->last_bnd + 255) / 256;
+    if (gy < 1) gy = 1;
+    if (gy > 64) gy = 64;
+    far_kernel<<<dim3(gx, gy), 256, 0, w->stream>>>(c->far_list, c->far_c, c->bnd_list, c->bnd_c, c->counters, w->half_ext, out, cap,
+                                                    counter);
+    TR_CUDA(cudaGetLastError());
+    w->stats.kernel_launches += 1;
+    return TR_OK;
+}
+
 // Detection: broad phase + narrow phase + side list, ONE host read-back at the end.  On return
 // the UNSORTED pairs are in `out` and *count is their number (may exceed cap => overflow).
 template <bool CANDIDATES>
@@ -1113,6 +1189,8 @@ static int detect(tr_world* w, unsigned long long* out, uint64_t cap, uint64_t* 
         w->stats.kernel_launches += 1;
         const bool side_launched = c->may_have_side && !CANDIDATES;
         if (side_launched) TR_TRY(launch_side(w, out, cap, counter));
+        const bool far_launched = c->last_far > 0 && !CANDIDATES;
+        if (far_launched) TR_TRY(launch_far(w, out, cap, counter));
         timer_end(w, &t);
         TR_CUDA(cudaGetLastError());
         TR_TRY(read_counters(w));
@@ -1122,15 +1200,26 @@ static int detect(tr_world* w, unsigned long long* out, uint64_t cap, uint64_t* 
             c->use_cub = true;
             continue;
         }
+        bool again = false;
         if (!CANDIDATES && !side_launched && c->h_counters[C_SIDE] > 0) {
-            // bodies left the grid domain at run time: test them now (rare path, one more read-back)
+            // a body's extent became oversize / non-finite at run time: test it now (rare path, one more read-back)
             c->may_have_side = true;
             TR_TRY(launch_side(w, out, cap, counter));
-            TR_TRY(read_counters(w));
+            again = true;
         }
+        if (!CANDIDATES && !far_launched && c->h_counters[C_FAR] > 0) {
+            // bodies left the grid domain at run time: first step with a far list
+            c->last_far = c->h_counters[C_FAR];
+            c->last_bnd = c->h_counters[C_BND];
+            TR_TRY(launch_far(w, out, cap, counter));
+            again = true;
+        }
+        if (again) TR_TRY(read_counters(w));
         break;
     }
     c->last_side = c->h_counters[C_SIDE];
+    c->last_far = c->h_counters[C_FAR];
+    c->last_bnd = c->h_counters[C_BND];
     c->last_grid = c->h_counters[C_GRID];
     const int k = CANDIDATES ? C_CAND : C_CONTACTS;
     *count = ((uint64_t)c->h_counters[k + 1] << 32) | c->h_counters[k];
@@ -1161,7 +1250,7 @@ int collide_step(tr_world* w) {
     Collide* c = state(w);
     uint64_t count = 0;
     TR_TRY(detect<false>(w, c->ckeys, c->cap_contacts, &count));
-    w->stats.side_list_size = c->last_side;
+    w->stats.side_list_size = c->last_side + c->last_far;   // everything outside the grid: oversize list + far list
     w->stats.last_contacts = count;
     c->last_contacts = 0;
     if (count > c->cap_contacts) {
@@ -1326,7 +1415,7 @@ int collide_free(tr_world* w) {
     if (!c) return TR_OK;
     cudaFree(c->keys); cudaFree(c->keys_sorted); cudaFree(c->vals); cudaFree(c->vals_sorted); cudaFree(c->tmp_ids);
     cudaFree(c->sorted_center_r); cudaFree(c->sorted_half_ext); cudaFree(c->cell_start); cudaFree(c->cell_count); cudaFree(c->tile_sum);
-    cudaFree(c->side_list); cudaFree(c->klass);
+    cudaFree(c->side_list); cudaFree(c->far_list); cudaFree(c->bnd_list); cudaFree(c->far_c); cudaFree(c->bnd_c); cudaFree(c->klass);
     cudaFree(c->row_start); cudaFree(c->col_start); cudaFree(c->body_cnt); cudaFree(c->counters);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_rounds) cudaFreeHost(c->h_rounds);
