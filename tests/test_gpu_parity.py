@@ -393,10 +393,9 @@ def test_full_size_1m_properties(tr, oracle):
         assert mine == {(min(i, j), max(i, j)) for j in hit.tolist()}
 
 
-def test_crowded_cell_falls_back_to_radix_sort(tr, oracle):
-    """More bodies in one cell than the quadratic rank step accepts (OCC_LIMIT = 1024): the
-    broad phase must switch to its radix-sort fallback and still produce the exact keys, order,
-    candidates and contact set."""
+def test_crowded_cell(tr, oracle):
+    """1500 bodies in ONE cell (over a million contacts): the counting sort, the on-demand stable
+    order and the narrow phase must still produce the exact keys, order, candidates and contact set."""
     n = 6000
     b = scenes.random_cloud(n, 5150, spheres=True, density_l=0.8)
     rs = np.random.RandomState(3)

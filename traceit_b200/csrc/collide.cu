@@ -5,16 +5,18 @@
 // Gauss-Seidel impulse + positional nudge (src/main.cpp:709-742).
 //
 // Broad phase = ONE-DIGIT radix sort of the wrapped cell keys (radix = number of cells):
-//   K2  keys_count_kernel    one thread per body: cell key from the collider centre, per-cell
-//                            histogram by atomics; bodies that cannot live in the grid (boxes,
-//                            oversize / out-of-domain spheres) go to a side list; mass<=0
+//   K2  keys_kernel          one thread per body: cell key from the collider centre, per-cell
+//                            histogram by atomics; bodies that cannot live in the grid (oversize,
+//                            out-of-domain, non-finite) go to the side / far lists; mass<=0
 //                            bodies are dropped (they can never collide, main.cpp:696).
 //   K3a tile_sums + scan     exclusive scan of the histogram in two unchained kernels
 //                            -> dense cell_start[ncell+1] table.
-//   K3b scatter_kernel       body ids into their cell's segment (arrival order).
-//   K4  rank_gather_kernel   rank of each id inside its cell (ascending id) -> the stable
-//                            (key,id) order; collider centres gathered into that order.
-//   (fallback for pathological occupancy: CUB radix sort + binary-search cell table.)
+//   K3b scatter_kernel       one 32-byte record per body (centre+radius, id|flags, half extents)
+//                            into its cell's segment: the bodies in cell order.  Inside a cell
+//                            the records are in arrival order; nothing downstream depends on it
+//                            (pairs are reported as (min id, max id) and re-sorted for K6).
+//   K4  canon_kernel         ON DEMAND (tr_debug_grid): the stable (key,id) order - rank of each id
+//                            inside its cell - as the list of sorted ids.
 //   K5  narrow_kernel        half of the 27-cell stencil (each pair reached once) as 5 contiguous
 //                            key ranges, exact reference predicate (no FMA contraction).
 //   K5b side_kernel          every side-list body (oversize / non-finite extent) against every live body.
@@ -35,7 +37,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <cub/device/device_radix_sort.cuh>
 
 #include "world.cuh"
 
@@ -47,13 +48,12 @@ constexpr uint32_t EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t ID_MASK = 0x3FFFFFFFu;      // body ids fit 30 bits (tr_bodies_add enforces it)
 constexpr uint32_t STATIC_BIT = 0x80000000u;   // collider::isStatic
 constexpr uint32_t BOX_BIT = 0x40000000u;      // !collider::isSphere: pairs with it use the AABB predicate
-constexpr uint32_t OCC_LIMIT = 1024;      // bodies per cell above which the O(occ^2) rank step is refused
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 // counters[] slots
-enum { C_SIDE = 0, C_GRID = 1, C_CONTACTS = 2 /*u64*/, C_CAND = 4 /*u64*/, C_MAXOCC = 6, C_FRONT = 8 /*3*/, C_ROUNDS = 11,
+enum { C_SIDE = 0, C_GRID = 1, C_CONTACTS = 2 /*u64*/, C_CAND = 4 /*u64*/, C_FRONT = 8 /*3*/, C_ROUNDS = 11,
        C_QHEAD = 12, C_QTAIL = 13, C_DONE = 14, C_ABORT = 15, C_FAR = 16, C_BND = 17, C_NCOUNTERS = 24 };
 
 }  // namespace tr
@@ -65,21 +65,16 @@ struct Collide {
     int bits = 2;
     bool may_have_side = true;    // some body is statically outside the grid (oversize / NaN extent)
     bool mixed = false;           // live boxes exist: they share the grid, extents include collider::size
-    bool use_cub = false;         // occupancy fallback engaged
     uint64_t cap_bodies = 0;      // arrays below sized for this many bodies
     uint64_t ncell_alloc = 0;
     uint64_t cap_contacts = 0;
 
     // per body
     uint32_t* keys = nullptr;        // K2 out: key, or sentinel 1<<(3*bits) for non-grid bodies
-    uint32_t* keys_sorted = nullptr;
-    uint32_t* vals = nullptr;        // fallback path: id | static<<31
-    uint32_t* vals_sorted = nullptr; // id | static<<31 in (key,id) order
-    uint2* tmp_ids = nullptr;        // K3b out: (id|static, key) grouped by cell, arrival order
+    struct tr_slot_rec* recs = nullptr;   // K3b out: tr::SlotRec per grid body, grouped by cell (arrival order inside a cell)
+    uint32_t* sorted_ids = nullptr;  // K4 (on demand): ids in the stable (key,id) order
     uint32_t* tile_sum = nullptr;    // scan: per-tile histogram sums
     uint64_t tile_sum_cap = 0;
-    float4* sorted_center_r = nullptr;
-    float4* sorted_half_ext = nullptr;   // gathered only in mixed worlds
     uint32_t* cell_count = nullptr;  // [ncell] histogram; self-cleaning (K3b counts it back to zero)
     uint32_t* cell_start = nullptr;  // [ncell+1] dense exclusive prefix
     uint32_t* side_list = nullptr;   // ids of side-list bodies (oversize / non-finite extent): tested against everyone
@@ -110,10 +105,7 @@ struct Collide {
     uint4* crec = nullptr;                    // packed {i, j, succ_i, succ_j} per contact (dataflow executor)
     uint32_t* frontier[2] = {nullptr, nullptr};
 
-    void* cub_tmp = nullptr;
-    size_t cub_tmp_bytes = 0;
-
-    // K2-K4 as one CUDA graph (memset + 5 kernels): launch parameters only change when the
+    // K2-K3b as one CUDA graph (memset + 4 kernels): launch parameters only change when the
     // buffers, the grid or the body count change, so the graph is re-captured only then
     cudaGraphExec_t bp_graph = nullptr;
     uint64_t bp_sig[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -168,16 +160,15 @@ __device__ __forceinline__ uint32_t pack_val(uint32_t id, uint8_t f) {
 // ---------------------------------------------------------------------------------------
 // K2: keys + classification (+ per-cell histogram on the fast path)
 // ---------------------------------------------------------------------------------------
-template <bool COUNT>
 __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ center_r, const float4* __restrict__ half_ext,
                                                    const uint8_t* __restrict__ flags, uint32_t n, GridParams g,
-                                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                   uint32_t* __restrict__ keys,
                                                    uint8_t* __restrict__ klass, uint32_t* __restrict__ side_list,
                                                    uint32_t* __restrict__ far_list, float4* __restrict__ far_c,
                                                    uint32_t* __restrict__ bnd_list, float4* __restrict__ bnd_c,
                                                    uint32_t* __restrict__ cell_count, uint32_t* counters) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (COUNT) {
+    {
         // stream the (zeroed) histogram into L2 ahead of the scattered REDs: one 128-byte line per
         // thread of the leading CTAs, so random cloud ids do not pay a DRAM round trip per atomic
         const uint32_t ncell = 1u << (3 * g.bits);
@@ -209,7 +200,7 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ ce
             if (fits && in_domain) {
                 key = pack_key(__float2int_rd(ux), __float2int_rd(uy), __float2int_rd(uz), g.bits);
                 k = 1;
-                if (COUNT) atomicAdd(&cell_count[key], 1u);   // result unused: a fire-and-forget RED
+                atomicAdd(&cell_count[key], 1u);   // result unused: a fire-and-forget RED
                 // grid bodies within two cells of the domain boundary are the only ones a "far" body can touch
                 if (fmaxf(fmaxf(fabsf(ux), fabsf(uy)), fabsf(uz)) >= 32766.0f) {
                     const uint32_t slot = atomicAdd(&counters[C_BND], 1u);
@@ -238,7 +229,6 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ ce
             }
         }
         keys[i] = key;
-        if (!COUNT) vals[i] = pack_val(i, f);
         klass[i] = k;
     }
 }
@@ -246,7 +236,7 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ ce
 // ---------------------------------------------------------------------------------------
 // K3a: exclusive scan of the histogram in two unchained kernels (a look-back chain over
 // ~1000 tiles costs more in latency than the second launch):
-//   tile_sums_kernel   one CTA per tile of 2048 cells -> tile_sum[tile], and the occupancy guard
+//   tile_sums_kernel   one CTA per tile of 2048 cells -> tile_sum[tile]
 //   scan_kernel        each CTA adds up the sums of the tiles before it (<= 4 KB, L2 hits),
 //                      scans its own tile and writes the dense cell_start table.
 // ---------------------------------------------------------------------------------------
@@ -263,21 +253,14 @@ __device__ __forceinline__ void load_tile_items(const uint32_t* __restrict__ cel
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) tile_sums_kernel(const uint32_t* __restrict__ cell_count, uint32_t ncell,
-                                                                 uint32_t* __restrict__ tile_sum, uint32_t* counters,
-                                                                 uint32_t occ_limit) {
+                                                                 uint32_t* __restrict__ tile_sum) {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     uint32_t v[SCAN_ITEMS];
     load_tile_items(cell_count, blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS, ncell, v);
-    uint32_t tsum = 0, vmax = 0;
+    uint32_t tsum = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        tsum += v[k];
-        vmax = max(vmax, v[k]);
-    }
+    for (int k = 0; k < SCAN_ITEMS; ++k) tsum += v[k];
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    // largest cell population guards the O(occ^2) rank step; almost never above a handful
-    vmax = __reduce_max_sync(0xFFFFFFFFu, vmax);
-    if (lane == 0 && vmax > occ_limit) atomicMax(&counters[C_MAXOCC], vmax);
     tsum = __reduce_add_sync(0xFFFFFFFFu, tsum);
     if (lane == 0) s_warp[wid] = tsum;
     __syncthreads();
@@ -353,65 +336,71 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const uint32_t* __re
     }
 }
 
-// K3b: (id|static, key) into the cell's segment; counting the histogram back down leaves it
-// zeroed for the next step.
+// K3b: one record per grid body into its cell's segment; counting the histogram back down leaves it
+// zeroed for the next step.  The record carries everything the narrow phase reads about a body -
+// centre + radius, id|flags, AABB half extents - in ONE 32-byte sector written by one 256-bit store
+// (SASS STG.E.ENL2.256) and read back by one 256-bit load, so nothing is gathered by id afterwards.
+struct __align__(32) SlotRec {
+    float4 c;              // collider centre, radius
+    uint32_t val;          // id | BOX_BIT | STATIC_BIT
+    float hx, hy, hz;      // collider::size (meaningful in mixed worlds only)
+};
+static_assert(sizeof(SlotRec) == 32, "one sector");
+
+__device__ __forceinline__ void st_rec(SlotRec* p, const float4 c, uint32_t val, const float4 h) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(__float_as_uint(c.x)), "r"(__float_as_uint(c.y)),
+                 "r"(__float_as_uint(c.z)), "r"(__float_as_uint(c.w)), "r"(val), "r"(__float_as_uint(h.x)),
+                 "r"(__float_as_uint(h.y)), "r"(__float_as_uint(h.z))
+                 : "memory");
+}
+__device__ __forceinline__ void ld_rec(const SlotRec* p, float4& c, uint32_t& val, float4& h) {
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+                 : "l"(p));
+    c = make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3));
+    val = r4;
+    h = make_float4(__uint_as_float(r5), __uint_as_float(r6), __uint_as_float(r7), 0.f);
+}
+
+// the key of an in-domain centre: the same operations as K2, hence the same key
+__device__ __forceinline__ uint32_t cell_key(const float4 c, const GridParams& g) {
+    const float ux = __fmul_rn(__fsub_rn(c.x, g.ox), g.inv_cell);
+    const float uy = __fmul_rn(__fsub_rn(c.y, g.oy), g.inv_cell);
+    const float uz = __fmul_rn(__fsub_rn(c.z, g.oz), g.inv_cell);
+    return pack_key(__float2int_rd(ux), __float2int_rd(uy), __float2int_rd(uz), g.bits);
+}
+
 __global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict__ keys, uint32_t sentinel,
-                                                      const uint8_t* __restrict__ flags, uint32_t n,
-                                                      const uint32_t* __restrict__ cell_start,
-                                                      uint32_t* __restrict__ cell_count, uint2* __restrict__ tmp) {
+                                                      const uint8_t* __restrict__ flags, const float4* __restrict__ center_r,
+                                                      const float4* __restrict__ half_ext,   // NULL unless boxes are in the grid
+                                                      uint32_t n, const uint32_t* __restrict__ cell_start,
+                                                      uint32_t* __restrict__ cell_count, SlotRec* __restrict__ recs) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t key = keys[i];
-    if (key >= sentinel) return;          // side-list or dropped body
+    if (key >= sentinel) return;          // side-list, far, lost or dropped body
+    const float4 c = center_r[i];
+    float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (half_ext) h = half_ext[i];
+    const uint32_t val = pack_val(i, flags[i]);
     const uint32_t old = atomicSub(&cell_count[key], 1u);
-    tmp[cell_start[key] + old - 1u] = make_uint2(pack_val(i, flags[i]), key);
+    st_rec(recs + (cell_start[key] + old - 1u), c, val, h);
 }
 
-// K4: deterministic order inside each cell (ascending id) + gather to sorted order.
-__global__ void __launch_bounds__(256) rank_gather_kernel(const uint2* __restrict__ tmp, const uint32_t* __restrict__ cell_start,
-                                                          const float4* __restrict__ center_r,
-                                                          const float4* __restrict__ half_ext,   // NULL unless boxes are in the grid
-                                                          const uint32_t* __restrict__ counters,
-                                                          uint32_t* __restrict__ keys_sorted, uint32_t* __restrict__ vals_sorted,
-                                                          float4* __restrict__ sorted_center_r,
-                                                          float4* __restrict__ sorted_half_ext) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= counters[C_GRID] || counters[C_MAXOCC] > OCC_LIMIT) return;
-    const uint2 me = tmp[t];
-    const uint32_t id = me.x & ID_MASK;
-    const float4 c = center_r[id];                        // issue the gather before the rank loop
-    const uint32_t s = cell_start[me.y], e = cell_start[me.y + 1];
-    uint32_t rank = 0;
-    for (uint32_t u = s; u < e; ++u) rank += ((tmp[u].x & ID_MASK) < id) ? 1u : 0u;
-    const uint32_t f = s + rank;
-    keys_sorted[f] = me.y;
-    vals_sorted[f] = me.x;
-    sorted_center_r[f] = c;
-    if (half_ext) sorted_half_ext[f] = half_ext[id];
-}
-
-// ---- fallback path (cell population above OCC_LIMIT): CUB radix sort, then the same tables ----
-__global__ void __launch_bounds__(256) dense_start_kernel(const uint32_t* __restrict__ keys_sorted, uint32_t n, uint32_t ncell,
-                                                          uint32_t* __restrict__ cell_start, uint32_t* counters) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k > ncell) return;
-    uint32_t lo = 0, hi = n;              // first slot whose key >= k   (sentinel keys sort last)
-    while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (keys_sorted[mid] < k) lo = mid + 1; else hi = mid;
-    }
-    cell_start[k] = lo;
-    if (k == ncell) counters[C_GRID] = lo;
-}
-
-__global__ void __launch_bounds__(256) gather_kernel(const uint32_t* __restrict__ vals_sorted, const float4* __restrict__ center_r,
-                                                     const float4* __restrict__ half_ext, const uint32_t* __restrict__ counters,
-                                                     float4* __restrict__ sorted_center_r, float4* __restrict__ sorted_half_ext) {
+// K4 (on demand): the stable (key,id) order.  The rank of a body inside its cell is the number of
+// co-occupants with a smaller id.
+__global__ void __launch_bounds__(256) canon_kernel(const SlotRec* __restrict__ recs, const uint32_t* __restrict__ cell_start,
+                                                    GridParams g, const uint32_t* __restrict__ counters,
+                                                    uint32_t* __restrict__ sorted_ids) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= counters[C_GRID]) return;
-    const uint32_t id = vals_sorted[t] & ID_MASK;
-    sorted_center_r[t] = center_r[id];
-    if (half_ext) sorted_half_ext[t] = half_ext[id];
+    const uint32_t key = cell_key(recs[t].c, g);
+    const uint32_t id = recs[t].val & ID_MASK;
+    const uint32_t s = cell_start[key], e = cell_start[key + 1];
+    uint32_t rank = 0;
+    for (uint32_t u = s; u < e; ++u) rank += ((recs[u].val & ID_MASK) < id) ? 1u : 0u;
+    sorted_ids[s + rank] = id;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -425,12 +414,12 @@ __device__ __forceinline__ void emit_pair(unsigned long long* out, unsigned long
 
 template <bool CANDIDATES, bool MIXED>
 __device__ __forceinline__ void test_range(uint32_t s, uint32_t e, uint32_t va, uint32_t ida, const float4 ca, const float4 ha,
-                                           const uint32_t* __restrict__ vals_sorted,
-                                           const float4* __restrict__ sorted_center_r,
-                                           const float4* __restrict__ sorted_half_ext, unsigned long long* out,
-                                           unsigned long long cap, unsigned long long* counter) {
+                                           const SlotRec* __restrict__ recs, unsigned long long* out, unsigned long long cap,
+                                           unsigned long long* counter) {
     for (uint32_t u = s; u < e; ++u) {
-        const uint32_t vb = vals_sorted[u];
+        float4 cb, hb;
+        uint32_t vb;
+        ld_rec(recs + u, cb, vb, hb);
         const uint32_t idb = vb & ID_MASK;
         const uint32_t lo = min(ida, idb), hi = max(ida, idb);       // pairs are reported as (i < j)
         if (CANDIDATES) {
@@ -438,8 +427,8 @@ __device__ __forceinline__ void test_range(uint32_t s, uint32_t e, uint32_t va, 
         } else {
             if (va & vb & STATIC_BIT) continue;                      // main.cpp:695
             bool hit;
-            if (MIXED && ((va | vb) & BOX_BIT)) hit = aabb_hit(ca, ha, sorted_center_r[u], sorted_half_ext[u]);   // main.cpp:704
-            else hit = sphere_hit(ca, sorted_center_r[u]);                                                       // main.cpp:702
+            if (MIXED && ((va | vb) & BOX_BIT)) hit = aabb_hit(ca, ha, cb, hb);   // main.cpp:704
+            else hit = sphere_hit(ca, cb);                                       // main.cpp:702
             if (hit) emit_pair(out, cap, counter, lo, hi);
         }
     }
@@ -452,29 +441,26 @@ __device__ __forceinline__ void test_range(uint32_t s, uint32_t e, uint32_t va, 
 // With x as the fastest key digit those are 5 contiguous slot ranges for an interior cell:
 //   [t+1, end of cell cx+1]  in the own row, and cells cx-1..cx+1 of the rows (dz,dy) =
 //   (0,+1), (+1,-1), (+1,0), (+1,+1).
+// "Later slots of the own cell" is any fixed order: the arrival order K3b left is as good as the id order.
 // MIXED: boxes live in the grid; a pair with at least one box uses the AABB predicate on the
 // collider sizes of both bodies, exactly as the reference dispatches (main.cpp:701-706).
 template <bool CANDIDATES, bool MIXED>
-__global__ void __launch_bounds__(128) narrow_kernel(const uint32_t* __restrict__ keys_sorted,
-                                                     const uint32_t* __restrict__ vals_sorted,
-                                                     const float4* __restrict__ sorted_center_r,
-                                                     const float4* __restrict__ sorted_half_ext,
-                                                     const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ counters,
-                                                     int bits, bool check_occ, unsigned long long* out, unsigned long long cap,
+__global__ void __launch_bounds__(128) narrow_kernel(const SlotRec* __restrict__ recs, const uint32_t* __restrict__ cell_start,
+                                                     const uint32_t* __restrict__ counters, GridParams g,
+                                                     unsigned long long* out, unsigned long long cap,
                                                      unsigned long long* counter) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= counters[C_GRID]) return;
-    if (check_occ && counters[C_MAXOCC] > OCC_LIMIT) return;   // fast path refused; the host reruns through the fallback
-    const uint32_t key = keys_sorted[t];
-    const uint32_t va = vals_sorted[t];
+    float4 ca, ha;
+    uint32_t va;
+    ld_rec(recs + t, ca, va, ha);
+    const uint32_t key = cell_key(ca, g);
     const uint32_t ida = va & ID_MASK;
-    const float4 ca = sorted_center_r[t];
-    float4 ha = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (MIXED) ha = sorted_half_ext[t];
+    const int bits = g.bits;
     const uint32_t msk = (1u << bits) - 1u;
     const uint32_t cx = key & msk, cy = (key >> bits) & msk, cz = (key >> (2 * bits)) & msk;
     const bool interior = cx > 0 && cx < msk;
-#define TR_RANGE(S, E) test_range<CANDIDATES, MIXED>((S), (E), va, ida, ca, ha, vals_sorted, sorted_center_r, sorted_half_ext, out, cap, counter)
+#define TR_RANGE(S, E) test_range<CANDIDATES, MIXED>((S), (E), va, ida, ca, ha, recs, out, cap, counter)
     // own row: the rest of the own cell, then cell cx+1
     if (cx < msk) {
         TR_RANGE(t + 1, cell_start[key + 2]);
@@ -887,6 +873,10 @@ static Collide* state(tr_world* w) {
 // A body's extent is |radius| for a sphere in an all-sphere world; as soon as one live box with
 // finite size exists ("mixed" world) any body may meet a box, box pairs use collider::size of both
 // bodies, and the extent becomes max(|radius| if sphere, |size.x|, |size.y|, |size.z|).
+static GridParams grid_params(const Collide* c) {
+    return GridParams{c->origin[0], c->origin[1], c->origin[2], c->inv_cell, c->rmax_grid, c->bits, c->mixed ? 1 : 0};
+}
+
 static float body_extent(const tr_body_desc& b, bool mixed) {
     float e = b.isSphere ? std::fabs(b.radius) : 0.f;
     if (mixed || !b.isSphere) e = std::max(e, std::max(std::fabs(b.size[0]), std::max(std::fabs(b.size[1]), std::fabs(b.size[2]))));
@@ -948,7 +938,6 @@ int collide_classify(tr_world* w) {
         while (bits < 10 && (1ull << (3 * bits)) < want) ++bits;
     }
     c->bits = bits;
-    c->use_cub = false;
     w->classified = true;
     return TR_OK;
 }
@@ -959,12 +948,8 @@ static int ensure_buffers(tr_world* w) {
     if (n > c->cap_bodies) {
         uint64_t cap = w->cap >= n ? w->cap : n;
         TR_TRY(realloc_dev(&c->keys, cap));
-        TR_TRY(realloc_dev(&c->keys_sorted, cap));
-        TR_TRY(realloc_dev(&c->vals, cap));
-        TR_TRY(realloc_dev(&c->vals_sorted, cap));
-        TR_TRY(realloc_dev(&c->tmp_ids, cap));
-        TR_TRY(realloc_dev(&c->sorted_center_r, cap));
-        TR_TRY(realloc_dev(&c->sorted_half_ext, cap));
+        TR_TRY(realloc_dev((SlotRec**)&c->recs, cap));
+        TR_TRY(realloc_dev(&c->sorted_ids, cap));
         TR_TRY(realloc_dev(&c->side_list, cap));
         TR_TRY(realloc_dev(&c->far_list, cap));
         TR_TRY(realloc_dev(&c->bnd_list, cap));
@@ -1015,77 +1000,62 @@ static int ensure_buffers(tr_world* w) {
         TR_CUDA(cudaMallocHost(&c->h_rounds, 8 * sizeof(uint32_t)));
         memset(c->h_rounds, 0, 8 * sizeof(uint32_t));
     }
-    // CUB scratch: only the crowded-cell fallback of the broad phase sorts with CUB
-    size_t need = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, need, c->keys, c->keys_sorted, c->vals, c->vals_sorted, (uint32_t)c->cap_bodies);
-    if (need > c->cub_tmp_bytes) {
-        if (c->cub_tmp) cudaFree(c->cub_tmp);
-        c->cub_tmp = nullptr;
-        TR_CUDA(cudaMalloc(&c->cub_tmp, need));
-        c->cub_tmp_bytes = need;
-    }
     return TR_OK;
 }
 
-// `ev` (debug, TR_BP_PROFILE=1): 6 events recorded around the five kernels
-static int launch_fast_broad(tr_world* w, cudaStream_t st, cudaEvent_t* ev = nullptr) {
+// K2-K3b.  `ev` (debug, TR_BP_PROFILE=1): 5 events recorded around the four kernels.
+static int launch_broad(tr_world* w, cudaStream_t st, cudaEvent_t* ev = nullptr) {
     Collide* c = state(w);
     const uint32_t n = (uint32_t)w->n;
     const uint32_t blocks = (n + 255) / 256;
     const uint32_t ncell = 1u << (3 * c->bits);
     const uint32_t ntiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
-    GridParams g{c->origin[0], c->origin[1], c->origin[2], c->inv_cell, c->rmax_grid, c->bits, c->mixed ? 1 : 0};
+    const GridParams g = grid_params(c);
     TR_CUDA(cudaMemsetAsync(c->counters, 0, C_NCOUNTERS * sizeof(uint32_t), st));
     if (ev) cudaEventRecord(ev[0], st);
-    keys_kernel<true><<<blocks, 256, 0, st>>>(w->center_r, w->half_ext, w->flags, n, g, c->keys, c->vals, c->klass, c->side_list,
-                                              c->far_list, c->far_c, c->bnd_list, c->bnd_c, c->cell_count, c->counters);
+    keys_kernel<<<blocks, 256, 0, st>>>(w->center_r, w->half_ext, w->flags, n, g, c->keys, c->klass, c->side_list, c->far_list, c->far_c,
+                                        c->bnd_list, c->bnd_c, c->cell_count, c->counters);
     if (ev) cudaEventRecord(ev[1], st);
-    tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, ncell, c->tile_sum, c->counters, OCC_LIMIT);
+    tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, ncell, c->tile_sum);
     if (ev) cudaEventRecord(ev[2], st);
     scan_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, c->tile_sum, c->cell_start, ncell, c->counters, C_GRID);
     if (ev) cudaEventRecord(ev[3], st);
-    scatter_kernel<<<blocks, 256, 0, st>>>(c->keys, ncell, w->flags, n, c->cell_start, c->cell_count, c->tmp_ids);
+    scatter_kernel<<<blocks, 256, 0, st>>>(c->keys, ncell, w->flags, w->center_r, c->mixed ? w->half_ext : nullptr, n, c->cell_start,
+                                           c->cell_count, (SlotRec*)c->recs);
     if (ev) cudaEventRecord(ev[4], st);
-    rank_gather_kernel<<<blocks, 256, 0, st>>>(c->tmp_ids, c->cell_start, w->center_r, c->mixed ? w->half_ext : nullptr,
-                                               c->counters, c->keys_sorted, c->vals_sorted, c->sorted_center_r, c->sorted_half_ext);
-    if (ev) cudaEventRecord(ev[5], st);
     TR_CUDA(cudaGetLastError());
     return TR_OK;
 }
 
-// Broad phase K2-K4.  Leaves counters[C_SIDE] / [C_GRID] / [C_MAXOCC] on the device; no host sync.
+// Broad phase K2-K3b.  Leaves counters[C_SIDE] / [C_FAR] / [C_BND] / [C_GRID] on the device; no host sync.
 static int broad_phase(tr_world* w) {
     Collide* c = state(w);
     const uint32_t n = (uint32_t)w->n;
-    const uint32_t blocks = (n + 255) / 256;
-    const uint32_t ncell = 1u << (3 * c->bits);
     PendingTimer t;
     static const bool bp_profile = getenv("TR_BP_PROFILE") != nullptr;
-    if (!c->use_cub && bp_profile) {
+    if (bp_profile) {
         // debug: plain launches with an event between the kernels, per-kernel times to stderr
         // (event gaps include the launch gap a graph does not have: ~2 us per kernel)
-        cudaEvent_t ev[6];
+        cudaEvent_t ev[5];
         for (auto& e : ev) TR_CUDA(cudaEventCreate(&e));
         timer_begin(w, T_BROAD, &t);
-        TR_TRY(launch_fast_broad(w, w->stream, ev));
+        TR_TRY(launch_broad(w, w->stream, ev));
         timer_end(w, &t);
-        TR_CUDA(cudaEventSynchronize(ev[5]));
-        float ms[5];
-        for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
-        fprintf(stderr, "[TR_BP_PROFILE] n=%u keys %.1f us, tile sums %.1f us, scan %.1f us, scatter %.1f us, rank+gather %.1f us\n", n,
-                ms[0] * 1e3f, ms[1] * 1e3f, ms[2] * 1e3f, ms[3] * 1e3f, ms[4] * 1e3f);
+        TR_CUDA(cudaEventSynchronize(ev[4]));
+        float ms[4];
+        for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
+        fprintf(stderr, "[TR_BP_PROFILE] n=%u keys %.1f us, tile sums %.1f us, scan %.1f us, scatter %.1f us\n", n, ms[0] * 1e3f,
+                ms[1] * 1e3f, ms[2] * 1e3f, ms[3] * 1e3f);
         for (auto& e : ev) cudaEventDestroy(e);
-        w->stats.kernel_launches += 5;
-    } else if (!c->use_cub && w->stream == nullptr) {
+    } else if (w->stream == nullptr) {
         // the legacy default stream cannot be captured: plain launches
         timer_begin(w, T_BROAD, &t);
-        TR_TRY(launch_fast_broad(w, w->stream));
+        TR_TRY(launch_broad(w, w->stream));
         timer_end(w, &t);
-        w->stats.kernel_launches += 5;
-    } else if (!c->use_cub) {
+    } else {
         // signature of everything the captured launches depend on
         uint64_t sig[8] = {(uint64_t)(uintptr_t)w->center_r, (uint64_t)(uintptr_t)w->flags, (uint64_t)(uintptr_t)c->keys,
-                           (uint64_t)(uintptr_t)c->cell_count, (uint64_t)(uintptr_t)c->ckeys ^ (uint64_t)(uintptr_t)c->tmp_ids,
+                           (uint64_t)(uintptr_t)c->cell_count, (uint64_t)(uintptr_t)c->ckeys ^ (uint64_t)(uintptr_t)c->recs,
                            ((uint64_t)n << 9) | ((uint64_t)(c->mixed ? 1 : 0) << 8) | (uint64_t)c->bits, 0, 0};
         memcpy(&sig[6], &c->inv_cell, 4);
         memcpy((char*)&sig[6] + 4, &c->rmax_grid, 4);
@@ -1098,7 +1068,7 @@ static int broad_phase(tr_world* w) {
             c->bp_graph = nullptr;
             cudaGraph_t graph = nullptr;
             TR_CUDA(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal));
-            int rc = launch_fast_broad(w, w->stream);
+            int rc = launch_broad(w, w->stream);
             cudaError_t e = cudaStreamEndCapture(w->stream, &graph);
             if (rc != TR_OK) return rc;
             if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
@@ -1110,22 +1080,8 @@ static int broad_phase(tr_world* w) {
         timer_begin(w, T_BROAD, &t);
         TR_CUDA(cudaGraphLaunch(c->bp_graph, w->stream));
         timer_end(w, &t);
-        w->stats.kernel_launches += 5;
-    } else {
-        GridParams g{c->origin[0], c->origin[1], c->origin[2], c->inv_cell, c->rmax_grid, c->bits, c->mixed ? 1 : 0};
-        timer_begin(w, T_BROAD, &t);
-        TR_CUDA(cudaMemsetAsync(c->counters, 0, C_NCOUNTERS * sizeof(uint32_t), w->stream));
-        keys_kernel<false><<<blocks, 256, 0, w->stream>>>(w->center_r, w->half_ext, w->flags, n, g, c->keys, c->vals, c->klass, c->side_list,
-                                                          c->far_list, c->far_c, c->bnd_list, c->bnd_c, c->cell_count, c->counters);
-        size_t tmp = c->cub_tmp_bytes;
-        TR_CUDA(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, c->keys, c->keys_sorted, c->vals, c->vals_sorted, n, 0,
-                                                3 * c->bits + 1, w->stream));
-        dense_start_kernel<<<(ncell + 1 + 255) / 256, 256, 0, w->stream>>>(c->keys_sorted, n, ncell, c->cell_start, c->counters);
-        gather_kernel<<<blocks, 256, 0, w->stream>>>(c->vals_sorted, w->center_r, c->mixed ? w->half_ext : nullptr, c->counters,
-                                                     c->sorted_center_r, c->sorted_half_ext);
-        timer_end(w, &t);
-        w->stats.kernel_launches += 3;
     }
+    w->stats.kernel_launches += 4;
     TR_CUDA(cudaGetLastError());
     return TR_OK;
 }
@@ -1172,51 +1128,39 @@ static int launch_far(tr_world* w, unsigned long long* out, uint64_t cap, unsign
 template <bool CANDIDATES>
 static int detect(tr_world* w, unsigned long long* out, uint64_t cap, uint64_t* count) {
     Collide* c = state(w);
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        TR_TRY(broad_phase(w));
-        unsigned long long* counter = (unsigned long long*)(c->counters + (CANDIDATES ? C_CAND : C_CONTACTS));
-        PendingTimer t;
-        timer_begin(w, T_NARROW, &t);
-        const uint32_t nb = (uint32_t)((w->n + 127) / 128);
-        if (c->mixed)
-            narrow_kernel<CANDIDATES, true><<<nb, 128, 0, w->stream>>>(c->keys_sorted, c->vals_sorted, c->sorted_center_r,
-                                                                       c->sorted_half_ext, c->cell_start, c->counters, c->bits,
-                                                                       !c->use_cub, out, cap, counter);
-        else
-            narrow_kernel<CANDIDATES, false><<<nb, 128, 0, w->stream>>>(c->keys_sorted, c->vals_sorted, c->sorted_center_r,
-                                                                        c->sorted_half_ext, c->cell_start, c->counters, c->bits,
-                                                                        !c->use_cub, out, cap, counter);
-        w->stats.kernel_launches += 1;
-        const bool side_launched = c->may_have_side && !CANDIDATES;
-        if (side_launched) TR_TRY(launch_side(w, out, cap, counter));
-        const bool far_launched = c->last_far > 0 && !CANDIDATES;
-        if (far_launched) TR_TRY(launch_far(w, out, cap, counter));
-        timer_end(w, &t);
-        TR_CUDA(cudaGetLastError());
-        TR_TRY(read_counters(w));
-        if (!c->use_cub && c->h_counters[C_MAXOCC] > OCC_LIMIT) {
-            // a cell holds more bodies than the quadratic rank step accepts: redo this step (and
-            // all later ones) through the radix-sort fallback
-            c->use_cub = true;
-            continue;
-        }
-        bool again = false;
-        if (!CANDIDATES && !side_launched && c->h_counters[C_SIDE] > 0) {
-            // a body's extent became oversize / non-finite at run time: test it now (rare path, one more read-back)
-            c->may_have_side = true;
-            TR_TRY(launch_side(w, out, cap, counter));
-            again = true;
-        }
-        if (!CANDIDATES && !far_launched && c->h_counters[C_FAR] > 0) {
-            // bodies left the grid domain at run time: first step with a far list
-            c->last_far = c->h_counters[C_FAR];
-            c->last_bnd = c->h_counters[C_BND];
-            TR_TRY(launch_far(w, out, cap, counter));
-            again = true;
-        }
-        if (again) TR_TRY(read_counters(w));
-        break;
+    TR_TRY(broad_phase(w));
+    unsigned long long* counter = (unsigned long long*)(c->counters + (CANDIDATES ? C_CAND : C_CONTACTS));
+    PendingTimer t;
+    timer_begin(w, T_NARROW, &t);
+    const uint32_t nb = (uint32_t)((w->n + 127) / 128);
+    const GridParams g = grid_params(c);
+    if (c->mixed)
+        narrow_kernel<CANDIDATES, true><<<nb, 128, 0, w->stream>>>((const SlotRec*)c->recs, c->cell_start, c->counters, g, out, cap, counter);
+    else
+        narrow_kernel<CANDIDATES, false><<<nb, 128, 0, w->stream>>>((const SlotRec*)c->recs, c->cell_start, c->counters, g, out, cap, counter);
+    w->stats.kernel_launches += 1;
+    const bool side_launched = c->may_have_side && !CANDIDATES;
+    if (side_launched) TR_TRY(launch_side(w, out, cap, counter));
+    const bool far_launched = c->last_far > 0 && !CANDIDATES;
+    if (far_launched) TR_TRY(launch_far(w, out, cap, counter));
+    timer_end(w, &t);
+    TR_CUDA(cudaGetLastError());
+    TR_TRY(read_counters(w));
+    bool again = false;
+    if (!CANDIDATES && !side_launched && c->h_counters[C_SIDE] > 0) {
+        // a body's extent became oversize / non-finite at run time: test it now (rare path, one more read-back)
+        c->may_have_side = true;
+        TR_TRY(launch_side(w, out, cap, counter));
+        again = true;
     }
+    if (!CANDIDATES && !far_launched && c->h_counters[C_FAR] > 0) {
+        // bodies left the grid domain at run time: first step with a far list
+        c->last_far = c->h_counters[C_FAR];
+        c->last_bnd = c->h_counters[C_BND];
+        TR_TRY(launch_far(w, out, cap, counter));
+        again = true;
+    }
+    if (again) TR_TRY(read_counters(w));
     c->last_side = c->h_counters[C_SIDE];
     c->last_far = c->h_counters[C_FAR];
     c->last_bnd = c->h_counters[C_BND];
@@ -1269,13 +1213,13 @@ int collide_step(tr_world* w) {
     const uint32_t btiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
     // lexicographic (i,j) order == the reference's visiting order: counting sort by i, rank by j
     chist_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, cn, 32, c->body_cnt);
-    tile_sums_kernel<<<btiles, SCAN_THREADS, 0, w->stream>>>(c->body_cnt, nb, c->tile_sum, c->counters, 0xFFFFFFFFu);
+    tile_sums_kernel<<<btiles, SCAN_THREADS, 0, w->stream>>>(c->body_cnt, nb, c->tile_sum);
     scan_kernel<<<btiles, SCAN_THREADS, 0, w->stream>>>(c->body_cnt, c->tile_sum, c->row_start, nb, c->counters, -1);
     cscatter_row_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, cn, c->row_start, c->body_cnt, c->ckeys_alt);
     crank_row_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys_alt, c->row_start, cn, c->ckeys);
     // column order (j, then i): the same, keyed by j
     chist_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, cn, 0, c->body_cnt);
-    tile_sums_kernel<<<btiles, SCAN_THREADS, 0, w->stream>>>(c->body_cnt, nb, c->tile_sum, c->counters, 0xFFFFFFFFu);
+    tile_sums_kernel<<<btiles, SCAN_THREADS, 0, w->stream>>>(c->body_cnt, nb, c->tile_sum);
     scan_kernel<<<btiles, SCAN_THREADS, 0, w->stream>>>(c->body_cnt, c->tile_sum, c->col_start, nb, c->counters, -1);
     cscatter_col_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, cn, c->col_start, c->body_cnt, c->colkeys);
     crank_col_kernel<<<cblocks, 256, 0, w->stream>>>(c->colkeys, c->ckeys, c->col_start, cn, c->colc, c->col_pos);
@@ -1352,15 +1296,12 @@ int collide_debug_grid(tr_world* w, uint32_t* keys, uint32_t* sorted_ids, uint64
     if (!w->classified) TR_TRY(collide_classify(w));
     TR_TRY(ensure_buffers(w));
     Collide* c = state(w);
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        TR_TRY(broad_phase(w));
-        TR_TRY(read_counters(w));
-        if (!c->use_cub && c->h_counters[C_MAXOCC] > OCC_LIMIT) {
-            c->use_cub = true;
-            continue;
-        }
-        break;
-    }
+    TR_TRY(broad_phase(w));
+    // K4, only here: the stable (key,id) order of the grid bodies
+    canon_kernel<<<(uint32_t)((w->n + 255) / 256), 256, 0, w->stream>>>((const SlotRec*)c->recs, c->cell_start, grid_params(c),
+                                                                          c->counters, c->sorted_ids);
+    TR_CUDA(cudaGetLastError());
+    TR_TRY(read_counters(w));
     const uint32_t gm = c->h_counters[C_GRID];
     if (m) *m = gm;
     if (cell) *cell = c->cell;
@@ -1374,9 +1315,8 @@ int collide_debug_grid(tr_world* w, uint32_t* keys, uint32_t* sorted_ids, uint64
             if (keys[i] == sentinel) keys[i] = EMPTY;
     }
     if (sorted_ids && gm) {
-        TR_CUDA(cudaMemcpyAsync(sorted_ids, c->vals_sorted, gm * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+        TR_CUDA(cudaMemcpyAsync(sorted_ids, c->sorted_ids, gm * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
         TR_CUDA(cudaStreamSynchronize(w->stream));
-        for (uint32_t i = 0; i < gm; ++i) sorted_ids[i] &= ID_MASK;
     }
     return TR_OK;
 }
@@ -1413,8 +1353,8 @@ int collide_debug_candidates(tr_world* w, int32_t* pairs, uint64_t cap, uint64_t
 int collide_free(tr_world* w) {
     Collide* c = w->col;
     if (!c) return TR_OK;
-    cudaFree(c->keys); cudaFree(c->keys_sorted); cudaFree(c->vals); cudaFree(c->vals_sorted); cudaFree(c->tmp_ids);
-    cudaFree(c->sorted_center_r); cudaFree(c->sorted_half_ext); cudaFree(c->cell_start); cudaFree(c->cell_count); cudaFree(c->tile_sum);
+    cudaFree(c->keys); cudaFree(c->recs); cudaFree(c->sorted_ids);
+    cudaFree(c->cell_start); cudaFree(c->cell_count); cudaFree(c->tile_sum);
     cudaFree(c->side_list); cudaFree(c->far_list); cudaFree(c->bnd_list); cudaFree(c->far_c); cudaFree(c->bnd_c); cudaFree(c->klass);
     cudaFree(c->row_start); cudaFree(c->col_start); cudaFree(c->body_cnt); cudaFree(c->counters);
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -1422,7 +1362,6 @@ int collide_free(tr_world* w) {
     cudaFree(c->ckeys); cudaFree(c->ckeys_alt); cudaFree(c->colkeys);
     cudaFree(c->colc); cudaFree(c->col_pos); cudaFree(c->dep);
     cudaFree(c->succ_i); cudaFree(c->succ_j); cudaFree(c->crec); cudaFree(c->frontier[0]); cudaFree(c->frontier[1]);
-    cudaFree(c->cub_tmp);
     if (c->bp_graph) cudaGraphExecDestroy(c->bp_graph);
     delete c;
     w->col = nullptr;
