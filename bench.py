@@ -355,7 +355,7 @@ def main():
                 bp_traffic = json.load(open(prof)).get(str(n))
             except Exception:
                 bp_traffic = None
-        bp = {"bound": "hbm", "kernel": "broad phase K2-K4 (keys, one-digit radix sort, cell table, gather)", "achieved": ach,
+        bp = {"bound": "hbm", "kernel": "broad phase K2-K3b (keys + histogram, cell-table scan, scatter of 32-byte body records into cell order)", "achieved": ach,
               "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": bp_traffic, "peak_source": src,
               "algorithmic": f"{BROADPHASE_BYTES_PER_BODY} B/body x {n} bodies", "kernel_ms": broad_ms}
         if roofline is None:

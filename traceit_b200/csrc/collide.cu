@@ -412,25 +412,71 @@ __device__ __forceinline__ void emit_pair(unsigned long long* out, unsigned long
     if (slot < cap) out[slot] = ((unsigned long long)i << 32) | j;
 }
 
+// Hits are staged per thread (NARROW_HITS partner ids in shared memory) and a warp reserves its
+// output slots with ONE atomic at the end.  Emitting from inside the loops - even warp-aggregated, as
+// ptxas does by itself - sends ~450K atomics to one address on the packed 1M scene, and same-address
+// atomics retire at ~0.85 clk each at L2: that queue, not the loads, was the packed narrow phase
+// (ncu: issue slots 15 % busy, L2 4 %, every warp waiting on the atomic's return).
+constexpr int NARROW_THREADS = 128;
+constexpr int NARROW_HITS = 8;
+
+__device__ __noinline__ void emit_pair_overflow(unsigned long long* out, unsigned long long cap, unsigned long long* counter,
+                                                uint32_t i, uint32_t j) {
+    emit_pair(out, cap, counter, i, j);
+}
+
 template <bool CANDIDATES, bool MIXED>
-__device__ __forceinline__ void test_range(uint32_t s, uint32_t e, uint32_t va, uint32_t ida, const float4 ca, const float4 ha,
-                                           const SlotRec* __restrict__ recs, unsigned long long* out, unsigned long long cap,
-                                           unsigned long long* counter) {
-    for (uint32_t u = s; u < e; ++u) {
-        float4 cb, hb;
-        uint32_t vb;
-        ld_rec(recs + u, cb, vb, hb);
-        const uint32_t idb = vb & ID_MASK;
-        const uint32_t lo = min(ida, idb), hi = max(ida, idb);       // pairs are reported as (i < j)
-        if (CANDIDATES) {
-            emit_pair(out, cap, counter, lo, hi);
+__device__ __forceinline__ void test_one(uint32_t u, uint32_t va, uint32_t ida, const float4 ca, const float4 ha,
+                                         const SlotRec* __restrict__ recs, uint32_t (*s_hit)[NARROW_THREADS], uint32_t& nh,
+                                         unsigned long long* out, unsigned long long cap, unsigned long long* counter) {
+    float4 cb, hb;
+    uint32_t vb;
+    ld_rec(recs + u, cb, vb, hb);
+    const uint32_t idb = vb & ID_MASK;
+    bool hit = true;
+    if (!CANDIDATES) {
+        if (MIXED && ((va | vb) & BOX_BIT)) hit = aabb_hit(ca, ha, cb, hb);   // main.cpp:704
+        else hit = sphere_hit(ca, cb);                                       // main.cpp:702
+        hit = hit && !(va & vb & STATIC_BIT);                                // main.cpp:695
+    }
+    if (hit) {
+        if (nh < (uint32_t)NARROW_HITS) s_hit[nh][threadIdx.x] = idb;
+        else emit_pair_overflow(out, cap, counter, min(ida, idb), max(ida, idb));   // staging full: straight out
+        ++nh;
+    }
+}
+
+// x-edge cell: the windows wrap around the row, so they are walked cell by cell (2 of 2^bits cells per row)
+template <bool CANDIDATES, bool MIXED>
+__device__ __noinline__ void narrow_edge(uint32_t t, uint32_t key, int bits, uint32_t va, const float4 ca, const float4 ha,
+                                         const SlotRec* __restrict__ recs, const uint32_t* __restrict__ cell_start,
+                                         uint32_t (*s_hit)[NARROW_THREADS], uint32_t& nh, unsigned long long* out,
+                                         unsigned long long cap, unsigned long long* counter) {
+    const uint32_t ida = va & ID_MASK;
+    const uint32_t msk = (1u << bits) - 1u;
+    const uint32_t cx = key & msk, cy = (key >> bits) & msk, cz = (key >> (2 * bits)) & msk;
+    // window w: 0 = rest of the own cell, 1 = cell cx+1 of the own row, 2.. = 3 cells of each forward row
+#pragma unroll 1
+    for (int w = 0; w < 14; ++w) {
+        uint32_t s, e;
+        if (w == 0) {
+            s = t + 1;
+            e = cell_start[key + 1];
         } else {
-            if (va & vb & STATIC_BIT) continue;                      // main.cpp:695
-            bool hit;
-            if (MIXED && ((va | vb) & BOX_BIT)) hit = aabb_hit(ca, ha, cb, hb);   // main.cpp:704
-            else hit = sphere_hit(ca, cb);                                       // main.cpp:702
-            if (hit) emit_pair(out, cap, counter, lo, hi);
+            uint32_t nk;
+            if (w == 1) {
+                nk = (key & ~msk) | ((cx + 1) & msk);
+            } else {
+                const int r = (w - 2) / 3, dx = (w - 2) % 3 - 1;
+                const int dz = r == 0 ? 0 : 1;
+                const int dy = r == 0 ? 1 : r - 2;
+                nk = (((cy + dy) & msk) << bits) | (((cz + dz) & msk) << (2 * bits)) | ((cx + dx) & msk);
+            }
+            s = cell_start[nk];
+            e = cell_start[nk + 1];
         }
+#pragma unroll 1
+        for (uint32_t u = s; u < e; ++u) test_one<CANDIDATES, MIXED>(u, va, ida, ca, ha, recs, s_hit, nh, out, cap, counter);
     }
 }
 
@@ -444,49 +490,70 @@ __device__ __forceinline__ void test_range(uint32_t s, uint32_t e, uint32_t va, 
 // "Later slots of the own cell" is any fixed order: the arrival order K3b left is as good as the id order.
 // MIXED: boxes live in the grid; a pair with at least one box uses the AABB predicate on the
 // collider sizes of both bodies, exactly as the reference dispatches (main.cpp:701-706).
+// One thread per slot.  (A warp-cooperative version - the union of a warp's windows per stencil
+// row staged in shared memory by coalesced loads, each record read once per warp - was measured at
+// 98.9 us sparse / 286.7 us packed against 54.6 / 321.8 for this one: the staging phases serialise
+// a warp that otherwise hides its latency with 64 independent threads per scheduler.)
 template <bool CANDIDATES, bool MIXED>
-__global__ void __launch_bounds__(128) narrow_kernel(const SlotRec* __restrict__ recs, const uint32_t* __restrict__ cell_start,
-                                                     const uint32_t* __restrict__ counters, GridParams g,
-                                                     unsigned long long* out, unsigned long long cap,
-                                                     unsigned long long* counter) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= counters[C_GRID]) return;
-    float4 ca, ha;
-    uint32_t va;
-    ld_rec(recs + t, ca, va, ha);
-    const uint32_t key = cell_key(ca, g);
-    const uint32_t ida = va & ID_MASK;
-    const int bits = g.bits;
-    const uint32_t msk = (1u << bits) - 1u;
-    const uint32_t cx = key & msk, cy = (key >> bits) & msk, cz = (key >> (2 * bits)) & msk;
-    const bool interior = cx > 0 && cx < msk;
-#define TR_RANGE(S, E) test_range<CANDIDATES, MIXED>((S), (E), va, ida, ca, ha, recs, out, cap, counter)
-    // own row: the rest of the own cell, then cell cx+1
-    if (cx < msk) {
-        TR_RANGE(t + 1, cell_start[key + 2]);
-    } else {
-        TR_RANGE(t + 1, cell_start[key + 1]);
-        const uint32_t nk = key & ~msk;                            // x wraps to cell 0 of the same row
-        TR_RANGE(cell_start[nk], cell_start[nk + 1]);
-    }
-    // the four forward rows
-#pragma unroll 1
-    for (int r = 0; r < 4; ++r) {
-        const int dz = r == 0 ? 0 : 1;
-        const int dy = r == 0 ? 1 : r - 2;
-        const uint32_t row = (((cy + dy) & msk) << bits) | (((cz + dz) & msk) << (2 * bits));
-        if (interior) {
-            // cells (cx-1, cx, cx+1) of this row are consecutive keys: one contiguous slot range
-            TR_RANGE(cell_start[row + cx - 1], cell_start[row + cx + 2]);
-        } else {
-#pragma unroll 1
-            for (int dx = -1; dx <= 1; ++dx) {
-                const uint32_t nk = row | ((cx + dx) & msk);
-                TR_RANGE(cell_start[nk], cell_start[nk + 1]);
+__global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* __restrict__ recs,
+                                                                const uint32_t* __restrict__ cell_start,
+                                                                const uint32_t* __restrict__ counters, GridParams g,
+                                                                unsigned long long* out, unsigned long long cap,
+                                                                unsigned long long* counter) {
+    __shared__ uint32_t s_hit[NARROW_HITS][NARROW_THREADS];
+    const uint32_t t = blockIdx.x * NARROW_THREADS + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t nh = 0, ida = 0;
+    if (t < counters[C_GRID]) {
+        float4 ca, ha;
+        uint32_t va;
+        ld_rec(recs + t, ca, va, ha);
+        const uint32_t key = cell_key(ca, g);
+        ida = va & ID_MASK;
+        const int bits = g.bits;
+        const uint32_t msk = (1u << bits) - 1u;
+        const uint32_t cx = key & msk, cy = (key >> bits) & msk, cz = (key >> (2 * bits)) & msk;
+        if (cx > 0 && cx < msk) {
+            // interior cell: five contiguous slot ranges, all nine look-ups issued before the first use
+            uint32_t rs[5], re[5];
+            rs[0] = t + 1;
+            re[0] = cell_start[key + 2];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int dz = r == 0 ? 0 : 1;
+                const int dy = r == 0 ? 1 : r - 2;
+                const uint32_t row = (((cy + dy) & msk) << bits) | (((cz + dz) & msk) << (2 * bits));
+                rs[r + 1] = cell_start[row + cx - 1];
+                re[r + 1] = cell_start[row + cx + 2];
             }
+            // (one flattened loop over the five windows - a lane moving on as soon as its own window is
+            // exhausted - was slower: 77 / 90 us against 62 / 73; the compiler pipelines these loops better)
+#pragma unroll
+            for (int r = 0; r < 5; ++r)
+                for (uint32_t u = rs[r]; u < re[r]; ++u)
+                    test_one<CANDIDATES, MIXED>(u, va, ida, ca, ha, recs, s_hit, nh, out, cap, counter);
+        } else {
+            narrow_edge<CANDIDATES, MIXED>(t, key, bits, va, ca, ha, recs, cell_start, s_hit, nh, out, cap, counter);
         }
     }
-#undef TR_RANGE
+    // one reservation per warp for everything it staged
+    if (!__any_sync(0xFFFFFFFFu, nh != 0)) return;
+    const uint32_t cnt = min(nh, (uint32_t)NARROW_HITS);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (uint32_t)o) incl += y;
+    }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (total == 0) return;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(counter, (unsigned long long)total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0) + (incl - cnt);
+    for (uint32_t k = 0; k < cnt; ++k) {
+        const uint32_t idb = s_hit[k][threadIdx.x];
+        if (base + k < cap) out[base + k] = ((unsigned long long)min(ida, idb) << 32) | max(ida, idb);
+    }
 }
 
 // K5b: side-list bodies against every live body.  grid = (ceil(n/256), up to 64).
@@ -1132,12 +1199,12 @@ static int detect(tr_world* w, unsigned long long* out, uint64_t cap, uint64_t* 
     unsigned long long* counter = (unsigned long long*)(c->counters + (CANDIDATES ? C_CAND : C_CONTACTS));
     PendingTimer t;
     timer_begin(w, T_NARROW, &t);
-    const uint32_t nb = (uint32_t)((w->n + 127) / 128);
+    const uint32_t nb = (uint32_t)((w->n + NARROW_THREADS - 1) / NARROW_THREADS);
     const GridParams g = grid_params(c);
     if (c->mixed)
-        narrow_kernel<CANDIDATES, true><<<nb, 128, 0, w->stream>>>((const SlotRec*)c->recs, c->cell_start, c->counters, g, out, cap, counter);
+        narrow_kernel<CANDIDATES, true><<<nb, NARROW_THREADS, 0, w->stream>>>((const SlotRec*)c->recs, c->cell_start, c->counters, g, out, cap, counter);
     else
-        narrow_kernel<CANDIDATES, false><<<nb, 128, 0, w->stream>>>((const SlotRec*)c->recs, c->cell_start, c->counters, g, out, cap, counter);
+        narrow_kernel<CANDIDATES, false><<<nb, NARROW_THREADS, 0, w->stream>>>((const SlotRec*)c->recs, c->cell_start, c->counters, g, out, cap, counter);
     w->stats.kernel_launches += 1;
     const bool side_launched = c->may_have_side && !CANDIDATES;
     if (side_launched) TR_TRY(launch_side(w, out, cap, counter));
