@@ -68,9 +68,11 @@ typedef struct tr_world_params {
     /* Largest extent admitted to the grid; 0 = automatic: the largest extent that is
      * <= 8x the median extent.                                           */
     float grid_max_radius;
-    /* Ordered collision response: 0 = dataflow (barrier-free, default), 1 = level-synchronous
-     * wavefronts (one grid barrier per wavefront).  Both replay the reference's Gauss-Seidel
-     * order exactly and give identical bits; see DESIGN.md K6.                            */
+    /* Ordered collision response: 0 = dataflow (barrier-free, default; single-lane workers for
+     * deep dependency graphs, whole warps for wide shallow ones, chosen from the previous step),
+     * 1 = level-synchronous wavefronts (one grid barrier per wavefront), 2 / 3 = dataflow forced
+     * to whole warps / single-lane workers.  All replay the reference's Gauss-Seidel order exactly
+     * and give identical bits; see DESIGN.md K6.                                          */
     uint32_t response_mode;
     uint32_t reserved[2];
 } tr_world_params;

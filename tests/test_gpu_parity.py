@@ -185,10 +185,11 @@ def test_far_bodies_meet_each_other_and_the_domain_boundary(tr, oracle):
 
 
 # ---------------------------------------------------------------- response order
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_dense_lattice_response_bit_exact(tr, oracle, mode):
     """Config 5 (small): ~3 contacts per body, lattice-ordered ids = long Gauss-Seidel chains.
-    mode 0 = dataflow response (default), mode 1 = level-synchronous wavefronts."""
+    mode 0 = dataflow response (default), 1 = level-synchronous wavefronts, 2 / 3 = dataflow with
+    whole warps / single-lane workers."""
     b = scenes.dense_lattice(20)           # 8000 bodies
     p = oracle.default_params(g=(0, 0, 0))
     want = b.copy()
@@ -198,10 +199,10 @@ def test_dense_lattice_response_bit_exact(tr, oracle, mode):
     got, contacts, st = gpu_run(tr, b, 10, g=(0, 0, 0), response_mode=mode)
     check_state(got, want, "dense lattice")
     assert np.array_equal(contacts, oracle.contacts(want))
-    assert st.last_response_rounds >= 10   # wavefronts (mode 1) / lock-step iterations of the longest warp (mode 0)
+    assert st.last_response_rounds >= 10   # wavefronts (mode 1) / iterations of the longest dataflow worker (modes 0, 2, 3)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_shuffled_ids_response_bit_exact(tr, oracle, mode):
     b = scenes.dense_lattice(16, shuffle_ids=True)
     p = oracle.default_params(g=(0, 0, 0))

@@ -18,7 +18,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 b = scenes.cfg5_dense(n) if name == "cfg5" else scenes.cfg3_cloud(n)
-p = tr.default_params(flags=tr.COLLISIONS, g=(0, 0, 0))
+p = tr.default_params(flags=tr.COLLISIONS, g=(0, 0, 0), response_mode=int(os.environ.get("TR_RESPONSE_MODE", "0")))
 dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(device=dev)
 torch.cuda.set_stream(stream)
@@ -37,4 +37,4 @@ with tr.World(p) as w:
     print(f"{name} n={len(b)} steps={steps}: broad {st.broadphase_ms / steps * 1e3:.1f} us "
           f"({140.0 * len(b) / (st.broadphase_ms / steps * 1e-3) / 1e9:.0f} GB/s algorithmic), "
           f"narrow {st.narrowphase_ms / steps * 1e3:.1f} us, response {st.response_ms / steps * 1e3:.1f} us, "
-          f"contacts {st.last_contacts}, side {st.side_list_size}")
+          f"contacts {st.last_contacts}, side {st.side_list_size}, rounds {st.last_response_rounds}")

@@ -400,8 +400,8 @@ static int validate_params(const tr_world_params* p) {
         set_error("grid_bits must be 0 (auto) or 2..10, got %d", p->grid_bits);
         return TR_ERR_INVALID_ARG;
     }
-    if (p->response_mode > 1) {
-        set_error("response_mode must be 0 (dataflow) or 1 (level-synchronous), got %u", p->response_mode);
+    if (p->response_mode > 3) {
+        set_error("response_mode must be 0 (dataflow, width chosen per step), 1 (level-synchronous), 2 (dataflow, whole warps) or 3 (dataflow, single-lane workers), got %u", p->response_mode);
         return TR_ERR_INVALID_ARG;
     }
     if (p->grid_cell < 0.f || p->grid_max_radius < 0.f) {

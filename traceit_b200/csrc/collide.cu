@@ -116,6 +116,8 @@ struct Collide {
     uint32_t last_far = 0;        // far / boundary list sizes of the previous step (launch sizing)
     uint32_t last_bnd = 0;
     int coop_blocks = 0;
+    uint64_t prev_contacts = 0;   // last dataflow response: contacts and iterations of the longest worker
+    uint32_t prev_rounds = 0;
 };
 
 namespace tr {
@@ -829,8 +831,16 @@ __global__ void __launch_bounds__(256) response_kernel(RespArgs a, const unsigne
 // the acquiring side.  A spin budget (C_ABORT) guarantees termination even if the graph were broken.
 constexpr uint32_t FLOW_SPIN_LIMIT = 1u << 21;
 
+// LANES = active lanes per warp.  1: a worker is a single lane (the other 31 exit at once), its hop
+// costs its own latency and nothing else - fastest on deep dependency graphs, where the critical
+// path is what is being timed (1M packed spheres: 2.4 ms against 3.5 ms for 32 lanes; 2, 4, 8 lanes
+// per warp on the same grid: 2.9, 4.7, 6.3 ms).  32: the whole warp in lock step, 5x the workers per
+// SM for wide shallow graphs.
+template <int LANES>
 __global__ void __launch_bounds__(128) response_flow_kernel(RespArgs a, const uint4* __restrict__ crec, uint32_t* dep,
                                                             uint32_t* q, uint32_t c_n, uint32_t* counters) {
+    if ((threadIdx.x & 31) >= LANES) return;
+    constexpr uint32_t LMASK = LANES == 32 ? 0xFFFFFFFFu : ((1u << LANES) - 1u);
     volatile uint32_t* vq = q;
     volatile uint32_t* vc = counters;
     uint32_t cur = EMPTY, slot = EMPTY, spins = 0, mine = 0;
@@ -846,7 +856,7 @@ __global__ void __launch_bounds__(128) response_flow_kernel(RespArgs a, const ui
     // bodies they touch are prefetched to L2, so the dependent chain of a hand-off is
     // body loads -> fence -> dependency atomics.
     while (true) {
-        if (!__any_sync(0xFFFFFFFFu, alive)) break;   // the warp leaves together (and reconverges here)
+        if (LANES == 1 ? !alive : !__any_sync(LMASK, alive)) break;   // the warp leaves together (and reconverges here)
         ++iters;
         // ---- phase 1 (loads): successors' records + this contact's bodies, all in flight together
         const bool work = cur != EMPTY;
@@ -1261,6 +1271,12 @@ int collide_step(tr_world* w) {
     Collide* c = state(w);
     uint64_t count = 0;
     TR_TRY(detect<false>(w, c->ckeys, c->cap_contacts, &count));
+    // detect() synchronised with the host: the previous response's iteration count has arrived
+    if (c->rounds_pending && c->flow_pending) {
+        c->prev_rounds = c->h_rounds[0];
+        c->prev_contacts = c->last_contacts;
+    }
+    collide_poll_stats(w);
     w->stats.side_list_size = c->last_side + c->last_far;   // everything outside the grid: oversize list + far list
     w->stats.last_contacts = count;
     c->last_contacts = 0;
@@ -1299,7 +1315,20 @@ int collide_step(tr_world* w) {
         int fblocks = w->num_sms;                     // resident by construction: 128 threads per SM
         int fwant = (int)((cn + 127) / 128);
         if (fwant < fblocks) fblocks = fwant < 1 ? 1 : fwant;
-        response_flow_kernel<<<fblocks, 128, 0, w->stream>>>(ra, c->crec, c->dep, c->frontier[0], cn, c->counters);
+        // Executor width.  Deep graphs (a packed lattice: ~800 dependent hand-offs) are latency bound:
+        // single-lane workers, 6 CTAs of 4 warps per SM (3, 4, 8 per SM: 3.0, 2.6, 2.5 ms against 2.4).
+        // Wide shallow graphs are throughput bound: whole warps.  The previous step tells which:
+        // contacts per lock-step iteration of its longest worker.
+        bool wide = w->params.response_mode == 2;
+        if (w->params.response_mode == 0 && c->prev_rounds > 0) wide = c->prev_contacts / c->prev_rounds > 16384;
+        if (wide) {
+            response_flow_kernel<32><<<fblocks, 128, 0, w->stream>>>(ra, c->crec, c->dep, c->frontier[0], cn, c->counters);
+        } else {
+            int sblocks = w->num_sms * 6;
+            const int swant = (int)((cn + 3) / 4);
+            if (swant < sblocks) sblocks = swant < 1 ? 1 : swant;
+            response_flow_kernel<1><<<sblocks, 128, 0, w->stream>>>(ra, c->crec, c->dep, c->frontier[0], cn, c->counters);
+        }
         TR_CUDA(cudaGetLastError());
         timer_end(w, &t);
         w->stats.kernel_launches += 12;   // 2 x (hist, tile sums, scan, scatter, rank) + deps + response
