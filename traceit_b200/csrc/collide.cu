@@ -53,8 +53,12 @@ constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 // counters[] slots
-enum { C_SIDE = 0, C_GRID = 1, C_CONTACTS = 2 /*u64*/, C_CAND = 4 /*u64*/, C_FRONT = 8 /*3*/, C_ROUNDS = 11,
-       C_QHEAD = 12, C_QTAIL = 13, C_DONE = 14, C_ABORT = 15, C_FAR = 16, C_BND = 17, C_NCOUNTERS = 24 };
+// The three counters every dataflow worker hammers (queue head, queue tail, finished work) sit on
+// 128-byte lines of their own: on one line their atomics and the idle workers' polls all queue at
+// one L2 slice (having idle workers merely READ the tail next to the pushes doubled the step time).
+enum { C_SIDE = 0, C_GRID = 1, C_CONTACTS = 2 /*u64*/, C_CAND = 4 /*u64*/, C_FRONT = 8 /*3*/, C_ROUNDS = 11, C_ABORT = 12, C_FIN = 13,
+       C_FAR = 16, C_BND = 17, C_NHOST = 24 /* read back by the host */,
+       C_QHEAD = 32, C_QTAIL = 64, C_DONE = 96, C_NCOUNTERS = 128 };
 
 }  // namespace tr
 
@@ -103,6 +107,8 @@ struct Collide {
     uint32_t* succ_i = nullptr;
     uint32_t* succ_j = nullptr;
     uint4* crec = nullptr;                    // packed {i, j, succ_i, succ_j} per contact (dataflow executor)
+    uint2* cver = nullptr;                    // versions of bodies i and j that contact c must see (dataflow executor)
+    struct tr_body_rec* brec = nullptr;       // per body: version-checked velocity + position record (tr::BodyRec)
     uint32_t* frontier[2] = {nullptr, nullptr};
 
     // K2-K3b as one CUDA graph (memset + 4 kernels): launch parameters only change when the
@@ -686,21 +692,55 @@ __global__ void __launch_bounds__(256) crank_col_kernel(const unsigned long long
 // Body b's contacts in sweep order are: its column entries (k,b) by ascending k, then its
 // row entries (b,j) by ascending j.  pred/succ below are the neighbours of contact c in the
 // lists of its two bodies.
+// Dataflow executors keep the mutable state of a body that is in contact in ONE 32-byte record
+// whose two 16-byte halves both carry a version = number of contacts applied to the body so far.
+// A contact knows the versions it must see (its rank in the sweep order of each of its bodies),
+// so a reader validates what it loaded by itself and the writer needs no fence between the data
+// and the hand-off (the fence was 42 % of the stall samples of the ordered replay).
+struct __align__(32) BodyRec {
+    float vx, vy, vz;
+    uint32_t ver_v;
+    float px, py, pz;
+    uint32_t ver_p;
+};
+static_assert(sizeof(BodyRec) == 32, "one sector");
+
+__device__ __forceinline__ void st_body(BodyRec* p, const float4 v, const float4 x, uint32_t ver) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)),
+                 "r"(__float_as_uint(v.z)), "r"(ver), "r"(__float_as_uint(x.x)), "r"(__float_as_uint(x.y)),
+                 "r"(__float_as_uint(x.z)), "r"(ver)
+                 : "memory");
+}
+// L2 load (the record is written by other SMs); true when both halves carry the expected version
+__device__ __forceinline__ bool ld_body(const BodyRec* p, uint32_t want, float4& v, float4& x) {
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+                 : "l"(p)
+                 : "memory");
+    v.x = __uint_as_float(r0); v.y = __uint_as_float(r1); v.z = __uint_as_float(r2);
+    x.x = __uint_as_float(r4); x.y = __uint_as_float(r5); x.z = __uint_as_float(r6);
+    return r3 == want && r7 == want;
+}
+
 __global__ void __launch_bounds__(256) deps_kernel(const unsigned long long* __restrict__ ckeys,
                                                    const uint32_t* __restrict__ colc, const uint32_t* __restrict__ col_pos,
                                                    const uint32_t* __restrict__ row_start,
                                                    const uint32_t* __restrict__ col_start, uint32_t c_n,
                                                    uint32_t* __restrict__ dep, uint32_t* __restrict__ succ_i,
                                                    uint32_t* __restrict__ succ_j, uint4* __restrict__ crec,
-                                                   uint32_t* __restrict__ frontier0, uint32_t* counters, int ready_counter) {
+                                                   uint32_t* __restrict__ frontier0, uint32_t* counters, int ready_counter,
+                                                   const float4* __restrict__ pos_m, const float4* __restrict__ vel_rest,
+                                                   BodyRec* __restrict__ brec, uint2* __restrict__ cver) {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= c_n) return;
     unsigned long long k = ckeys[c];
     uint32_t i = (uint32_t)(k >> 32), j = (uint32_t)k;
     uint32_t t = col_pos[c];
-    bool pred_i = c > row_start[i] || col_start[i + 1] > col_start[i];   // an earlier row entry, or any column entry of i
-    bool pred_j = t > col_start[j];                                      // an earlier column entry of j
-    uint32_t d = (pred_i ? 1u : 0u) + (pred_j ? 1u : 0u);
+    // contacts applied to each body before this one: column entries of i + earlier row entries; earlier column entries of j
+    const uint32_t ei = (col_start[i + 1] - col_start[i]) + (c - row_start[i]);
+    const uint32_t ej = t - col_start[j];
+    uint32_t d = (ei ? 1u : 0u) + (ej ? 1u : 0u);
     dep[c] = d;
     const uint32_t si = (c + 1 < row_start[i + 1]) ? c + 1 : EMPTY;
     uint32_t sj;
@@ -709,6 +749,11 @@ __global__ void __launch_bounds__(256) deps_kernel(const unsigned long long* __r
     succ_i[c] = si;
     succ_j[c] = sj;
     crec[c] = make_uint4(i, j, si, sj);
+    if (brec) {                                   // dataflow executors: expected versions, version-0 records
+        cver[c] = make_uint2(ei, ej);
+        if (ei == 0) st_body(brec + i, vel_rest[i], pos_m[i], 0u);
+        if (ej == 0) st_body(brec + j, vel_rest[j], pos_m[j], 0u);
+    }
     if (d == 0) frontier0[atomicAdd(&counters[ready_counter], 1u)] = c;
 }
 
@@ -787,6 +832,107 @@ __device__ __forceinline__ void respond(const RespArgs& a, uint32_t i, uint32_t 
     }
 }
 
+// The same contact on version-checked body records (dataflow executors).  Returns false when the
+// watchdog fired.  Every path bumps both versions, also the ones that change nothing (static body,
+// the approach test): the successors wait for exactly that version.
+struct FlowArgs {
+    const float4* pos_m;       // .w = mass (immutable here); xyz written back at a body's last contact
+    const float4* vel_rest;    // .w = restitution (immutable)
+    float4* pos_out;
+    float4* vel_out;
+    const float4* center_r;
+    const float4* half_ext;
+    const uint8_t* flags;
+    BodyRec* brec;
+    const uint2* cver;
+};
+constexpr uint32_t VERSION_SPIN_LIMIT = 1u << 20;
+
+__device__ __forceinline__ bool respond_rec(const FlowArgs& a, uint32_t c, uint32_t i, uint32_t j, bool last_i, bool last_j,
+                                            uint32_t* counters) {
+    const uint8_t fi = a.flags[i], fj = a.flags[j];
+    const float4 ci = a.center_r[i], cj = a.center_r[j];
+    const uint2 want = a.cver[c];
+    const float mi = a.pos_m[i].w, mj = a.pos_m[j].w;
+    const float ri = a.vel_rest[i].w, rj = a.vel_rest[j].w;
+    float4 vi, vj, pi, pj;
+    bool oki = ld_body(a.brec + i, want.x, vi, pi), okj = ld_body(a.brec + j, want.y, vj, pj);
+    float nx, ny, nz;
+    if ((fi & F_SPHERE) && (fj & F_SPHERE)) {
+        // normalize(b.center - a.center), main.cpp:703 + 211-223
+        float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
+        float len = __fsqrt_rn(dot3_rn(dx, dy, dz, dx, dy, dz));
+        if (len != 0.0f) {
+            nx = __fdiv_rn(dx, len);
+            ny = __fdiv_rn(dy, len);
+            nz = __fdiv_rn(dz, len);
+        } else {
+            nx = dx; ny = dy; nz = dz;
+        }
+    } else {
+        // calculateAABBNormal, main.cpp:622-638
+        const float4 hi = a.half_ext[i], hj = a.half_ext[j];
+        float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
+        float ox = __fsub_rn(__fadd_rn(hi.x, hj.x), fabsf(dx));
+        float oy = __fsub_rn(__fadd_rn(hi.y, hj.y), fabsf(dy));
+        float oz = __fsub_rn(__fadd_rn(hi.z, hj.z), fabsf(dz));
+        nx = ny = nz = 0.0f;
+        if (ox < oy && ox < oz) nx = dx > 0 ? 1.0f : -1.0f;
+        else if (oy < oz) ny = dy > 0 ? 1.0f : -1.0f;
+        else nz = dz > 0 ? 1.0f : -1.0f;
+    }
+    // the writer's stores may still be on their way when its hand-off arrives: poll until they land
+    uint32_t spins = 0;
+    while (!oki || !okj) {
+        if (!oki) oki = ld_body(a.brec + i, want.x, vi, pi);
+        if (!okj) okj = ld_body(a.brec + j, want.y, vj, pj);
+        if (++spins > VERSION_SPIN_LIMIT) {
+            atomicExch(&counters[C_ABORT], 1u);
+            return false;
+        }
+    }
+    float rvx = __fsub_rn(vi.x, vj.x), rvy = __fsub_rn(vi.y, vj.y), rvz = __fsub_rn(vi.z, vj.z);
+    float vn = dot3_rn(rvx, rvy, rvz, nx, ny, nz);
+    if (!(vn > 0)) {                                     // main.cpp:714 (as written)
+        float e = (rj < ri) ? rj : ri;                   // std::min(a.rest, b.rest)
+        float jimp = __fmul_rn(-__fadd_rn(1.0f, e), vn); // -(1 + e) * vn
+        float ima = __fdiv_rn(1.0f, mi), imb = __fdiv_rn(1.0f, mj);
+        jimp = __fdiv_rn(jimp, __fadd_rn(ima, imb));
+        float ix = __fmul_rn(nx, jimp), iy = __fmul_rn(ny, jimp), iz = __fmul_rn(nz, jimp);
+        const float kcorr = 0.2f * 0.01f;                // percent * penetrationSlop (fp32 product)
+        float cx = __fmul_rn(nx, kcorr), cy = __fmul_rn(ny, kcorr), cz = __fmul_rn(nz, kcorr);
+        if (!(fi & F_STATIC)) {
+            vi.x = __fsub_rn(vi.x, __fmul_rn(ix, ima));
+            vi.y = __fsub_rn(vi.y, __fmul_rn(iy, ima));
+            vi.z = __fsub_rn(vi.z, __fmul_rn(iz, ima));
+            pi.x = __fsub_rn(pi.x, __fmul_rn(cx, ima));
+            pi.y = __fsub_rn(pi.y, __fmul_rn(cy, ima));
+            pi.z = __fsub_rn(pi.z, __fmul_rn(cz, ima));
+        }
+        if (!(fj & F_STATIC)) {
+            vj.x = __fadd_rn(vj.x, __fmul_rn(ix, imb));
+            vj.y = __fadd_rn(vj.y, __fmul_rn(iy, imb));
+            vj.z = __fadd_rn(vj.z, __fmul_rn(iz, imb));
+            pj.x = __fadd_rn(pj.x, __fmul_rn(cx, imb));
+            pj.y = __fadd_rn(pj.y, __fmul_rn(cy, imb));
+            pj.z = __fadd_rn(pj.z, __fmul_rn(cz, imb));
+        }
+    }
+    if (last_i) {                                        // nobody reads the record again: back to the SoA state
+        a.vel_out[i] = make_float4(vi.x, vi.y, vi.z, ri);
+        a.pos_out[i] = make_float4(pi.x, pi.y, pi.z, mi);
+    } else {
+        st_body(a.brec + i, vi, pi, want.x + 1u);
+    }
+    if (last_j) {
+        a.vel_out[j] = make_float4(vj.x, vj.y, vj.z, rj);
+        a.pos_out[j] = make_float4(pj.x, pj.y, pj.z, mj);
+    } else {
+        st_body(a.brec + j, vj, pj, want.y + 1u);
+    }
+    return true;
+}
+
 // Persistent cooperative kernel: one wavefront per round, grid-wide barrier between rounds.
 // counters[8 + r%3] is the size of round r's frontier.
 __global__ void __launch_bounds__(256) response_kernel(RespArgs a, const unsigned long long* __restrict__ ckeys,
@@ -825,19 +971,22 @@ __global__ void __launch_bounds__(256) response_kernel(RespArgs a, const unsigne
 // and CONTINUES with one that became ready; a second one goes to a global FIFO that idle threads
 // drain.  A contact still runs only after the previous contact of both its bodies, and never
 // concurrently with another contact of the same body, so the result is the sequential sweep's,
-// bit for bit - but the critical path costs one L2 hand-off per contact (~3 us) instead of a
-// barrier round (~9 us).  Message passing: writes -> __threadfence -> atomicSub(dep) on the
-// releasing side; atomicSub returns 1 (or the queue slot fills) -> __threadfence -> L2 loads on
-// the acquiring side.  A spin budget (C_ABORT) guarantees termination even if the graph were broken.
+// bit for bit - but the critical path costs one L2 hand-off per contact instead of a barrier round
+// (~9 us).  Hand-off protocol: the mutable state of a body lives in a version-stamped 32-byte record
+// (BodyRec above); the releasing side stores the records and decrements the successors' dependency
+// counters WITHOUT a fence in between, the side that sees a counter reach zero (or its queue slot
+// fill) loads the records from L2 and polls until both carry the versions the contact expects.
+// A spin budget (C_ABORT) guarantees termination even if the graph were broken.
 constexpr uint32_t FLOW_SPIN_LIMIT = 1u << 21;
 
 // LANES = active lanes per warp.  1: a worker is a single lane (the other 31 exit at once), its hop
 // costs its own latency and nothing else - fastest on deep dependency graphs, where the critical
-// path is what is being timed (1M packed spheres: 2.4 ms against 3.5 ms for 32 lanes; 2, 4, 8 lanes
-// per warp on the same grid: 2.9, 4.7, 6.3 ms).  32: the whole warp in lock step, 5x the workers per
-// SM for wide shallow graphs.
+// path is what is being timed (1M packed spheres: 1.8 ms against 3.0 ms for 32 lanes; with the
+// fence-based hand-off of the first version 2.4 against 3.5 ms, and 2, 4, 8 lanes per warp on the
+// same grid 2.9, 4.7, 6.3 ms).  32: the whole warp in lock step, 5x the workers per SM for wide
+// shallow graphs.
 template <int LANES>
-__global__ void __launch_bounds__(128) response_flow_kernel(RespArgs a, const uint4* __restrict__ crec, uint32_t* dep,
+__global__ void __launch_bounds__(128) response_flow_kernel(FlowArgs a, const uint4* __restrict__ crec, uint32_t* dep,
                                                             uint32_t* q, uint32_t c_n, uint32_t* counters, uint32_t idle_ns) {
     if ((threadIdx.x & 31) >= LANES) return;
     constexpr uint32_t LMASK = LANES == 32 ? 0xFFFFFFFFu : ((1u << LANES) - 1u);
@@ -847,14 +996,13 @@ __global__ void __launch_bounds__(128) response_flow_kernel(RespArgs a, const ui
     uint4 rec = make_uint4(0, 0, EMPTY, EMPTY);    // {i, j, succ_i, succ_j} of `cur`, loaded one iteration early
     bool alive = true;
     uint32_t iters = 0;
-    // One lock-step iteration per warp, two memory phases: (1) lanes with work resolve one contact,
-    // (2) they release its successors while idle lanes try to acquire from the queue.  Lanes never
-    // wait inside the iteration, so the warp stays converged (a lane-divergent formulation
-    // serialises the lanes and is no faster than the barrier version) and each phase costs one
-    // memory round trip; the fence executes once per warp-iteration.  Software pipelining: the
-    // records of both successors are loaded while the current contact is being resolved, and the
-    // bodies they touch are prefetched to L2, so the dependent chain of a hand-off is
-    // body loads -> fence -> dependency atomics.
+    // One iteration, two memory phases: (1) a lane with work resolves one contact on the
+    // version-checked body records, (2) it releases the contact's successors while idle lanes try to
+    // acquire from the queue.  With LANES = 32 the warp runs these in lock step (lanes never wait on
+    // each other's hand-offs inside an iteration, only on the records' versions).  Software
+    // pipelining: the records of both successors are loaded while the current contact is being
+    // resolved, and the bodies they touch are prefetched to L2.  The dependent chain of a hand-off
+    // is body-record loads -> dependency atomics: no fence, the records validate themselves.
     while (true) {
         if (LANES == 1 ? !alive : !__any_sync(LMASK, alive)) break;   // the warp leaves together (and reconverges here)
         ++iters;
@@ -864,30 +1012,19 @@ __global__ void __launch_bounds__(128) response_flow_kernel(RespArgs a, const ui
         uint4 n1 = make_uint4(0, 0, EMPTY, EMPTY), n2 = make_uint4(0, 0, EMPTY, EMPTY);
         if (s1 != EMPTY) n1 = crec[s1];
         if (s2 != EMPTY) n2 = crec[s2];
-        if (work) respond(a, rec.x, rec.y);
-        // release: impulses/nudges are visible device-wide before the hand-off below.  No acquire
-        // fence is needed on the other side: everything another thread may have written is read
-        // with ld.cg / atomics issued after the queue slot or the dependency counter was observed.
-        // (The fence is the single most expensive step of a hand-off - 42 % of the stall samples - so
-        // a single-lane worker without work skips it, and nothing else is in flight when it runs:
-        // the L2 prefetches of the successors' bodies are issued behind it, next to the atomics.)
-        if (LANES != 1 || work) asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        else __nanosleep(idle_ns);                // an idle worker that polls flat out slows the busy ones down
+        if (work && !respond_rec(a, cur, rec.x, rec.y, s1 == EMPTY, s2 == EMPTY, counters)) alive = false;   // watchdog
+        if (LANES == 1 && !work) __nanosleep(idle_ns);   // an idle worker that polls flat out slows the busy ones down
         // ---- phase 2 (atomics): working lanes release their successors, idle lanes try to acquire
         if (work) {
             const uint32_t r1 = (s1 != EMPTY) ? atomicSub(&dep[s1], 1u) : 0u;
             const uint32_t r2 = (s2 != EMPTY) ? atomicSub(&dep[s2], 1u) : 0u;
             if (s1 != EMPTY) {                    // the next hand-off will touch these bodies
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vel_rest + n1.x));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vel_rest + n1.y));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pos_m + n1.x));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pos_m + n1.y));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.brec + n1.x));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.brec + n1.y));
             }
             if (s2 != EMPTY) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vel_rest + n2.x));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vel_rest + n2.y));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pos_m + n2.x));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pos_m + n2.y));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.brec + n2.x));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.brec + n2.y));
             }
             ++mine;
             uint32_t next = EMPTY;
@@ -906,7 +1043,9 @@ __global__ void __launch_bounds__(128) response_flow_kernel(RespArgs a, const ui
             cur = next;
         } else if (alive) {
             if (mine) {                           // publish finished work only when a chain has ended:
-                atomicAdd(&counters[C_DONE], mine);   // one hot-address atomic per chain, not per contact
+                // one hot-address atomic per chain, not per contact; whoever completes the count raises
+                // the FIN flag on a line nobody updates, which is what the idle workers poll
+                if (atomicAdd(&counters[C_DONE], mine) + mine >= c_n) vc[C_FIN] = 1u;
                 mine = 0;
             }
             if (slot == EMPTY) {
@@ -921,7 +1060,7 @@ __global__ void __launch_bounds__(128) response_flow_kernel(RespArgs a, const ui
                     rec = crec[c];
                     slot = EMPTY;
                     spins = 0;
-                } else if ((++spins & 15u) == 0 && (vc[C_DONE] >= c_n || vc[C_ABORT])) {
+                } else if ((++spins & 15u) == 0 && (vc[C_FIN] || vc[C_ABORT])) {
                     alive = false;                // termination is polled every 16th idle iteration
                 } else if (spins > FLOW_SPIN_LIMIT) {
                     atomicExch(&counters[C_ABORT], 1u);
@@ -1031,6 +1170,7 @@ static int ensure_buffers(tr_world* w) {
         TR_TRY(realloc_dev(&c->keys, cap));
         TR_TRY(realloc_dev((SlotRec**)&c->recs, cap));
         TR_TRY(realloc_dev(&c->sorted_ids, cap));
+        TR_TRY(realloc_dev((BodyRec**)&c->brec, cap));
         TR_TRY(realloc_dev(&c->side_list, cap));
         TR_TRY(realloc_dev(&c->far_list, cap));
         TR_TRY(realloc_dev(&c->bnd_list, cap));
@@ -1071,13 +1211,14 @@ static int ensure_buffers(tr_world* w) {
         TR_TRY(realloc_dev(&c->succ_i, want_c));
         TR_TRY(realloc_dev(&c->succ_j, want_c));
         TR_TRY(realloc_dev(&c->crec, want_c));
+        TR_TRY(realloc_dev(&c->cver, want_c));
         TR_TRY(realloc_dev(&c->frontier[0], want_c));
         TR_TRY(realloc_dev(&c->frontier[1], want_c));
         c->cap_contacts = want_c;
     }
     if (!c->counters) {
         TR_CUDA(cudaMalloc(&c->counters, C_NCOUNTERS * sizeof(uint32_t)));
-        TR_CUDA(cudaMallocHost(&c->h_counters, C_NCOUNTERS * sizeof(uint32_t)));
+        TR_CUDA(cudaMallocHost(&c->h_counters, C_NHOST * sizeof(uint32_t)));
         TR_CUDA(cudaMallocHost(&c->h_rounds, 8 * sizeof(uint32_t)));
         memset(c->h_rounds, 0, 8 * sizeof(uint32_t));
     }
@@ -1169,7 +1310,7 @@ static int broad_phase(tr_world* w) {
 
 static int read_counters(tr_world* w) {
     Collide* c = state(w);
-    TR_CUDA(cudaMemcpyAsync(c->h_counters, c->counters, C_NCOUNTERS * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+    TR_CUDA(cudaMemcpyAsync(c->h_counters, c->counters, C_NHOST * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
     TR_CUDA(cudaStreamSynchronize(w->stream));
     return TR_OK;
 }
@@ -1313,14 +1454,15 @@ int collide_step(tr_world* w) {
     const bool flow = w->params.response_mode != 1;   // 1 selects the level-synchronous kernel
     if (flow) TR_CUDA(cudaMemsetAsync(c->frontier[0], 0xFF, (size_t)cn * sizeof(uint32_t), w->stream));   // queue = all EMPTY
     deps_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, c->colc, c->col_pos, c->row_start, c->col_start, cn, c->dep, c->succ_i,
-                                                c->succ_j, c->crec, c->frontier[0], c->counters, flow ? C_QTAIL : C_FRONT);
+                                                c->succ_j, c->crec, c->frontier[0], c->counters, flow ? C_QTAIL : C_FRONT, w->pos_m[w->cur],
+                                                w->vel_rest, flow ? (BodyRec*)c->brec : nullptr, c->cver);
     if (flow) {
-        RespArgs ra{w->pos_m[w->cur], w->vel_rest, w->center_r, w->half_ext, w->flags};
+        FlowArgs ra{w->pos_m[w->cur], w->vel_rest, w->pos_m[w->cur], w->vel_rest, w->center_r, w->half_ext, w->flags, (BodyRec*)c->brec, c->cver};
         int fblocks = w->num_sms;                     // resident by construction: 128 threads per SM
         int fwant = (int)((cn + 127) / 128);
         if (fwant < fblocks) fblocks = fwant < 1 ? 1 : fwant;
         // Executor width.  Deep graphs (a packed lattice: ~800 dependent hand-offs) are latency bound:
-        // single-lane workers, 6 CTAs of 4 warps per SM (3, 4, 8 per SM: 3.0, 2.6, 2.5 ms against 2.4).
+        // single-lane workers, 6 CTAs of 4 warps per SM (3, 4, 5, 7 per SM: 2.47, 2.08, 1.90, 1.82 ms against 1.78).
         // Wide shallow graphs are throughput bound: whole warps.  The previous step tells which:
         // contacts per lock-step iteration of its longest worker.
         bool wide = w->params.response_mode == 2;
@@ -1331,15 +1473,15 @@ int collide_step(tr_world* w) {
             int sblocks = w->num_sms * 6;
             const int swant = (int)((cn + 3) / 4);
             if (swant < sblocks) sblocks = swant < 1 ? 1 : swant;
-            // idle back-off swept on the packed 1M scene: 100 / 300 / 600 / 1000 / 2000 ns -> 2.58 / 2.33 / 2.29 / 2.30 / 2.51 ms
-            response_flow_kernel<1><<<sblocks, 128, 0, w->stream>>>(ra, c->crec, c->dep, c->frontier[0], cn, c->counters, 700u);
+            // idle back-off: 300 and 700 ns are equivalent (1.78 / 1.80 ms), 100 ns and 2000 ns are 10 % slower
+            response_flow_kernel<1><<<sblocks, 128, 0, w->stream>>>(ra, c->crec, c->dep, c->frontier[0], cn, c->counters, 500u);
         }
         TR_CUDA(cudaGetLastError());
         timer_end(w, &t);
         w->stats.kernel_launches += 12;   // 2 x (hist, tile sums, scan, scatter, rank) + deps + response
         c->last_contacts = count;
         // watchdog flag + (unused) round counter come back with the next sync
-        TR_CUDA(cudaMemcpyAsync(c->h_rounds, c->counters + C_ROUNDS, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+        TR_CUDA(cudaMemcpyAsync(c->h_rounds, c->counters + C_ROUNDS, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
         c->rounds_pending = true;
         c->flow_pending = true;
         return TR_OK;
@@ -1462,7 +1604,7 @@ int collide_free(tr_world* w) {
     if (c->h_rounds) cudaFreeHost(c->h_rounds);
     cudaFree(c->ckeys); cudaFree(c->ckeys_alt); cudaFree(c->colkeys);
     cudaFree(c->colc); cudaFree(c->col_pos); cudaFree(c->dep);
-    cudaFree(c->succ_i); cudaFree(c->succ_j); cudaFree(c->crec); cudaFree(c->frontier[0]); cudaFree(c->frontier[1]);
+    cudaFree(c->succ_i); cudaFree(c->succ_j); cudaFree(c->crec); cudaFree(c->cver); cudaFree(c->brec); cudaFree(c->frontier[0]); cudaFree(c->frontier[1]);
     if (c->bp_graph) cudaGraphExecDestroy(c->bp_graph);
     delete c;
     w->col = nullptr;
