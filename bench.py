@@ -352,7 +352,7 @@ def main():
         prof = os.path.join(ROOT, "profiles", "broadphase_traffic.json")
         if os.path.exists(prof):
             try:
-                bp_traffic = json.load(open(prof)).get(str(n))
+                bp_traffic = json.load(open(prof)).get(f"{name}:{n}")   # ncu capture of this workload only
             except Exception:
                 bp_traffic = None
         bp = {"bound": "hbm", "kernel": "broad phase K2-K3b (keys + histogram, cell-table scan, scatter of 32-byte body records into cell order)", "achieved": ach,
