@@ -108,6 +108,7 @@ struct Collide {
     uint32_t* succ_j = nullptr;
     uint4* crec = nullptr;                    // packed {i, j, succ_i, succ_j} per contact (dataflow executor)
     uint2* cver = nullptr;                    // versions of bodies i and j that contact c must see (dataflow executor)
+    struct tr_contact_geo* cgeo = nullptr;    // per contact: normal, inverse masses, restitution, static bits (tr::ContactGeo)
     struct tr_body_rec* brec = nullptr;       // per body: version-checked velocity + position record (tr::BodyRec)
     uint32_t* frontier[2] = {nullptr, nullptr};
 
@@ -692,6 +693,47 @@ __global__ void __launch_bounds__(256) crank_col_kernel(const unsigned long long
 // Body b's contacts in sweep order are: its column entries (k,b) by ascending k, then its
 // row entries (b,j) by ascending j.  pred/succ below are the neighbours of contact c in the
 // lists of its two bodies.
+// Everything about a contact that the sweep never changes - the contact normal (collider centres are
+// not touched by the response, main.cpp:655-659 vs 725-741), the inverse masses, min(restitution),
+// the isStatic bits - is computed once, in parallel, by the K6 prep and stored in one 32-byte
+// record, so the square root and five of the six IEEE divisions of a contact are off the critical
+// path of the ordered replay and a contact costs one load for all its constants.
+struct __align__(32) ContactGeo {
+    float nx, ny, nz;      // main.cpp:703 / calculateAABBNormal
+    float ima, imb;        // 1/ma, 1/mb
+    float den;             // (1/ma) + (1/mb)
+    float e;               // std::min(a.rest, b.rest)
+    uint32_t bits;         // 1: a.isStatic, 2: b.isStatic
+};
+static_assert(sizeof(ContactGeo) == 32, "one sector");
+
+__device__ __forceinline__ void contact_normal(uint8_t fi, uint8_t fj, const float4 ci, const float4 cj, const float4* half_ext,
+                                               uint32_t i, uint32_t j, float& nx, float& ny, float& nz) {
+    if ((fi & F_SPHERE) && (fj & F_SPHERE)) {
+        // normalize(b.center - a.center), main.cpp:703 + 211-223
+        float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
+        float len = __fsqrt_rn(dot3_rn(dx, dy, dz, dx, dy, dz));
+        if (len != 0.0f) {
+            nx = __fdiv_rn(dx, len);
+            ny = __fdiv_rn(dy, len);
+            nz = __fdiv_rn(dz, len);
+        } else {
+            nx = dx; ny = dy; nz = dz;
+        }
+    } else {
+        // calculateAABBNormal, main.cpp:622-638
+        const float4 hi = half_ext[i], hj = half_ext[j];
+        float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
+        float ox = __fsub_rn(__fadd_rn(hi.x, hj.x), fabsf(dx));
+        float oy = __fsub_rn(__fadd_rn(hi.y, hj.y), fabsf(dy));
+        float oz = __fsub_rn(__fadd_rn(hi.z, hj.z), fabsf(dz));
+        nx = ny = nz = 0.0f;
+        if (ox < oy && ox < oz) nx = dx > 0 ? 1.0f : -1.0f;
+        else if (oy < oz) ny = dy > 0 ? 1.0f : -1.0f;
+        else nz = dz > 0 ? 1.0f : -1.0f;
+    }
+}
+
 // Dataflow executors keep the mutable state of a body that is in contact in ONE 32-byte record
 // whose two 16-byte halves both carry a version = number of contacts applied to the body so far.
 // A contact knows the versions it must see (its rank in the sweep order of each of its bodies),
@@ -731,7 +773,9 @@ __global__ void __launch_bounds__(256) deps_kernel(const unsigned long long* __r
                                                    uint32_t* __restrict__ succ_j, uint4* __restrict__ crec,
                                                    uint32_t* __restrict__ frontier0, uint32_t* counters, int ready_counter,
                                                    const float4* __restrict__ pos_m, const float4* __restrict__ vel_rest,
-                                                   BodyRec* __restrict__ brec, uint2* __restrict__ cver) {
+                                                   const float4* __restrict__ center_r, const float4* __restrict__ half_ext,
+                                                   const uint8_t* __restrict__ flags, BodyRec* __restrict__ brec,
+                                                   uint2* __restrict__ cver, ContactGeo* __restrict__ cgeo) {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= c_n) return;
     unsigned long long k = ckeys[c];
@@ -749,10 +793,20 @@ __global__ void __launch_bounds__(256) deps_kernel(const unsigned long long* __r
     succ_i[c] = si;
     succ_j[c] = sj;
     crec[c] = make_uint4(i, j, si, sj);
-    if (brec) {                                   // dataflow executors: expected versions, version-0 records
+    if (brec) {                                   // dataflow executors: expected versions, version-0 records, constants
         cver[c] = make_uint2(ei, ej);
-        if (ei == 0) st_body(brec + i, vel_rest[i], pos_m[i], 0u);
-        if (ej == 0) st_body(brec + j, vel_rest[j], pos_m[j], 0u);
+        const float4 vi = vel_rest[i], vj = vel_rest[j], pi = pos_m[i], pj = pos_m[j];
+        if (ei == 0) st_body(brec + i, vi, pi, 0u);
+        if (ej == 0) st_body(brec + j, vj, pj, 0u);
+        const uint8_t fi = flags[i], fj = flags[j];
+        ContactGeo g;
+        contact_normal(fi, fj, center_r[i], center_r[j], half_ext, i, j, g.nx, g.ny, g.nz);
+        g.ima = __fdiv_rn(1.0f, pi.w);
+        g.imb = __fdiv_rn(1.0f, pj.w);
+        g.den = __fadd_rn(g.ima, g.imb);
+        g.e = (vj.w < vi.w) ? vj.w : vi.w;               // std::min(a.rest, b.rest)
+        g.bits = ((fi & F_STATIC) ? 1u : 0u) | ((fj & F_STATIC) ? 2u : 0u);
+        cgeo[c] = g;
     }
     if (d == 0) frontier0[atomicAdd(&counters[ready_counter], 1u)] = c;
 }
@@ -840,47 +894,18 @@ struct FlowArgs {
     const float4* vel_rest;    // .w = restitution (immutable)
     float4* pos_out;
     float4* vel_out;
-    const float4* center_r;
-    const float4* half_ext;
-    const uint8_t* flags;
     BodyRec* brec;
     const uint2* cver;
+    const ContactGeo* cgeo;
 };
 constexpr uint32_t VERSION_SPIN_LIMIT = 1u << 20;
 
 __device__ __forceinline__ bool respond_rec(const FlowArgs& a, uint32_t c, uint32_t i, uint32_t j, bool last_i, bool last_j,
                                             uint32_t* counters) {
-    const uint8_t fi = a.flags[i], fj = a.flags[j];
-    const float4 ci = a.center_r[i], cj = a.center_r[j];
     const uint2 want = a.cver[c];
-    const float mi = a.pos_m[i].w, mj = a.pos_m[j].w;
-    const float ri = a.vel_rest[i].w, rj = a.vel_rest[j].w;
     float4 vi, vj, pi, pj;
     bool oki = ld_body(a.brec + i, want.x, vi, pi), okj = ld_body(a.brec + j, want.y, vj, pj);
-    float nx, ny, nz;
-    if ((fi & F_SPHERE) && (fj & F_SPHERE)) {
-        // normalize(b.center - a.center), main.cpp:703 + 211-223
-        float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
-        float len = __fsqrt_rn(dot3_rn(dx, dy, dz, dx, dy, dz));
-        if (len != 0.0f) {
-            nx = __fdiv_rn(dx, len);
-            ny = __fdiv_rn(dy, len);
-            nz = __fdiv_rn(dz, len);
-        } else {
-            nx = dx; ny = dy; nz = dz;
-        }
-    } else {
-        // calculateAABBNormal, main.cpp:622-638
-        const float4 hi = a.half_ext[i], hj = a.half_ext[j];
-        float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
-        float ox = __fsub_rn(__fadd_rn(hi.x, hj.x), fabsf(dx));
-        float oy = __fsub_rn(__fadd_rn(hi.y, hj.y), fabsf(dy));
-        float oz = __fsub_rn(__fadd_rn(hi.z, hj.z), fabsf(dz));
-        nx = ny = nz = 0.0f;
-        if (ox < oy && ox < oz) nx = dx > 0 ? 1.0f : -1.0f;
-        else if (oy < oz) ny = dy > 0 ? 1.0f : -1.0f;
-        else nz = dz > 0 ? 1.0f : -1.0f;
-    }
+    const ContactGeo g = a.cgeo[c];
     // the writer's stores may still be on their way when its hand-off arrives: poll until they land
     uint32_t spins = 0;
     while (!oki || !okj) {
@@ -892,41 +917,39 @@ __device__ __forceinline__ bool respond_rec(const FlowArgs& a, uint32_t c, uint3
         }
     }
     float rvx = __fsub_rn(vi.x, vj.x), rvy = __fsub_rn(vi.y, vj.y), rvz = __fsub_rn(vi.z, vj.z);
-    float vn = dot3_rn(rvx, rvy, rvz, nx, ny, nz);
+    float vn = dot3_rn(rvx, rvy, rvz, g.nx, g.ny, g.nz);
     if (!(vn > 0)) {                                     // main.cpp:714 (as written)
-        float e = (rj < ri) ? rj : ri;                   // std::min(a.rest, b.rest)
-        float jimp = __fmul_rn(-__fadd_rn(1.0f, e), vn); // -(1 + e) * vn
-        float ima = __fdiv_rn(1.0f, mi), imb = __fdiv_rn(1.0f, mj);
-        jimp = __fdiv_rn(jimp, __fadd_rn(ima, imb));
-        float ix = __fmul_rn(nx, jimp), iy = __fmul_rn(ny, jimp), iz = __fmul_rn(nz, jimp);
+        float jimp = __fmul_rn(-__fadd_rn(1.0f, g.e), vn);   // -(1 + e) * vn
+        jimp = __fdiv_rn(jimp, g.den);                   // / (1/ma + 1/mb)
+        float ix = __fmul_rn(g.nx, jimp), iy = __fmul_rn(g.ny, jimp), iz = __fmul_rn(g.nz, jimp);
         const float kcorr = 0.2f * 0.01f;                // percent * penetrationSlop (fp32 product)
-        float cx = __fmul_rn(nx, kcorr), cy = __fmul_rn(ny, kcorr), cz = __fmul_rn(nz, kcorr);
-        if (!(fi & F_STATIC)) {
-            vi.x = __fsub_rn(vi.x, __fmul_rn(ix, ima));
-            vi.y = __fsub_rn(vi.y, __fmul_rn(iy, ima));
-            vi.z = __fsub_rn(vi.z, __fmul_rn(iz, ima));
-            pi.x = __fsub_rn(pi.x, __fmul_rn(cx, ima));
-            pi.y = __fsub_rn(pi.y, __fmul_rn(cy, ima));
-            pi.z = __fsub_rn(pi.z, __fmul_rn(cz, ima));
+        float cx = __fmul_rn(g.nx, kcorr), cy = __fmul_rn(g.ny, kcorr), cz = __fmul_rn(g.nz, kcorr);
+        if (!(g.bits & 1u)) {
+            vi.x = __fsub_rn(vi.x, __fmul_rn(ix, g.ima));
+            vi.y = __fsub_rn(vi.y, __fmul_rn(iy, g.ima));
+            vi.z = __fsub_rn(vi.z, __fmul_rn(iz, g.ima));
+            pi.x = __fsub_rn(pi.x, __fmul_rn(cx, g.ima));
+            pi.y = __fsub_rn(pi.y, __fmul_rn(cy, g.ima));
+            pi.z = __fsub_rn(pi.z, __fmul_rn(cz, g.ima));
         }
-        if (!(fj & F_STATIC)) {
-            vj.x = __fadd_rn(vj.x, __fmul_rn(ix, imb));
-            vj.y = __fadd_rn(vj.y, __fmul_rn(iy, imb));
-            vj.z = __fadd_rn(vj.z, __fmul_rn(iz, imb));
-            pj.x = __fadd_rn(pj.x, __fmul_rn(cx, imb));
-            pj.y = __fadd_rn(pj.y, __fmul_rn(cy, imb));
-            pj.z = __fadd_rn(pj.z, __fmul_rn(cz, imb));
+        if (!(g.bits & 2u)) {
+            vj.x = __fadd_rn(vj.x, __fmul_rn(ix, g.imb));
+            vj.y = __fadd_rn(vj.y, __fmul_rn(iy, g.imb));
+            vj.z = __fadd_rn(vj.z, __fmul_rn(iz, g.imb));
+            pj.x = __fadd_rn(pj.x, __fmul_rn(cx, g.imb));
+            pj.y = __fadd_rn(pj.y, __fmul_rn(cy, g.imb));
+            pj.z = __fadd_rn(pj.z, __fmul_rn(cz, g.imb));
         }
     }
     if (last_i) {                                        // nobody reads the record again: back to the SoA state
-        a.vel_out[i] = make_float4(vi.x, vi.y, vi.z, ri);
-        a.pos_out[i] = make_float4(pi.x, pi.y, pi.z, mi);
+        a.vel_out[i] = make_float4(vi.x, vi.y, vi.z, a.vel_rest[i].w);
+        a.pos_out[i] = make_float4(pi.x, pi.y, pi.z, a.pos_m[i].w);
     } else {
         st_body(a.brec + i, vi, pi, want.x + 1u);
     }
     if (last_j) {
-        a.vel_out[j] = make_float4(vj.x, vj.y, vj.z, rj);
-        a.pos_out[j] = make_float4(pj.x, pj.y, pj.z, mj);
+        a.vel_out[j] = make_float4(vj.x, vj.y, vj.z, a.vel_rest[j].w);
+        a.pos_out[j] = make_float4(pj.x, pj.y, pj.z, a.pos_m[j].w);
     } else {
         st_body(a.brec + j, vj, pj, want.y + 1u);
     }
@@ -1212,6 +1235,7 @@ static int ensure_buffers(tr_world* w) {
         TR_TRY(realloc_dev(&c->succ_j, want_c));
         TR_TRY(realloc_dev(&c->crec, want_c));
         TR_TRY(realloc_dev(&c->cver, want_c));
+        TR_TRY(realloc_dev((ContactGeo**)&c->cgeo, want_c));
         TR_TRY(realloc_dev(&c->frontier[0], want_c));
         TR_TRY(realloc_dev(&c->frontier[1], want_c));
         c->cap_contacts = want_c;
@@ -1455,9 +1479,10 @@ int collide_step(tr_world* w) {
     if (flow) TR_CUDA(cudaMemsetAsync(c->frontier[0], 0xFF, (size_t)cn * sizeof(uint32_t), w->stream));   // queue = all EMPTY
     deps_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, c->colc, c->col_pos, c->row_start, c->col_start, cn, c->dep, c->succ_i,
                                                 c->succ_j, c->crec, c->frontier[0], c->counters, flow ? C_QTAIL : C_FRONT, w->pos_m[w->cur],
-                                                w->vel_rest, flow ? (BodyRec*)c->brec : nullptr, c->cver);
+                                                w->vel_rest, w->center_r, w->half_ext, w->flags, flow ? (BodyRec*)c->brec : nullptr, c->cver,
+                                                (ContactGeo*)c->cgeo);
     if (flow) {
-        FlowArgs ra{w->pos_m[w->cur], w->vel_rest, w->pos_m[w->cur], w->vel_rest, w->center_r, w->half_ext, w->flags, (BodyRec*)c->brec, c->cver};
+        FlowArgs ra{w->pos_m[w->cur], w->vel_rest, w->pos_m[w->cur], w->vel_rest, (BodyRec*)c->brec, c->cver, (const ContactGeo*)c->cgeo};
         int fblocks = w->num_sms;                     // resident by construction: 128 threads per SM
         int fwant = (int)((cn + 127) / 128);
         if (fwant < fblocks) fblocks = fwant < 1 ? 1 : fwant;
@@ -1470,7 +1495,8 @@ int collide_step(tr_world* w) {
         if (wide) {
             response_flow_kernel<32><<<fblocks, 128, 0, w->stream>>>(ra, c->crec, c->dep, c->frontier[0], cn, c->counters, 0u);
         } else {
-            int sblocks = w->num_sms * 6;
+            static const int per_sm = getenv("TR_FLOW_CTAS") ? atoi(getenv("TR_FLOW_CTAS")) : 6;
+            int sblocks = w->num_sms * per_sm;
             const int swant = (int)((cn + 3) / 4);
             if (swant < sblocks) sblocks = swant < 1 ? 1 : swant;
             // idle back-off: 300 and 700 ns are equivalent (1.78 / 1.80 ms), 100 ns and 2000 ns are 10 % slower
@@ -1604,7 +1630,7 @@ int collide_free(tr_world* w) {
     if (c->h_rounds) cudaFreeHost(c->h_rounds);
     cudaFree(c->ckeys); cudaFree(c->ckeys_alt); cudaFree(c->colkeys);
     cudaFree(c->colc); cudaFree(c->col_pos); cudaFree(c->dep);
-    cudaFree(c->succ_i); cudaFree(c->succ_j); cudaFree(c->crec); cudaFree(c->cver); cudaFree(c->brec); cudaFree(c->frontier[0]); cudaFree(c->frontier[1]);
+    cudaFree(c->succ_i); cudaFree(c->succ_j); cudaFree(c->crec); cudaFree(c->cver); cudaFree(c->cgeo); cudaFree(c->brec); cudaFree(c->frontier[0]); cudaFree(c->frontier[1]);
     if (c->bp_graph) cudaGraphExecDestroy(c->bp_graph);
     delete c;
     w->col = nullptr;
