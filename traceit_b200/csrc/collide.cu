@@ -1019,6 +1019,9 @@ __global__ void __launch_bounds__(128) response_flow_kernel(FlowArgs a, const ui
     uint4 rec = make_uint4(0, 0, EMPTY, EMPTY);    // {i, j, succ_i, succ_j} of `cur`, loaded one iteration early
     bool alive = true;
     uint32_t iters = 0;
+#ifdef TR_FLOW_STATS   // instrumented build (make EXTRA=-DTR_FLOW_STATS TAG=stats OUT=...): cycles of the busy iterations
+    unsigned long long st_busy = 0, st_nbusy = 0, st_push = 0;
+#endif
     // One iteration, two memory phases: (1) a lane with work resolves one contact on the
     // version-checked body records, (2) it releases the contact's successors while idle lanes try to
     // acquire from the queue.  With LANES = 32 the warp runs these in lock step (lanes never wait on
@@ -1031,6 +1034,9 @@ __global__ void __launch_bounds__(128) response_flow_kernel(FlowArgs a, const ui
         ++iters;
         // ---- phase 1 (loads): successors' records + this contact's bodies, all in flight together
         const bool work = cur != EMPTY;
+#ifdef TR_FLOW_STATS
+        const long long st_t0 = clock64();
+#endif
         const uint32_t s1 = work ? rec.z : EMPTY, s2 = work ? rec.w : EMPTY;
         uint4 n1 = make_uint4(0, 0, EMPTY, EMPTY), n2 = make_uint4(0, 0, EMPTY, EMPTY);
         if (s1 != EMPTY) n1 = crec[s1];
@@ -1064,6 +1070,11 @@ __global__ void __launch_bounds__(128) response_flow_kernel(FlowArgs a, const ui
                 }
             }
             cur = next;
+#ifdef TR_FLOW_STATS
+            st_busy += (unsigned long long)(clock64() - st_t0);
+            ++st_nbusy;
+            st_push += (r1 == 1u && r2 == 1u) ? 1u : 0u;
+#endif
         } else if (alive) {
             if (mine) {                           // publish finished work only when a chain has ended:
                 // one hot-address atomic per chain, not per contact; whoever completes the count raises
@@ -1092,6 +1103,20 @@ __global__ void __launch_bounds__(128) response_flow_kernel(FlowArgs a, const ui
             }
         }
     }
+#ifdef TR_FLOW_STATS
+    {
+        unsigned long long* st = reinterpret_cast<unsigned long long*>(counters + C_NCOUNTERS);
+        atomicAdd(st + 0, st_busy);
+        atomicAdd(st + 1, st_nbusy);
+        atomicAdd(st + 2, st_push);
+        atomicAdd(st + 3, (unsigned long long)iters);
+        if (atomicAdd(st + 4, 1ull) + 1ull == (unsigned long long)gridDim.x * (blockDim.x / 32) * LANES) {
+            printf("[TR_FLOW_STATS] workers %llu busy iterations %llu avg cycles per busy iteration %.0f queue pushes %llu all iterations %llu\n",
+                   st[4], st[1], (double)st[0] / (double)st[1], st[2], st[3]);
+            for (int k = 0; k < 5; ++k) st[k] = 0;
+        }
+    }
+#endif
     if ((threadIdx.x & 31) == 0) atomicMax(&counters[C_ROUNDS], iters);   // observability: longest warp
 }
 
@@ -1241,7 +1266,8 @@ static int ensure_buffers(tr_world* w) {
         c->cap_contacts = want_c;
     }
     if (!c->counters) {
-        TR_CUDA(cudaMalloc(&c->counters, C_NCOUNTERS * sizeof(uint32_t)));
+        TR_CUDA(cudaMalloc(&c->counters, (C_NCOUNTERS + 32) * sizeof(uint32_t)));   // + statistics of TR_FLOW_STATS builds
+        TR_CUDA(cudaMemset(c->counters, 0, (C_NCOUNTERS + 32) * sizeof(uint32_t)));
         TR_CUDA(cudaMallocHost(&c->h_counters, C_NHOST * sizeof(uint32_t)));
         TR_CUDA(cudaMallocHost(&c->h_rounds, 8 * sizeof(uint32_t)));
         memset(c->h_rounds, 0, 8 * sizeof(uint32_t));
