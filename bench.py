@@ -210,7 +210,26 @@ def run_reference_arm(args, rank: int):
         "e2e": {"value": r["value"], "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout: anything a library prints there (NCCL's version
+    banner under NCCL_DEBUG=VERSION, for one) is sent to stderr instead."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 # ------------------------------------------------------------------------------------------
@@ -221,6 +240,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
+        protect_stdout()
         run_reference_arm(args, rank)
         return
 
@@ -230,6 +250,7 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
 
+    protect_stdout()
     import torch
     import torch.distributed as dist
 
@@ -448,7 +469,7 @@ def main():
         "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3, "secondary": secondary,
     }
     line.update(extra)
-    print(json.dumps(line))
+    emit(line)
 
 
 if __name__ == "__main__":
