@@ -1,7 +1,7 @@
 """Small end-to-end case for compute-sanitizer (memcheck / racecheck): every kernel of the
 library runs at least once - gravity with the fused integrator (incl. the guarded diagonal path
 and ragged tails), standalone integrator, counting-sort broad phase, narrow phase, side list,
-ordered response, radix-sort fallback, pack/unpack."""
+far list, every ordered-response executor, a crowded cell, pack/unpack."""
 import sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -21,8 +21,11 @@ with tr.World(tr.default_params(flags=tr.PAIR_GRAVITY | tr.COLLISIONS, G=np.floa
 with tr.World(tr.default_params()) as w:
     w.add(scenes.default_scene()); w.step(20); w.read_state()
 d = scenes.dense_lattice(8)
-with tr.World(tr.default_params(g=(0, 0, 0))) as w:
-    w.add(d); w.step(2); w.contacts()
+d["pos"][:6] += np.float32(4.0e4)          # a few bodies outside the grid domain: far list
+d["center"] = d["pos"]
+for mode in (0, 1, 2, 3):
+    with tr.World(tr.default_params(g=(0, 0, 0), response_mode=mode)) as w:
+        w.add(d); w.step(2); w.contacts()
 c = scenes.random_cloud(2500, 2, spheres=True)
 c["pos"][:1200] = 0.5; c["center"] = c["pos"]
 with tr.World(tr.default_params(g=(0, 0, 0), max_contacts=2_000_000)) as w:
