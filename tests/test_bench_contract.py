@@ -48,3 +48,13 @@ def test_gpu_arm_fails_loudly_without_a_gpu():
         pytest.skip("a GPU is present")
     r = _run(["--steps", "1", "--warmup", "0", "--workload", "cfg2"])
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_library_chatter_on_stdout_is_diverted():
+    """NCCL prints its version banner on stdout under NCCL_DEBUG=VERSION: the JSON line must stay alone there."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.protect_stdout(); "
+            "os.write(1, b'NCCL version 2.28.9+cuda12.9\\n'); print('more chatter'); bench.emit({'a': 1})") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout == '{"a": 1}\n'
+    assert "NCCL version" in r.stderr and "more chatter" in r.stderr
