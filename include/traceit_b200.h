@@ -103,11 +103,12 @@ typedef struct tr_stats {
     uint64_t last_contacts;      /* contacts found by the last step                      */
     uint64_t last_candidates;    /* candidate pairs tested by the last step (debug mode) */
     uint32_t last_response_rounds; /* last ordered response: wavefronts (level-synchronous)
-                                      or lock-step iterations of the longest warp (dataflow) */
-    uint32_t side_list_size;     /* bodies outside the grid at the last step             */
+                                      or iterations of the longest worker (dataflow)      */
+    uint32_t side_list_size;     /* bodies outside the grid at the last step: oversize /
+                                    non-finite extent (side list) + outside the domain (far list) */
     double gravity_ms;           /* accumulated device time of the gravity kernel        */
     uint64_t gravity_launches;
-    double broadphase_ms;        /* keys + sort + ranges (K2-K4)                         */
+    double broadphase_ms;        /* keys + histogram, cell-table scan, record scatter (K2-K3b) */
     uint64_t broadphase_launches;/* number of timed broad-phase passes (one per step)    */
     double narrowphase_ms;       /* K5                                                   */
     double response_ms;          /* contact sort + dependency build + K6                 */
