@@ -1,0 +1,364 @@
+// K2-K5c: grid keys + histogram, record scatter, on-demand stable order, narrow phase, side and far lists.
+// Device code only; included by collide.cu after collide_common.cuh.
+#pragma once
+#include "collide_common.cuh"
+
+namespace tr {
+
+// ---------------------------------------------------------------------------------------
+// K2: keys + classification (+ per-cell histogram on the fast path)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ center_r, const float4* __restrict__ half_ext,
+                                                   const uint8_t* __restrict__ flags, uint32_t n, GridParams g,
+                                                   uint32_t* __restrict__ keys,
+                                                   uint8_t* __restrict__ klass, uint32_t* __restrict__ side_list,
+                                                   uint32_t* __restrict__ far_list, float4* __restrict__ far_c,
+                                                   uint32_t* __restrict__ bnd_list, float4* __restrict__ bnd_c,
+                                                   uint32_t* __restrict__ cell_count, uint32_t* counters) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    {
+        // stream the (zeroed) histogram into L2 ahead of the scattered REDs: one 128-byte line per
+        // thread of the leading CTAs, so random cloud ids do not pay a DRAM round trip per atomic
+        const uint32_t ncell = 1u << (3 * g.bits);
+        if (i < ncell / 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(cell_count + (size_t)i * 32));
+    }
+    if (i < n) {
+        const float4 c = center_r[i];
+        const uint8_t f = flags[i];
+        const uint32_t sentinel = 1u << (3 * g.bits);
+        uint32_t key = sentinel;
+        uint8_t k = 0;
+        if (f & F_LIVE) {   // main.cpp:696 drops mass<=0 bodies from every pair (flag set at upload)
+            float ux = __fmul_rn(__fsub_rn(c.x, g.ox), g.inv_cell);
+            float uy = __fmul_rn(__fsub_rn(c.y, g.oy), g.inv_cell);
+            float uz = __fmul_rn(__fsub_rn(c.z, g.oz), g.inv_cell);
+            const bool in_domain = fabsf(ux) < 32768.0f && fabsf(uy) < 32768.0f && fabsf(uz) < 32768.0f;
+            const bool finite_c = fabsf(c.x) <= 3.0e38f && fabsf(c.y) <= 3.0e38f && fabsf(c.z) <= 3.0e38f;   // false for NaN / inf
+            bool fits;   // extent admitted to the grid
+            if (g.mixed) {
+                // any body may meet a box, and box pairs use collider::size of BOTH bodies (main.cpp:704-705)
+                const float4 h = half_ext[i];
+                float ext = fmaxf(fmaxf(fabsf(h.x), fabsf(h.y)), fabsf(h.z));
+                const bool finite_h = fabsf(h.x) <= 3.0e38f && fabsf(h.y) <= 3.0e38f && fabsf(h.z) <= 3.0e38f;
+                if (f & F_SPHERE) ext = fmaxf(ext, fabsf(c.w));
+                fits = finite_h && ext <= g.rmax_grid && (!(f & F_SPHERE) || fabsf(c.w) <= g.rmax_grid);
+            } else {
+                fits = (f & F_SPHERE) && fabsf(c.w) <= g.rmax_grid;
+            }
+            if (fits && in_domain) {
+                key = pack_key(__float2int_rd(ux), __float2int_rd(uy), __float2int_rd(uz), g.bits);
+                k = 1;
+                atomicAdd(&cell_count[key], 1u);   // result unused: a fire-and-forget RED
+                // grid bodies within two cells of the domain boundary are the only ones a "far" body can touch
+                if (fmaxf(fmaxf(fabsf(ux), fabsf(uy)), fabsf(uz)) >= 32766.0f) {
+                    const uint32_t slot = atomicAdd(&counters[C_BND], 1u);
+                    bnd_list[slot] = pack_val(i, f);
+                    bnd_c[slot] = c;
+                }
+            } else if (fits && finite_c) {
+                // "far": normal extent, finite centre, outside the grid domain.  It can only touch other
+                // far bodies, boundary grid bodies (computed |u| differs by >= 2 cells from everyone else:
+                // more than the largest admitted reach) and oversize side-list bodies.
+                k = 4;
+                const uint32_t slot = atomicAdd(&counters[C_FAR], 1u);
+                far_list[slot] = pack_val(i, f);
+                far_c[slot] = c;
+            } else if (fits && g.rmax_grid < 1.0e18f) {
+                // "lost": a NaN / infinite centre makes both predicates false (delta is +-inf or NaN)
+                // unless the radius / size SUM is itself infinite, i.e. the partner is an oversize
+                // side-list body.  Not a grid body, not a side-list body; side_kernel still tests it
+                // against every side-list body.  (Bodies the reference's inverted approach test blows
+                // up end here instead of turning the side list into an O(N^2) sweep.)
+                k = 3;
+            } else {
+                k = 2;
+                uint32_t slot = atomicAdd(&counters[C_SIDE], 1u);
+                side_list[slot] = i;
+            }
+        }
+        keys[i] = key;
+        klass[i] = k;
+    }
+}
+
+// K3b: one record per grid body into its cell's segment; counting the histogram back down leaves it
+// zeroed for the next step.  The record carries everything the narrow phase reads about a body -
+// centre + radius, id|flags, AABB half extents - in ONE 32-byte sector written by one 256-bit store
+// (SASS STG.E.ENL2.256) and read back by one 256-bit load, so nothing is gathered by id afterwards.
+struct __align__(32) SlotRec {
+    float4 c;              // collider centre, radius
+    uint32_t val;          // id | BOX_BIT | STATIC_BIT
+    float hx, hy, hz;      // collider::size (meaningful in mixed worlds only)
+};
+static_assert(sizeof(SlotRec) == 32, "one sector");
+
+__device__ __forceinline__ void st_rec(SlotRec* p, const float4 c, uint32_t val, const float4 h) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(__float_as_uint(c.x)), "r"(__float_as_uint(c.y)),
+                 "r"(__float_as_uint(c.z)), "r"(__float_as_uint(c.w)), "r"(val), "r"(__float_as_uint(h.x)),
+                 "r"(__float_as_uint(h.y)), "r"(__float_as_uint(h.z))
+                 : "memory");
+}
+__device__ __forceinline__ void ld_rec(const SlotRec* p, float4& c, uint32_t& val, float4& h) {
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+                 : "l"(p));
+    c = make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3));
+    val = r4;
+    h = make_float4(__uint_as_float(r5), __uint_as_float(r6), __uint_as_float(r7), 0.f);
+}
+
+// the key of an in-domain centre: the same operations as K2, hence the same key
+__device__ __forceinline__ uint32_t cell_key(const float4 c, const GridParams& g) {
+    const float ux = __fmul_rn(__fsub_rn(c.x, g.ox), g.inv_cell);
+    const float uy = __fmul_rn(__fsub_rn(c.y, g.oy), g.inv_cell);
+    const float uz = __fmul_rn(__fsub_rn(c.z, g.oz), g.inv_cell);
+    return pack_key(__float2int_rd(ux), __float2int_rd(uy), __float2int_rd(uz), g.bits);
+}
+
+__global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict__ keys, uint32_t sentinel,
+                                                      const uint8_t* __restrict__ flags, const float4* __restrict__ center_r,
+                                                      const float4* __restrict__ half_ext,   // NULL unless boxes are in the grid
+                                                      uint32_t n, const uint32_t* __restrict__ cell_start,
+                                                      uint32_t* __restrict__ cell_count, SlotRec* __restrict__ recs) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t key = keys[i];
+    if (key >= sentinel) return;          // side-list, far, lost or dropped body
+    const float4 c = center_r[i];
+    float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (half_ext) h = half_ext[i];
+    const uint32_t val = pack_val(i, flags[i]);
+    const uint32_t old = atomicSub(&cell_count[key], 1u);
+    st_rec(recs + (cell_start[key] + old - 1u), c, val, h);
+}
+
+// K4 (on demand): the stable (key,id) order.  The rank of a body inside its cell is the number of
+// co-occupants with a smaller id.
+__global__ void __launch_bounds__(256) canon_kernel(const SlotRec* __restrict__ recs, const uint32_t* __restrict__ cell_start,
+                                                    GridParams g, const uint32_t* __restrict__ counters,
+                                                    uint32_t* __restrict__ sorted_ids) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= counters[C_GRID]) return;
+    const uint32_t key = cell_key(recs[t].c, g);
+    const uint32_t id = recs[t].val & ID_MASK;
+    const uint32_t s = cell_start[key], e = cell_start[key + 1];
+    uint32_t rank = 0;
+    for (uint32_t u = s; u < e; ++u) rank += ((recs[u].val & ID_MASK) < id) ? 1u : 0u;
+    sorted_ids[s + rank] = id;
+}
+
+// ---------------------------------------------------------------------------------------
+// K5: narrow phase over the 27-cell stencil (9 runs of up to 3 key-contiguous cells)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void emit_pair(unsigned long long* out, unsigned long long cap, unsigned long long* counter,
+                                          uint32_t i, uint32_t j) {
+    unsigned long long slot = atomicAdd(counter, 1ull);
+    if (slot < cap) out[slot] = ((unsigned long long)i << 32) | j;
+}
+
+// Hits are staged per thread (NARROW_HITS partner ids in shared memory) and a warp reserves its
+// output slots with ONE atomic at the end.  Emitting from inside the loops - even warp-aggregated, as
+// ptxas does by itself - sends ~450K atomics to one address on the packed 1M scene, and same-address
+// atomics retire at ~0.85 clk each at L2: that queue, not the loads, was the packed narrow phase
+// (ncu: issue slots 15 % busy, L2 4 %, every warp waiting on the atomic's return).
+constexpr int NARROW_THREADS = 128;
+constexpr int NARROW_HITS = 8;
+
+__device__ __noinline__ void emit_pair_overflow(unsigned long long* out, unsigned long long cap, unsigned long long* counter,
+                                                uint32_t i, uint32_t j) {
+    emit_pair(out, cap, counter, i, j);
+}
+
+template <bool CANDIDATES, bool MIXED>
+__device__ __forceinline__ void test_one(uint32_t u, uint32_t va, uint32_t ida, const float4 ca, const float4 ha,
+                                         const SlotRec* __restrict__ recs, uint32_t (*s_hit)[NARROW_THREADS], uint32_t& nh,
+                                         unsigned long long* out, unsigned long long cap, unsigned long long* counter) {
+    float4 cb, hb;
+    uint32_t vb;
+    ld_rec(recs + u, cb, vb, hb);
+    const uint32_t idb = vb & ID_MASK;
+    bool hit = true;
+    if (!CANDIDATES) {
+        if (MIXED && ((va | vb) & BOX_BIT)) hit = aabb_hit(ca, ha, cb, hb);   // main.cpp:704
+        else hit = sphere_hit(ca, cb);                                       // main.cpp:702
+        hit = hit && !(va & vb & STATIC_BIT);                                // main.cpp:695
+    }
+    if (hit) {
+        if (nh < (uint32_t)NARROW_HITS) s_hit[nh][threadIdx.x] = idb;
+        else emit_pair_overflow(out, cap, counter, min(ida, idb), max(ida, idb));   // staging full: straight out
+        ++nh;
+    }
+}
+
+// x-edge cell: the windows wrap around the row, so they are walked cell by cell (2 of 2^bits cells per row)
+template <bool CANDIDATES, bool MIXED>
+__device__ __noinline__ void narrow_edge(uint32_t t, uint32_t key, int bits, uint32_t va, const float4 ca, const float4 ha,
+                                         const SlotRec* __restrict__ recs, const uint32_t* __restrict__ cell_start,
+                                         uint32_t (*s_hit)[NARROW_THREADS], uint32_t& nh, unsigned long long* out,
+                                         unsigned long long cap, unsigned long long* counter) {
+    const uint32_t ida = va & ID_MASK;
+    const uint32_t msk = (1u << bits) - 1u;
+    const uint32_t cx = key & msk, cy = (key >> bits) & msk, cz = (key >> (2 * bits)) & msk;
+    // window w: 0 = rest of the own cell, 1 = cell cx+1 of the own row, 2.. = 3 cells of each forward row
+#pragma unroll 1
+    for (int w = 0; w < 14; ++w) {
+        uint32_t s, e;
+        if (w == 0) {
+            s = t + 1;
+            e = cell_start[key + 1];
+        } else {
+            uint32_t nk;
+            if (w == 1) {
+                nk = (key & ~msk) | ((cx + 1) & msk);
+            } else {
+                const int r = (w - 2) / 3, dx = (w - 2) % 3 - 1;
+                const int dz = r == 0 ? 0 : 1;
+                const int dy = r == 0 ? 1 : r - 2;
+                nk = (((cy + dy) & msk) << bits) | (((cz + dz) & msk) << (2 * bits)) | ((cx + dx) & msk);
+            }
+            s = cell_start[nk];
+            e = cell_start[nk + 1];
+        }
+#pragma unroll 1
+        for (uint32_t u = s; u < e; ++u) test_one<CANDIDATES, MIXED>(u, va, ida, ca, ha, recs, s_hit, nh, out, cap, counter);
+    }
+}
+
+// The candidate relation "cell(b) is in the 27-cell stencil of cell(a)" is symmetric, so every
+// unordered pair is reached from exactly one side by a HALF stencil: the later slots of a's own
+// cell, and the 13 cells at "forward" offsets (dz,dy,dx) > (0,0,0) lexicographically (an offset o
+// and its opposite -o are distinct modulo 2^bits >= 4, and exactly one of them is forward).
+// With x as the fastest key digit those are 5 contiguous slot ranges for an interior cell:
+//   [t+1, end of cell cx+1]  in the own row, and cells cx-1..cx+1 of the rows (dz,dy) =
+//   (0,+1), (+1,-1), (+1,0), (+1,+1).
+// "Later slots of the own cell" is any fixed order: the arrival order K3b left is as good as the id order.
+// MIXED: boxes live in the grid; a pair with at least one box uses the AABB predicate on the
+// collider sizes of both bodies, exactly as the reference dispatches (main.cpp:701-706).
+// One thread per slot.  (A warp-cooperative version - the union of a warp's windows per stencil
+// row staged in shared memory by coalesced loads, each record read once per warp - was measured at
+// 98.9 us sparse / 286.7 us packed against 54.6 / 321.8 for this one: the staging phases serialise
+// a warp that otherwise hides its latency with 64 independent threads per scheduler.)
+template <bool CANDIDATES, bool MIXED>
+__global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* __restrict__ recs,
+                                                                const uint32_t* __restrict__ cell_start,
+                                                                const uint32_t* __restrict__ counters, GridParams g,
+                                                                unsigned long long* out, unsigned long long cap,
+                                                                unsigned long long* counter) {
+    __shared__ uint32_t s_hit[NARROW_HITS][NARROW_THREADS];
+    const uint32_t t = blockIdx.x * NARROW_THREADS + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t nh = 0, ida = 0;
+    if (t < counters[C_GRID]) {
+        float4 ca, ha;
+        uint32_t va;
+        ld_rec(recs + t, ca, va, ha);
+        const uint32_t key = cell_key(ca, g);
+        ida = va & ID_MASK;
+        const int bits = g.bits;
+        const uint32_t msk = (1u << bits) - 1u;
+        const uint32_t cx = key & msk, cy = (key >> bits) & msk, cz = (key >> (2 * bits)) & msk;
+        if (cx > 0 && cx < msk) {
+            // interior cell: five contiguous slot ranges, all nine look-ups issued before the first use
+            uint32_t rs[5], re[5];
+            rs[0] = t + 1;
+            re[0] = cell_start[key + 2];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int dz = r == 0 ? 0 : 1;
+                const int dy = r == 0 ? 1 : r - 2;
+                const uint32_t row = (((cy + dy) & msk) << bits) | (((cz + dz) & msk) << (2 * bits));
+                rs[r + 1] = cell_start[row + cx - 1];
+                re[r + 1] = cell_start[row + cx + 2];
+            }
+            // (one flattened loop over the five windows - a lane moving on as soon as its own window is
+            // exhausted - was slower: 77 / 90 us against 62 / 73; the compiler pipelines these loops better)
+#pragma unroll
+            for (int r = 0; r < 5; ++r)
+                for (uint32_t u = rs[r]; u < re[r]; ++u)
+                    test_one<CANDIDATES, MIXED>(u, va, ida, ca, ha, recs, s_hit, nh, out, cap, counter);
+        } else {
+            narrow_edge<CANDIDATES, MIXED>(t, key, bits, va, ca, ha, recs, cell_start, s_hit, nh, out, cap, counter);
+        }
+    }
+    // one reservation per warp for everything it staged
+    if (!__any_sync(0xFFFFFFFFu, nh != 0)) return;
+    const uint32_t cnt = min(nh, (uint32_t)NARROW_HITS);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (uint32_t)o) incl += y;
+    }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (total == 0) return;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(counter, (unsigned long long)total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0) + (incl - cnt);
+    for (uint32_t k = 0; k < cnt; ++k) {
+        const uint32_t idb = s_hit[k][threadIdx.x];
+        if (base + k < cap) out[base + k] = ((unsigned long long)min(ida, idb) << 32) | max(ida, idb);
+    }
+}
+
+// K5b: side-list bodies against every live body.  grid = (ceil(n/256), up to 64).
+__global__ void __launch_bounds__(256) side_kernel(const uint32_t* __restrict__ side_list, const uint32_t* __restrict__ counters,
+                                                   const float4* __restrict__ center_r,
+                                                   const float4* __restrict__ half_ext,
+                                                   const uint8_t* __restrict__ flags, const uint8_t* __restrict__ klass,
+                                                   uint32_t n, unsigned long long* out, unsigned long long cap,
+                                                   unsigned long long* counter) {
+    const uint32_t side_count = counters[C_SIDE];
+    uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    const uint8_t kx = klass[x];
+    if (kx == 0) return;
+    const float4 cx = center_r[x], hx = half_ext[x];
+    const uint8_t fx = flags[x];
+    for (uint32_t si = blockIdx.y; si < side_count; si += gridDim.y) {
+        const uint32_t s = side_list[si];
+        if (s == x) continue;
+        if (kx == 2 && x < s) continue;   // side-side pairs are emitted once, from the lower id's row
+        const uint8_t fs = flags[s];
+        if ((fx & F_STATIC) && (fs & F_STATIC)) continue;
+        const float4 cs = center_r[s];
+        bool hit;
+        if ((fx & F_SPHERE) && (fs & F_SPHERE)) hit = sphere_hit(cx, cs);
+        else hit = aabb_hit(cx, hx, cs, half_ext[s]);
+        if (hit) emit_pair(out, cap, counter, min(x, s), max(x, s));
+    }
+}
+
+// K5c: "far" bodies (normal extent, finite centre, outside the grid domain |u| < 32768) against each
+// other and against the grid bodies within two cells of the domain boundary; side_kernel covers
+// far-vs-oversize.  A contact implies |delta u| < 1 per axis (cell = 2*rmax*(1+2^-7)) and computed
+// u carries < 0.01 of error at that magnitude, so a grid body that touches a far body has
+// |u| > 32766 on that axis: nobody else needs testing.  Thread = far body (grid-stride), rows
+// (gridDim.y) stride over the partner list, so any launch geometry is correct.
+// Both lists carry id|flags (pack_val) and a compact copy of the centres, so the partner loop
+// streams consecutive 16-byte entries instead of gathering by id.
+__global__ void __launch_bounds__(256) far_kernel(const uint32_t* __restrict__ far_list, const float4* __restrict__ far_c,
+                                                  const uint32_t* __restrict__ bnd_list, const float4* __restrict__ bnd_c,
+                                                  const uint32_t* __restrict__ counters, const float4* __restrict__ half_ext,
+                                                  unsigned long long* out, unsigned long long cap, unsigned long long* counter) {
+    const uint32_t nfar = counters[C_FAR], nbnd = counters[C_BND];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nfar; t += gridDim.x * blockDim.x) {
+        const uint32_t va = far_list[t];
+        const uint32_t a = va & ID_MASK;
+        const float4 ca = far_c[t];
+        // partners: far bodies later in the list, then every boundary grid body
+        for (uint32_t k = t + 1 + blockIdx.y; k < nfar + nbnd; k += gridDim.y) {
+            const bool kf = k < nfar;
+            const uint32_t vb = kf ? far_list[k] : bnd_list[k - nfar];
+            if (va & vb & STATIC_BIT) continue;                      // main.cpp:695
+            const float4 cb = kf ? far_c[k] : bnd_c[k - nfar];
+            const uint32_t b = vb & ID_MASK;
+            bool hit;
+            if ((va | vb) & BOX_BIT) hit = aabb_hit(ca, half_ext[a], cb, half_ext[b]);   // main.cpp:704
+            else hit = sphere_hit(ca, cb);                                               // main.cpp:702
+            if (hit) emit_pair(out, cap, counter, min(a, b), max(a, b));
+        }
+    }
+}
+
+}  // namespace tr
