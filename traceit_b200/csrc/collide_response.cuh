@@ -266,6 +266,11 @@ __device__ __forceinline__ void respond(const RespArgs& a, uint32_t i, uint32_t 
     }
 }
 
+__device__ __forceinline__ void store_xyz(float4* p, const float4 v) {
+    *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y);
+    reinterpret_cast<float*>(p)[2] = v.z;
+}
+
 // The same contact on version-checked body records (dataflow executors).  Returns false when the
 // watchdog fired.  Every path bumps both versions, also the ones that change nothing (static body,
 // the approach test): the successors wait for exactly that version.
@@ -321,15 +326,18 @@ __device__ __forceinline__ bool respond_rec(const FlowArgs& a, uint32_t c, uint3
             pj.z = __fadd_rn(pj.z, __fmul_rn(cz, g.imb));
         }
     }
-    if (last_i) {                                        // nobody reads the record again: back to the SoA state
-        a.vel_out[i] = make_float4(vi.x, vi.y, vi.z, a.vel_rest[i].w);
-        a.pos_out[i] = make_float4(pi.x, pi.y, pi.z, a.pos_m[i].w);
+    // nobody reads the record of a body again after its last contact: back to the SoA state.  Only
+    // x, y, z are written (8 + 4 bytes): the w components (restitution, mass) are already there, and
+    // loading them to rebuild a float4 would park the store - and the atomics behind it - on an L2 round trip.
+    if (last_i) {
+        store_xyz(a.vel_out + i, vi);
+        store_xyz(a.pos_out + i, pi);
     } else {
         st_body(a.brec + i, vi, pi, want.x + 1u);
     }
     if (last_j) {
-        a.vel_out[j] = make_float4(vj.x, vj.y, vj.z, a.vel_rest[j].w);
-        a.pos_out[j] = make_float4(pj.x, pj.y, pj.z, a.pos_m[j].w);
+        store_xyz(a.vel_out + j, vj);
+        store_xyz(a.pos_out + j, pj);
     } else {
         st_body(a.brec + j, vj, pj, want.y + 1u);
     }
@@ -425,8 +433,23 @@ __global__ void __launch_bounds__(128) response_flow_kernel(FlowArgs a, const ui
         if (LANES == 1 && !work) __nanosleep(idle_ns);   // an idle worker that polls flat out slows the busy ones down
         // ---- phase 2 (atomics): working lanes release their successors, idle lanes try to acquire
         if (work) {
-            const uint32_t r1 = (s1 != EMPTY) ? atomicSub(&dep[s1], 1u) : 0u;
-            const uint32_t r2 = (s2 != EMPTY) ? atomicSub(&dep[s2], 1u) : 0u;
+            // both decrements in flight together: written as two ?: expressions the compiler wraps each
+            // atomic in its own branch and tests the first result inside it, i.e. the second atomic is
+            // not issued until the first has returned (530 cycles each, see tools/lat_microbench)
+            uint32_t r1, r2;
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p1, p2;\n\t"
+                "setp.ne.u32 p1, %4, 0xffffffff;\n\t"
+                "setp.ne.u32 p2, %5, 0xffffffff;\n\t"
+                "mov.u32 %0, 0;\n\t"
+                "mov.u32 %1, 0;\n\t"
+                "@p1 atom.global.add.u32 %0, [%2], 0xffffffff;\n\t"
+                "@p2 atom.global.add.u32 %1, [%3], 0xffffffff;\n\t"
+                "}"
+                : "=&r"(r1), "=&r"(r2)
+                : "l"(dep + (s1 != EMPTY ? s1 : 0u)), "l"(dep + (s2 != EMPTY ? s2 : 0u)), "r"(s1), "r"(s2)
+                : "memory");
             if (s1 != EMPTY) {                    // the next hand-off will touch these bodies
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(a.brec + n1.x));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(a.brec + n1.y));
