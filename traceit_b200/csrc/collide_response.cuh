@@ -429,27 +429,37 @@ __global__ void __launch_bounds__(128) response_flow_kernel(FlowArgs a, const ui
         uint4 n1 = make_uint4(0, 0, EMPTY, EMPTY), n2 = make_uint4(0, 0, EMPTY, EMPTY);
         if (s1 != EMPTY) n1 = crec[s1];
         if (s2 != EMPTY) n2 = crec[s2];
+        // Single-lane workers release the successors FIRST, together with the loads: the dependency
+        // counters only schedule - what a successor reads is validated by the record versions, so one
+        // that starts early just polls until this contact's records land - and the 530-cycle round trip
+        // of the atomics overlaps this contact's loads and arithmetic instead of following them.
+        // (Lock-step warps release after the stores: a lane polling for a record that another lane of
+        // its own warp still has to write would stall that very lane.)
+        // Both decrements are in flight together: written as two ?: expressions the compiler wraps each
+        // atomic in its own branch and tests the first result inside it, i.e. the second atomic is
+        // not issued until the first has returned.
+        uint32_t r1 = 0, r2 = 0;
+#define TR_RELEASE_SUCCESSORS()                                                                                          \
+        asm volatile(                                                                                                    \
+            "{\n\t"                                                                                                      \
+            ".reg .pred p1, p2;\n\t"                                                                                     \
+            "setp.ne.u32 p1, %4, 0xffffffff;\n\t"                                                                        \
+            "setp.ne.u32 p2, %5, 0xffffffff;\n\t"                                                                        \
+            "mov.u32 %0, 0;\n\t"                                                                                         \
+            "mov.u32 %1, 0;\n\t"                                                                                         \
+            "@p1 atom.global.add.u32 %0, [%2], 0xffffffff;\n\t"                                                          \
+            "@p2 atom.global.add.u32 %1, [%3], 0xffffffff;\n\t"                                                          \
+            "}"                                                                                                          \
+            : "=&r"(r1), "=&r"(r2)                                                                                       \
+            : "l"(dep + (s1 != EMPTY ? s1 : 0u)), "l"(dep + (s2 != EMPTY ? s2 : 0u)), "r"(s1), "r"(s2)                   \
+            : "memory")
+        if (LANES == 1 && work) TR_RELEASE_SUCCESSORS();
         if (work && !respond_rec(a, cur, rec.x, rec.y, s1 == EMPTY, s2 == EMPTY, counters)) alive = false;   // watchdog
         if (LANES == 1 && !work) __nanosleep(idle_ns);   // an idle worker that polls flat out slows the busy ones down
-        // ---- phase 2 (atomics): working lanes release their successors, idle lanes try to acquire
+        // ---- phase 2: working lanes pick their next contact, idle lanes try to acquire one
         if (work) {
-            // both decrements in flight together: written as two ?: expressions the compiler wraps each
-            // atomic in its own branch and tests the first result inside it, i.e. the second atomic is
-            // not issued until the first has returned (530 cycles each, see tools/lat_microbench)
-            uint32_t r1, r2;
-            asm volatile(
-                "{\n\t"
-                ".reg .pred p1, p2;\n\t"
-                "setp.ne.u32 p1, %4, 0xffffffff;\n\t"
-                "setp.ne.u32 p2, %5, 0xffffffff;\n\t"
-                "mov.u32 %0, 0;\n\t"
-                "mov.u32 %1, 0;\n\t"
-                "@p1 atom.global.add.u32 %0, [%2], 0xffffffff;\n\t"
-                "@p2 atom.global.add.u32 %1, [%3], 0xffffffff;\n\t"
-                "}"
-                : "=&r"(r1), "=&r"(r2)
-                : "l"(dep + (s1 != EMPTY ? s1 : 0u)), "l"(dep + (s2 != EMPTY ? s2 : 0u)), "r"(s1), "r"(s2)
-                : "memory");
+            if (LANES != 1) TR_RELEASE_SUCCESSORS();
+#undef TR_RELEASE_SUCCESSORS
             if (s1 != EMPTY) {                    // the next hand-off will touch these bodies
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(a.brec + n1.x));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(a.brec + n1.y));
