@@ -429,7 +429,8 @@ int collide_step(tr_world* w) {
         int fwant = (int)((cn + 127) / 128);
         if (fwant < fblocks) fblocks = fwant < 1 ? 1 : fwant;
         // Executor width.  Deep graphs (a packed lattice: ~800 dependent hand-offs) are latency bound:
-        // single-lane workers, 6 CTAs of 4 warps per SM (3, 4, 5, 7 per SM: 2.47, 2.08, 1.90, 1.82 ms against 1.78).
+        // single-lane workers, 5 CTAs of 4 warps per SM (3, 4, 6, 7, 8, 9 per SM: 1.59, 1.39, 1.36, 1.38, 1.40, 1.42 ms
+        // against 1.34: beyond ~3K workers the extra pollers cost more than the extra hands bring).
         // Wide shallow graphs are throughput bound: whole warps.  The previous step tells which:
         // contacts per lock-step iteration of its longest worker.
         bool wide = w->params.response_mode == 2;
@@ -437,8 +438,7 @@ int collide_step(tr_world* w) {
         if (wide) {
             response_flow_kernel<32><<<fblocks, 128, 0, w->stream>>>(ra, c->crec, c->dep, c->frontier[0], cn, c->counters, 0u);
         } else {
-            static const int per_sm = getenv("TR_FLOW_CTAS") ? atoi(getenv("TR_FLOW_CTAS")) : 6;
-            int sblocks = w->num_sms * per_sm;
+            int sblocks = w->num_sms * 5;
             const int swant = (int)((cn + 3) / 4);
             if (swant < sblocks) sblocks = swant < 1 ? 1 : swant;
             // idle back-off: 300 and 700 ns are equivalent (1.78 / 1.80 ms), 100 ns and 2000 ns are 10 % slower
