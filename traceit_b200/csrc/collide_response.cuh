@@ -435,6 +435,11 @@ __global__ void __launch_bounds__(128) response_flow_kernel(FlowArgs a, const ui
         // of the atomics overlaps this contact's loads and arithmetic instead of following them.
         // (Lock-step warps release after the stores: a lane polling for a record that another lane of
         // its own warp still has to write would stall that very lane.)
+        // No deadlock: a contact is handed to a worker only when both its predecessors have STARTED, and
+        // a started contact stays with its worker until it is finished; so the earliest unfinished
+        // contact among those in workers' hands has finished predecessors, i.e. valid records, and
+        // proceeds.  A worker can poll for at most the time the <= ~3K contacts started ahead of the
+        // data take (milliseconds), far below VERSION_SPIN_LIMIT (~0.2 s of polling).
         // Both decrements are in flight together: written as two ?: expressions the compiler wraps each
         // atomic in its own branch and tests the first result inside it, i.e. the second atomic is
         // not issued until the first has returned.
