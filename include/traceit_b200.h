@@ -58,9 +58,11 @@ typedef struct tr_world_params {
     /* Uniform-grid broad phase (no reference counterpart; the reference is brute force).
      * 0 / zeros = automatic.  cell edge defaults to 2*rmax*(1+2^-7) where rmax is the
      * largest radius among grid bodies; grid_bits is bits per axis of the wrapped key
-     * (2..10).  Spheres and boxes share the grid (a body's extent is |radius|, and
-     * max|size| as soon as boxes exist); oversize or out-of-domain bodies go to a side
-     * list that is tested against every body.                                            */
+     * (2..10, the same on x, y, z); automatic = the smallest table with 2 cells per body,
+     * its bits spread over the axes (x first).  Spheres and boxes share the grid (a body's
+     * extent is |radius|, and max|size| as soon as boxes exist); oversize bodies go to a
+     * side list tested against every body, bodies outside the grid domain to a far list
+     * tested against each other and the grid bodies next to the domain boundary.           */
     float grid_origin[3];
     float grid_cell;
     int32_t grid_bits;
@@ -180,7 +182,8 @@ int tr_read_contacts(tr_world* w, int32_t* pairs_ij, uint64_t cap, uint64_t* n);
 /* Broad-phase internals of the last step (each pointer may be NULL):
  *   keys[N]        wrapped cell key per body id (0xFFFFFFFF for side-list bodies)
  *   sorted_ids[M]  grid body ids in (key,id) order;  *m receives M
- *   cell, inv_cell, bits: the grid actually used.                                       */
+ *   cell, inv_cell, bits: the grid actually used; bits = b when every axis has b bits,
+ *                  else bx | by << 8 | bz << 16.                                        */
 int tr_debug_grid(tr_world* w, uint32_t* keys, uint32_t* sorted_ids, uint64_t* m,
                   float* cell, float* inv_cell, int32_t* bits);
 /* Re-run the last step's broad phase emitting every candidate pair (i<j) of the grid

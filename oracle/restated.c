@@ -360,10 +360,12 @@ void orc_integrate(orc_body* b, int n, const orc_params* p, const float* fgrav) 
  *
  *   u_a   = (center_a - origin_a) * inv_cell          fp32 sub, fp32 mul, no FMA
  *   c_a   = (int32) floorf(u_a)   saturating, NaN -> 0
- *   key   = (cx & m) | (cy & m) << bits | (cz & m) << 2*bits,  m = 2^bits - 1, 2<=bits<=10
+ *   key   = (cx & mx) | (cy & my) << bx | (cz & mz) << (bx+by),  m_a = 2^b_a - 1, 2 <= b_a <= 10
  *   order = stable sort of body ids by key  ==  ascending (key, id)
  *   candidates = { (i,j) : i<j, both grid bodies, cell(j) in the 27-stencil of cell(i)
- *                  taken modulo 2^bits per axis }
+ *                  taken modulo 2^b_a per axis }
+ * The `bits` argument of the functions below is a code: b (< 256) = the same b bits on every
+ * axis, otherwise bx | by << 8 | bz << 16 (what tr_debug_grid reports for the grid it used).
  * A body is a "grid body" when in_grid[id] != 0 (spheres with radius <= the grid's
  * rmax and |u| < 32768 on every axis; the host decides - see traceit_b200 DESIGN.md).
  * --------------------------------------------------------------------------------- */
@@ -381,9 +383,27 @@ void orc_grid_cells(const orc_body* b, int n, const float* origin, float inv_cel
         for (int c = 0; c < 3; ++c) cells[3 * i + c] = cell_coord(b[i].center[c], origin[c], inv_cell);
 }
 
+static inline void axis_bits(int code, int* bx, int* by, int* bz) {
+    if (code < 256) {
+        *bx = *by = *bz = code;
+    } else {
+        *bx = code & 0xFF;
+        *by = (code >> 8) & 0xFF;
+        *bz = (code >> 16) & 0xFF;
+    }
+}
+
+static inline size_t table_cells(int code) {
+    int bx, by, bz;
+    axis_bits(code, &bx, &by, &bz);
+    return (size_t)1 << (bx + by + bz);
+}
+
 static inline uint32_t pack_key(int32_t cx, int32_t cy, int32_t cz, int bits) {
-    uint32_t m = (1u << bits) - 1u;
-    return ((uint32_t)cx & m) | (((uint32_t)cy & m) << bits) | (((uint32_t)cz & m) << (2 * bits));
+    int bx, by, bz;
+    axis_bits(bits, &bx, &by, &bz);
+    uint32_t mx = (1u << bx) - 1u, my = (1u << by) - 1u, mz = (1u << bz) - 1u;
+    return ((uint32_t)cx & mx) | (((uint32_t)cy & my) << bx) | (((uint32_t)cz & mz) << (bx + by));
 }
 
 void orc_grid_keys(const orc_body* b, int n, const float* origin, float inv_cell, int bits, uint32_t* keys) {
@@ -411,7 +431,7 @@ void orc_grid_in_domain(const orc_body* b, int n, const float* origin, float inv
  * order_out receives the m ids in (key, id) order; sorted_keys_out their keys. */
 void orc_grid_sort(const uint32_t* keys, const int32_t* ids, int m, int bits, int32_t* order_out,
                    uint32_t* sorted_keys_out) {
-    size_t ncell = (size_t)1 << (3 * bits);
+    size_t ncell = table_cells(bits);
     uint32_t* cnt = (uint32_t*)calloc(ncell + 1, sizeof(uint32_t));
     for (int t = 0; t < m; ++t) cnt[keys[ids[t]] + 1]++;
     for (size_t c = 0; c < ncell; ++c) cnt[c + 1] += cnt[c];
@@ -445,7 +465,7 @@ int orc_grid_pairs(const orc_body* b, int n, const uint8_t* in_grid, const float
     int32_t* cells = (int32_t*)malloc(sizeof(int32_t) * 3 * (size_t)(n > 0 ? n : 1));
     uint32_t* keys = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(n > 0 ? n : 1));
     int32_t* order = (int32_t*)malloc(sizeof(int32_t) * (size_t)(m > 0 ? m : 1));
-    size_t ncell = (size_t)1 << (3 * bits);
+    size_t ncell = table_cells(bits);
     uint32_t* start = (uint32_t*)calloc(ncell + 1, sizeof(uint32_t));
     if (!ids || !cells || !keys || !order || !start) return -1;
     orc_grid_cells(b, n, origin, inv_cell, cells);

@@ -135,9 +135,11 @@ def test_pair_gravity_coincident_bodies_are_nan(oracle):
 
 def test_grid_contacts_equal_brute_force(oracle):
     """CPU grid restatement finds exactly the brute-force contact set (incl. wrap-around)."""
-    for n, dens, bits in ((3000, 0.5, 4), (3000, 0.5, 2), (5000, 2.0, 3)):
-        b = scenes.random_cloud(n, 11 + bits, spheres=True, density_l=dens)
-        b["radius"] = np.random.RandomState(bits).uniform(0.1, 0.5, n).astype(np.float32)
+    # bits code: b = the same on every axis, or bx | by << 8 | bz << 16
+    for n, dens, bits in ((3000, 0.5, 4), (3000, 0.5, 2), (5000, 2.0, 3), (4000, 0.7, 5 | (4 << 8) | (4 << 16)),
+                          (3000, 0.5, 3 | (2 << 8) | (2 << 16))):
+        b = scenes.random_cloud(n, 11 + (bits & 0xFF), spheres=True, density_l=dens)
+        b["radius"] = np.random.RandomState(bits & 0xFF).uniform(0.1, 0.5, n).astype(np.float32)
         rmax = float(b["radius"].max())
         cell = np.float32(np.float32(2.0 * rmax) * np.float32(1.0078125))
         inv = np.float32(1.0) / cell

@@ -58,7 +58,7 @@ static Collide* state(tr_world* w) {
 // finite size exists ("mixed" world) any body may meet a box, box pairs use collider::size of both
 // bodies, and the extent becomes max(|radius| if sphere, |size.x|, |size.y|, |size.z|).
 static GridParams grid_params(const Collide* c) {
-    return GridParams{c->origin[0], c->origin[1], c->origin[2], c->inv_cell, c->rmax_grid, c->bits, c->mixed ? 1 : 0};
+    return GridParams{c->origin[0], c->origin[1], c->origin[2], c->inv_cell, c->rmax_grid, c->bx, c->by, c->bz, c->mixed ? 1 : 0};
 }
 
 static float body_extent(const tr_body_desc& b, bool mixed) {
@@ -115,13 +115,18 @@ int collide_classify(tr_world* w) {
     c->cell = cell;
     c->inv_cell = 1.0f / cell;
     memcpy(c->origin, p.grid_origin, sizeof(c->origin));
-    int bits = p.grid_bits;
-    if (bits == 0) {
-        uint64_t want = 2 * (w->n ? w->n : 1);
-        bits = 2;
-        while (bits < 10 && (1ull << (3 * bits)) < want) ++bits;
+    if (p.grid_bits != 0) {
+        c->bx = c->by = c->bz = p.grid_bits;       // the caller's choice: the same on every axis
+    } else {
+        // smallest table with at least 2 cells per body, bits spread over the axes (x, the fastest key
+        // digit, first): with the same bits on every axis the table could only grow in steps of 8x
+        const uint64_t want = 2 * (w->n ? w->n : 1);
+        int total = 6;
+        while (total < 30 && (1ull << total) < want) ++total;
+        c->bx = (total + 2) / 3;
+        c->by = (total - c->bx + 1) / 2;
+        c->bz = total - c->bx - c->by;
     }
-    c->bits = bits;
     w->classified = true;
     return TR_OK;
 }
@@ -147,7 +152,7 @@ static int ensure_buffers(tr_world* w) {
         TR_CUDA(cudaMemsetAsync(c->body_cnt, 0, cap * sizeof(uint32_t), w->stream));
         c->cap_bodies = cap;
     }
-    const uint64_t ncell = 1ull << (3 * c->bits);
+    const uint64_t ncell = 1ull << (c->bx + c->by + c->bz);
     if (ncell > c->ncell_alloc) {
         TR_TRY(realloc_dev(&c->cell_start, ncell + 1));
         TR_TRY(realloc_dev(&c->cell_count, ncell));
@@ -196,7 +201,7 @@ static int launch_broad(tr_world* w, cudaStream_t st, cudaEvent_t* ev = nullptr)
     Collide* c = state(w);
     const uint32_t n = (uint32_t)w->n;
     const uint32_t blocks = (n + 255) / 256;
-    const uint32_t ncell = 1u << (3 * c->bits);
+    const uint32_t ncell = 1u << (c->bx + c->by + c->bz);
     const uint32_t ntiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
     const GridParams g = grid_params(c);
     TR_CUDA(cudaMemsetAsync(c->counters, 0, C_NCOUNTERS * sizeof(uint32_t), st));
@@ -244,7 +249,7 @@ static int broad_phase(tr_world* w) {
         // signature of everything the captured launches depend on
         uint64_t sig[8] = {(uint64_t)(uintptr_t)w->center_r, (uint64_t)(uintptr_t)w->flags, (uint64_t)(uintptr_t)c->keys,
                            (uint64_t)(uintptr_t)c->cell_count, (uint64_t)(uintptr_t)c->ckeys ^ (uint64_t)(uintptr_t)c->recs,
-                           ((uint64_t)n << 9) | ((uint64_t)(c->mixed ? 1 : 0) << 8) | (uint64_t)c->bits, 0, 0};
+                           ((uint64_t)n << 16) | ((uint64_t)(c->mixed ? 1 : 0) << 15) | (uint64_t)(c->bx | (c->by << 5) | (c->bz << 10)), 0, 0};
         memcpy(&sig[6], &c->inv_cell, 4);
         memcpy((char*)&sig[6] + 4, &c->rmax_grid, 4);
         memcpy(&sig[7], &c->origin[0], 8);
@@ -517,8 +522,9 @@ int collide_debug_grid(tr_world* w, uint32_t* keys, uint32_t* sorted_ids, uint64
     if (m) *m = gm;
     if (cell) *cell = c->cell;
     if (inv_cell) *inv_cell = c->inv_cell;
-    if (bits) *bits = c->bits;
-    const uint32_t sentinel = 1u << (3 * c->bits);
+    // one number when the axes agree, else bx | by << 8 | bz << 16 (the oracle's grid functions take the same code)
+    if (bits) *bits = (c->bx == c->by && c->by == c->bz) ? c->bx : (c->bx | (c->by << 8) | (c->bz << 16));
+    const uint32_t sentinel = 1u << (c->bx + c->by + c->bz);
     if (keys) {
         TR_CUDA(cudaMemcpyAsync(keys, c->keys, w->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
         TR_CUDA(cudaStreamSynchronize(w->stream));

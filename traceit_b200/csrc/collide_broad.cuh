@@ -19,13 +19,13 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ ce
     {
         // stream the (zeroed) histogram into L2 ahead of the scattered REDs: one 128-byte line per
         // thread of the leading CTAs, so random cloud ids do not pay a DRAM round trip per atomic
-        const uint32_t ncell = 1u << (3 * g.bits);
+        const uint32_t ncell = 1u << g.total_bits();
         if (i < ncell / 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(cell_count + (size_t)i * 32));
     }
     if (i < n) {
         const float4 c = center_r[i];
         const uint8_t f = flags[i];
-        const uint32_t sentinel = 1u << (3 * g.bits);
+        const uint32_t sentinel = 1u << g.total_bits();
         uint32_t key = sentinel;
         uint8_t k = 0;
         if (f & F_LIVE) {   // main.cpp:696 drops mass<=0 bodies from every pair (flag set at upload)
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ ce
                 fits = (f & F_SPHERE) && fabsf(c.w) <= g.rmax_grid;
             }
             if (fits && in_domain) {
-                key = pack_key(__float2int_rd(ux), __float2int_rd(uy), __float2int_rd(uz), g.bits);
+                key = pack_key(__float2int_rd(ux), __float2int_rd(uy), __float2int_rd(uz), g);
                 k = 1;
                 atomicAdd(&cell_count[key], 1u);   // result unused: a fire-and-forget RED
                 // grid bodies within two cells of the domain boundary are the only ones a "far" body can touch
@@ -113,7 +113,7 @@ __device__ __forceinline__ uint32_t cell_key(const float4 c, const GridParams& g
     const float ux = __fmul_rn(__fsub_rn(c.x, g.ox), g.inv_cell);
     const float uy = __fmul_rn(__fsub_rn(c.y, g.oy), g.inv_cell);
     const float uz = __fmul_rn(__fsub_rn(c.z, g.oz), g.inv_cell);
-    return pack_key(__float2int_rd(ux), __float2int_rd(uy), __float2int_rd(uz), g.bits);
+    return pack_key(__float2int_rd(ux), __float2int_rd(uy), __float2int_rd(uz), g);
 }
 
 __global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict__ keys, uint32_t sentinel,
@@ -191,15 +191,15 @@ __device__ __forceinline__ void test_one(uint32_t u, uint32_t va, uint32_t ida, 
     }
 }
 
-// x-edge cell: the windows wrap around the row, so they are walked cell by cell (2 of 2^bits cells per row)
+// x-edge cell: the windows wrap around the row, so they are walked cell by cell (2 of 2^bx cells per row)
 template <bool CANDIDATES, bool MIXED>
-__device__ __noinline__ void narrow_edge(uint32_t t, uint32_t key, int bits, uint32_t va, const float4 ca, const float4 ha,
+__device__ __noinline__ void narrow_edge(uint32_t t, uint32_t key, int bx, int by, int bz, uint32_t va, const float4 ca, const float4 ha,
                                          const SlotRec* __restrict__ recs, const uint32_t* __restrict__ cell_start,
                                          uint32_t (*s_hit)[NARROW_THREADS], uint32_t& nh, unsigned long long* out,
                                          unsigned long long cap, unsigned long long* counter) {
     const uint32_t ida = va & ID_MASK;
-    const uint32_t msk = (1u << bits) - 1u;
-    const uint32_t cx = key & msk, cy = (key >> bits) & msk, cz = (key >> (2 * bits)) & msk;
+    const uint32_t mx = (1u << bx) - 1u, my = (1u << by) - 1u, mz = (1u << bz) - 1u;
+    const uint32_t cx = key & mx, cy = (key >> bx) & my, cz = (key >> (bx + by)) & mz;
     // window w: 0 = rest of the own cell, 1 = cell cx+1 of the own row, 2.. = 3 cells of each forward row
 #pragma unroll 1
     for (int w = 0; w < 14; ++w) {
@@ -210,12 +210,12 @@ __device__ __noinline__ void narrow_edge(uint32_t t, uint32_t key, int bits, uin
         } else {
             uint32_t nk;
             if (w == 1) {
-                nk = (key & ~msk) | ((cx + 1) & msk);
+                nk = (key & ~mx) | ((cx + 1) & mx);
             } else {
                 const int r = (w - 2) / 3, dx = (w - 2) % 3 - 1;
                 const int dz = r == 0 ? 0 : 1;
                 const int dy = r == 0 ? 1 : r - 2;
-                nk = (((cy + dy) & msk) << bits) | (((cz + dz) & msk) << (2 * bits)) | ((cx + dx) & msk);
+                nk = (((cy + dy) & my) << bx) | (((cz + dz) & mz) << (bx + by)) | ((cx + dx) & mx);
             }
             s = cell_start[nk];
             e = cell_start[nk + 1];
@@ -228,7 +228,7 @@ __device__ __noinline__ void narrow_edge(uint32_t t, uint32_t key, int bits, uin
 // The candidate relation "cell(b) is in the 27-cell stencil of cell(a)" is symmetric, so every
 // unordered pair is reached from exactly one side by a HALF stencil: the later slots of a's own
 // cell, and the 13 cells at "forward" offsets (dz,dy,dx) > (0,0,0) lexicographically (an offset o
-// and its opposite -o are distinct modulo 2^bits >= 4, and exactly one of them is forward).
+// and its opposite -o are distinct modulo the per-axis table size >= 4, and exactly one of them is forward).
 // With x as the fastest key digit those are 5 contiguous slot ranges for an interior cell:
 //   [t+1, end of cell cx+1]  in the own row, and cells cx-1..cx+1 of the rows (dz,dy) =
 //   (0,+1), (+1,-1), (+1,0), (+1,+1).
@@ -255,10 +255,9 @@ __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* _
         ld_rec(recs + t, ca, va, ha);
         const uint32_t key = cell_key(ca, g);
         ida = va & ID_MASK;
-        const int bits = g.bits;
-        const uint32_t msk = (1u << bits) - 1u;
-        const uint32_t cx = key & msk, cy = (key >> bits) & msk, cz = (key >> (2 * bits)) & msk;
-        if (cx > 0 && cx < msk) {
+        const uint32_t mx = (1u << g.bx) - 1u, my = (1u << g.by) - 1u, mz = (1u << g.bz) - 1u;
+        const uint32_t cx = key & mx, cy = (key >> g.bx) & my, cz = (key >> (g.bx + g.by)) & mz;
+        if (cx > 0 && cx < mx) {
             // interior cell: five contiguous slot ranges, all nine look-ups issued before the first use
             uint32_t rs[5], re[5];
             rs[0] = t + 1;
@@ -267,7 +266,7 @@ __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* _
             for (int r = 0; r < 4; ++r) {
                 const int dz = r == 0 ? 0 : 1;
                 const int dy = r == 0 ? 1 : r - 2;
-                const uint32_t row = (((cy + dy) & msk) << bits) | (((cz + dz) & msk) << (2 * bits));
+                const uint32_t row = (((cy + dy) & my) << g.bx) | (((cz + dz) & mz) << (g.bx + g.by));
                 rs[r + 1] = cell_start[row + cx - 1];
                 re[r + 1] = cell_start[row + cx + 2];
             }
@@ -278,7 +277,7 @@ __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* _
                 for (uint32_t u = rs[r]; u < re[r]; ++u)
                     test_one<CANDIDATES, MIXED>(u, va, ida, ca, ha, recs, s_hit, nh, out, cap, counter);
         } else {
-            narrow_edge<CANDIDATES, MIXED>(t, key, bits, va, ca, ha, recs, cell_start, s_hit, nh, out, cap, counter);
+            narrow_edge<CANDIDATES, MIXED>(t, key, g.bx, g.by, g.bz, va, ca, ha, recs, cell_start, s_hit, nh, out, cap, counter);
         }
     }
     // one reservation per warp for everything it staged

@@ -38,7 +38,7 @@ struct Collide {
     // grid description (host decides, see collide_classify)
     float cell = 1.f, inv_cell = 1.f, rmax_grid = 0.f;
     float origin[3] = {0, 0, 0};
-    int bits = 2;
+    int bx = 2, by = 2, bz = 2;   // bits per axis of the wrapped cell key (x is the fastest digit)
     bool may_have_side = true;    // some body is statically outside the grid (oversize / NaN extent)
     bool mixed = false;           // live boxes exist: they share the grid, extents include collider::size
     uint64_t cap_bodies = 0;      // arrays below sized for this many bodies
@@ -46,7 +46,7 @@ struct Collide {
     uint64_t cap_contacts = 0;
 
     // per body
-    uint32_t* keys = nullptr;        // K2 out: key, or sentinel 1<<(3*bits) for non-grid bodies
+    uint32_t* keys = nullptr;        // K2 out: key, or sentinel 1<<(bx+by+bz) for non-grid bodies
     struct tr_slot_rec* recs = nullptr;   // K3b out: tr::SlotRec per grid body, grouped by cell (arrival order inside a cell)
     uint32_t* sorted_ids = nullptr;  // K4 (on demand): ids in the stable (key,id) order
     uint32_t* tile_sum = nullptr;    // scan: per-tile histogram sums
@@ -123,16 +123,17 @@ __device__ __forceinline__ bool aabb_hit(const float4 ca, const float4 ha, const
            fabsf(__fsub_rn(ca.z, cb.z)) <= __fadd_rn(ha.z, hb.z);
 }
 
-__device__ __forceinline__ uint32_t pack_key(int cx, int cy, int cz, int bits) {
-    uint32_t m = (1u << bits) - 1u;
-    return ((uint32_t)cx & m) | (((uint32_t)cy & m) << bits) | (((uint32_t)cz & m) << (2 * bits));
-}
-
 struct GridParams {
     float ox, oy, oz, inv_cell, rmax_grid;
-    int bits;
-    int mixed;   // boxes live in the grid too: a body's extent is max(|radius| if sphere, |size.xyz|)
+    int bx, by, bz;   // bits per axis: the table has 2^(bx+by+bz) cells, at least 4 per axis
+    int mixed;        // boxes live in the grid too: a body's extent is max(|radius| if sphere, |size.xyz|)
+    __host__ __device__ int total_bits() const { return bx + by + bz; }
 };
+
+__device__ __forceinline__ uint32_t pack_key(int cx, int cy, int cz, const GridParams& g) {
+    const uint32_t mx = (1u << g.bx) - 1u, my = (1u << g.by) - 1u, mz = (1u << g.bz) - 1u;
+    return ((uint32_t)cx & mx) | (((uint32_t)cy & my) << g.bx) | (((uint32_t)cz & mz) << (g.bx + g.by));
+}
 
 __device__ __forceinline__ uint32_t pack_val(uint32_t id, uint8_t f) {
     return id | ((f & F_STATIC) ? STATIC_BIT : 0u) | ((f & F_SPHERE) ? 0u : BOX_BIT);
