@@ -475,16 +475,18 @@ __global__ void __launch_bounds__(128) response_flow_kernel(FlowArgs a, const ui
             }
             ++mine;
             uint32_t next = EMPTY;
-            if (r1 == 1u) {
-                next = s1;
-                rec = n1;
-            }
+            // both ready: keep the successor along body j (the column side), queue the one along body i -
+            // 5 % faster on the packed scene than the other way round (1.27 against 1.33 ms)
             if (r2 == 1u) {
+                next = s2;
+                rec = n2;
+            }
+            if (r1 == 1u) {
                 if (next == EMPTY) {
-                    next = s2;
-                    rec = n2;
+                    next = s1;
+                    rec = n1;
                 } else {
-                    vq[atomicAdd(&counters[C_QTAIL], 1u)] = s2;   // second ready successor: to the global queue
+                    vq[atomicAdd(&counters[C_QTAIL], 1u)] = s1;   // second ready successor: to the global queue
                 }
             }
             cur = next;
