@@ -465,7 +465,8 @@ __global__ void __launch_bounds__(128) response_flow_kernel(FlowArgs a, const ui
         if (work) {
             if (LANES != 1) TR_RELEASE_SUCCESSORS();
 #undef TR_RELEASE_SUCCESSORS
-            if (s1 != EMPTY) {                    // the next hand-off will touch these bodies
+            if (s1 != EMPTY) {                    // the next hand-off will touch these records (neutral while they are L2
+                                                  // resident - 1.26 ms with or without - kept for worlds that are not)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(a.brec + n1.x));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(a.brec + n1.y));
             }
