@@ -2,6 +2,9 @@
 vectors, which were produced by the verbatim reference build, and (b) the verbatim
 reference library directly when it is present (oracle/_ref, built where /root/reference
 exists).  This is what pins the oracle."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
@@ -158,3 +161,22 @@ def test_grid_sort_is_key_then_id(oracle):
     ref = np.lexsort((np.arange(4096), keys))
     assert np.array_equal(order, ref.astype(np.int32))
     assert np.array_equal(skeys, keys[ref])
+
+
+@pytest.mark.parametrize("name,n,dens", [("grid_2000_b5", 2000, 0.6), ("grid_3000_b544", 3000, 0.7)])
+def test_grid_definition_goldens(oracle, name, n, dens):
+    """The grid has no reference counterpart, so its DEFINITION (keys, stable order, candidate set) is
+    pinned by committed vectors (tests/golden/make_grid_golden.py, whose contact sets were checked
+    against the verbatim reference's sweep); one case has the same bits on every axis, one has not."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_grid_golden as mg
+    g = load_golden(name + ".npz")
+    b = mg.scene(n, dens)
+    bits, inv = int(g["bits"]), np.float32(g["inv_cell"])
+    keys = oracle.grid_keys(b, (0, 0, 0), inv, bits)
+    assert np.array_equal(keys, g["keys"])
+    order, _ = oracle.grid_sort(keys, np.arange(n, dtype=np.int32), bits)
+    assert np.array_equal(order, g["order"])
+    cand, cont, nc, _ = oracle.grid_pairs(b, np.ones(n, np.uint8), (0, 0, 0), inv, bits)
+    assert nc == int(g["n_candidates"]) and mg.fnv1a(cand) == int(g["candidates_fnv1a"])
+    assert np.array_equal(cont, g["contacts"])
