@@ -114,6 +114,27 @@ def test_grid_keys_sort_candidates_bit_exact(tr, oracle, n, dens, bits):
     assert g["cell"] == np.float32(np.float32(2.0 * rmax) * np.float32(1.0078125))
 
 
+@pytest.mark.parametrize("name,n,dens,grid_bits", [("grid_2000_b5", 2000, 0.6, 5), ("grid_3000_b544", 3000, 0.7, 0)])
+def test_grid_definition_goldens_gpu(tr, name, n, dens, grid_bits):
+    """The committed grid vectors (tests/golden/make_grid_golden.py): same bits on every axis when
+    forced, (5,4,4) chosen automatically for 3000 bodies."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_grid_golden as mg
+    g = load_golden(name + ".npz")
+    b = mg.scene(n, dens)
+    with tr.World(tr.default_params(flags=tr.COLLISIONS, grid_bits=grid_bits)) as w:
+        w.add(b)
+        gg = w.debug_grid()
+        ncand, cand = w.debug_candidates()
+    assert gg["bits"] == int(g["bits"]) and np.float32(gg["inv_cell"]) == np.float32(g["inv_cell"])
+    assert np.array_equal(gg["keys"], g["keys"])
+    assert np.array_equal(gg["sorted_ids"].astype(np.int32), g["order"])
+    assert ncand == int(g["n_candidates"])
+    assert mg.fnv1a(np.ascontiguousarray(cand, dtype=np.int32)) == int(g["candidates_fnv1a"])
+
+
 @pytest.mark.parametrize("n,dens", [(30000, 0.6), (30000, 4.0)])
 def test_contact_set_equals_brute_force(tr, oracle, n, dens):
     b = scenes.random_cloud(n, 321, spheres=True, density_l=dens)
