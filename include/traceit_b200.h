@@ -161,6 +161,21 @@ int tr_sync(tr_world* w);                        /* wait; reports deferred devic
  * allocated for that long.                                                              */
 int tr_step_host(tr_world* w, uint64_t n, tr_body_desc* bodies_inout, int nsteps);
 
+/* Per-frame call for a DEVICE-RESIDENT world (the renderer hand-off, src/main.cpp:1589 then
+ * drawWorld): upload the step's only per-frame input - the external forces obj.force, which
+ * the step consumes and zeroes (main.cpp:782,811); 3 floats per body, NULL = leave them - run
+ * nsteps, and read back exactly what a step changes: pos, vel and the collider centre
+ * (main.cpp:787-791, 725-741).  12 bytes up and 36 bytes down per body instead of the 92-byte
+ * descriptor each way of tr_step_host.  n = world size (owned count on a sharded world).
+ * Everything else about a body changes only through tr_write_bodies / tr_bodies_add.  The same
+ * page-locking of reused caller buffers as tr_step_host applies to force_xyz and out.        */
+typedef struct tr_frame_body {
+    float pos[3];
+    float vel[3];
+    float center[3];
+} tr_frame_body;        /* 36 bytes */
+int tr_step_frame(tr_world* w, uint64_t n, const float* force_xyz, tr_frame_body* out, int nsteps);
+
 /* ---- state access: replaces direct reads/writes of w.objects[i] -------------------- */
 int tr_read_state(tr_world* w, uint64_t first, uint64_t count, float* pos_xyz, float* vel_xyz);
 int tr_read_bodies(tr_world* w, uint64_t first, uint64_t count, tr_body_desc* out);

@@ -6,6 +6,7 @@ int use_every_entry_point(void) {
     tr_world* w = 0;
     tr_body_desc b;
     tr_stats st;
+    tr_frame_body fr;
     uint32_t id;
     uint64_t n, a, c;
     float v[3], cell, inv;
@@ -33,6 +34,7 @@ int use_every_entry_point(void) {
     (void)tr_step(w, 1);
     (void)tr_sync(w);
     (void)tr_step_host(w, 1, &b, 1);
+    (void)tr_step_frame(w, 1, v, &fr, 1);
     (void)tr_read_state(w, 0, 1, v, v);
     (void)tr_read_bodies(w, 0, 1, &b);
     (void)tr_write_bodies(w, 0, 1, &b);
@@ -48,5 +50,5 @@ int use_every_entry_point(void) {
     (void)tr_enable_timing(w, 1);
     (void)tr_measure_fma_peak(0, &ops, &mhz);
     (void)tr_world_destroy(w);
-    return (int)sizeof(tr_body_desc);
+    return (int)(sizeof(tr_body_desc) + sizeof(tr_frame_body));
 }

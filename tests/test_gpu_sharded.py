@@ -39,3 +39,17 @@ def test_two_ranks_with_replicated_collisions_equal_unsharded():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SHARDED_OK" in r.stdout
+
+
+@pytest.mark.parametrize("mode", ["grow", "growc"])
+def test_two_ranks_world_grown_mid_run_equals_unsharded(mode):
+    """Adding bodies to an already-stepped sharded world moves the block boundaries: bodies change
+    owner.  The new owner must continue from the old owner's velocity / pending force / collider
+    centre (all-gathered under the old partition before the switch), i.e. == the unsharded run."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29546", os.path.join(ROOT, "tools", "sharded_check.py"), "9001", "6", mode]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "SHARDED_OK" in r.stdout

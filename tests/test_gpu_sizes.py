@@ -1,0 +1,94 @@
+"""GPU parity at the sizes SURVEY.md 8d states, against committed goldens of the CPU oracle
+(tests/golden/make_traj_golden.py ran the restated C step here for minutes; the GPU box cannot),
+and the per-frame API (tr_step_frame) against the plain step."""
+import numpy as np
+import pytest
+
+from conftest import assert_bits_equal, load_golden
+from traceit_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+TRAJ_REL_TOL = 1e-4   # pos/vel after K steps vs the fp32 restated oracle, relative to cloud extent / rms speed
+
+
+def test_gravity_k100_at_65536_vs_oracle_golden(tr, oracle):
+    """Config 2 at its stated size and horizon: N = 65,536, K = 100, gravity + drag + integration,
+    G = 1e-3 (well-conditioned regime): max error <= 1e-4 of the cloud extent / rms speed against the
+    fp32 restated oracle (golden: tests/golden/traj_cfg2_64k_k100.npz)."""
+    g = load_golden("traj_cfg2_64k_k100.npz")
+    n, steps = 65536, int(g["steps"])
+    b = scenes.random_cloud(n, scenes.SEED_CFG2, spheres=True)
+    assert oracle.state_hash(b) == int(g["input_hash"]), "scene generator drifted from the golden's inputs"
+    p = tr.default_params(flags=tr.PAIR_GRAVITY, G=np.float32(g["G"]), g=(0, 0, 0))
+    with tr.World(p) as w:
+        w.add(b)
+        w.step(steps)
+        got = w.read_bodies()
+        st = w.stats()
+    ids = g["ids"]
+    epos = np.abs(got["pos"][ids].astype(np.float64) - g["pos"]).max() / float(g["extent"])
+    evel = np.abs(got["vel"][ids].astype(np.float64) - g["vel"]).max() / float(g["vrms"])
+    print(f"N=65536 K={steps}: max pos err / extent = {epos:.3e}, max vel err / vrms = {evel:.3e} over {len(ids)} sampled bodies")
+    assert epos <= TRAJ_REL_TOL and evel <= TRAJ_REL_TOL
+    assert st.interactions == n * n * steps
+    # whole-cloud sanity on the normalisers (a single bad body outside the sample would move them)
+    assert abs(np.abs(got["pos"]).max() / float(g["extent"]) - 1) < 1e-4
+
+
+def test_gravity_plus_collisions_k20_at_65536_vs_oracle_golden(tr, oracle):
+    """The config-3 cloud generator at N = 65,536 (same density as the 1M cloud), gravity + drag +
+    integration + sphere collisions, K = 20: the contact set of EVERY step equals the oracle's, and
+    positions / velocities of the sampled bodies and of every body that was ever in contact agree
+    within 1e-4 (golden: tests/golden/traj_cfg3cut_64k_k20.npz)."""
+    g = load_golden("traj_cfg3cut_64k_k20.npz")
+    n, steps = 65536, int(g["steps"])
+    b = scenes.random_cloud(n, scenes.SEED_CFG3, spheres=True)
+    assert oracle.state_hash(b) == int(g["input_hash"])
+    offs, want_c = g["offsets"], g["contacts"]
+    p = tr.default_params(flags=tr.PAIR_GRAVITY | tr.COLLISIONS, G=np.float32(g["G"]), g=(0, 0, 0))
+    with tr.World(p) as w:
+        w.add(b)
+        for s in range(steps):
+            w.step(1)
+            c = w.contacts()
+            assert np.array_equal(c, want_c[offs[s]:offs[s + 1]]), f"contact set of step {s} differs ({len(c)} vs {offs[s + 1] - offs[s]})"
+        got = w.read_bodies()
+    ids = g["ids"]
+    epos = np.abs(got["pos"][ids].astype(np.float64) - g["pos"]).max() / float(g["extent"])
+    evel = np.abs(got["vel"][ids].astype(np.float64) - g["vel"]).max() / float(g["vrms"])
+    print(f"N=65536 K={steps} gravity+collisions: {len(want_c)} contacts over the run, pos err {epos:.3e}, vel err {evel:.3e} "
+          f"over {len(ids)} bodies (sample + every body ever in contact)")
+    assert epos <= TRAJ_REL_TOL and evel <= TRAJ_REL_TOL
+
+
+def test_step_frame_equals_step(tr, oracle):
+    """tr_step_frame (forces up, pos/vel/centre down) == tr_set_force + tr_step + tr_read_bodies, bit for bit,
+    and == the oracle fed the same forces."""
+    rs = np.random.RandomState(3)
+    n = 5000
+    b = scenes.random_cloud(n, 12, spheres=True, density_l=0.6)
+    b["stationary"][::17] = 1
+    want = b.copy()
+    frame = np.zeros(n, dtype=tr.FRAME_DTYPE)
+    with tr.World(tr.default_params()) as w:
+        w.add(b)
+        for k in range(4):
+            f = rs.uniform(-30, 30, size=(n, 3)).astype(np.float32) if k % 2 == 0 else None
+            w.step_frame(frame, f, 1)
+            if f is not None:
+                want["force"] = f
+            oracle.step(want, oracle.default_params(), 1)
+            for fld in ("pos", "vel", "center"):
+                assert_bits_equal(frame[fld], want[fld], f"frame {k}:{fld}")
+        full = w.read_bodies()
+    # stationary bodies keep their pending force (main.cpp:764 skips them), the others had it zeroed (main.cpp:811)
+    assert_bits_equal(full["force"], want["force"], "force after frames")
+
+
+def test_step_frame_on_an_empty_world_and_bad_sizes(tr):
+    with tr.World(tr.default_params()) as w:
+        w.step_frame(np.zeros(0, dtype=tr.FRAME_DTYPE))
+        w.add(scenes.random_cloud(10, 1, spheres=True))
+        with pytest.raises(tr.TraceItError):
+            w.step_frame(np.zeros(9, dtype=tr.FRAME_DTYPE))

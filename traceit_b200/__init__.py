@@ -19,7 +19,7 @@ import numpy as np
 __all__ = [
     "BODY_DTYPE", "Params", "Stats", "TraceItError", "World", "lib", "lib_path", "build_extension",
     "default_params", "to_spherical", "area_from_size", "new_bodies", "PAIR_GRAVITY", "COLLISIONS",
-    "comm_unique_id", "measure_fma_peak", "ABI_SYMBOLS",
+    "comm_unique_id", "measure_fma_peak", "ABI_SYMBOLS", "FRAME_DTYPE",
 ]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -81,8 +81,12 @@ ABI_SYMBOLS = [
     "tr_world_owned_range", "tr_to_spherical", "tr_area_from_size", "tr_step", "tr_sync", "tr_step_host",
     "tr_read_state", "tr_read_bodies", "tr_write_bodies", "tr_set_force", "tr_read_contacts", "tr_debug_grid",
     "tr_debug_candidates", "tr_debug_gravity", "tr_get_stats", "tr_reset_stats", "tr_enable_timing",
-    "tr_measure_fma_peak", "tr_world_enable_trajectory", "tr_read_trajectory",
+    "tr_measure_fma_peak", "tr_world_enable_trajectory", "tr_read_trajectory", "tr_step_frame",
 ]
+
+# tr_frame_body: what one step changes (pos, vel, collider centre), 36 bytes
+FRAME_DTYPE = np.dtype([("pos", "<f4", 3), ("vel", "<f4", 3), ("center", "<f4", 3)], align=False)
+assert FRAME_DTYPE.itemsize == 36
 
 
 def lib_path() -> str:
@@ -129,6 +133,7 @@ def lib():
         L.tr_step.argtypes = [vp, C.c_int]
         L.tr_sync.argtypes = [vp]
         L.tr_step_host.argtypes = [vp, C.c_uint64, vp, C.c_int]
+        L.tr_step_frame.argtypes = [vp, C.c_uint64, vp, vp, C.c_int]
         L.tr_read_state.argtypes = [vp, C.c_uint64, C.c_uint64, vp, vp]
         L.tr_read_bodies.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
         L.tr_write_bodies.argtypes = [vp, C.c_uint64, C.c_uint64, vp]
@@ -281,6 +286,14 @@ class World:
         assert bodies.dtype == BODY_DTYPE and bodies.flags.c_contiguous
         _check(self._L.tr_step_host(self._h, len(bodies), _ptr(bodies), nsteps))
         return bodies
+
+    def step_frame(self, out: np.ndarray, forces: np.ndarray | None = None, nsteps: int = 1) -> np.ndarray:
+        """tr_step_frame: forces (n,3) float32 up (optional), nsteps, pos/vel/centre down into `out` (FRAME_DTYPE)."""
+        assert out.dtype == FRAME_DTYPE and out.flags.c_contiguous
+        if forces is not None:
+            assert forces.dtype == np.float32 and forces.flags.c_contiguous and forces.shape == (len(out), 3)
+        _check(self._L.tr_step_frame(self._h, len(out), _ptr(forces), _ptr(out), nsteps))
+        return out
 
     # -- state
     def read_state(self, first: int = 0, count: int | None = None, vel: bool = True):

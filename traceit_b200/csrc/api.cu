@@ -158,6 +158,28 @@ __global__ void __launch_bounds__(256) read_state_kernel(const float4* __restric
     }
 }
 
+// per-frame API (tr_step_frame): the only per-step INPUT of the reference step is object::force
+// (consumed and zeroed, main.cpp:782,811); what a step CHANGES is pos, vel and the collider centre
+__global__ void __launch_bounds__(256) force_unpack_kernel(const float* __restrict__ in, uint32_t first, uint32_t count,
+                                                           float4* __restrict__ force) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    force[first + t] = make_float4(in[3 * t + 0], in[3 * t + 1], in[3 * t + 2], 0.f);
+}
+
+__global__ void __launch_bounds__(256) frame_pack_kernel(const float4* __restrict__ pos_m, const float4* __restrict__ vel_rest,
+                                                         const float4* __restrict__ center_r, uint32_t first, uint32_t count,
+                                                         float* __restrict__ out /* 9 floats per body */) {
+    // one thread per output float: coalesced stores, the float4 loads are shared by neighbouring threads through L1
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)count * 9) return;
+    const uint32_t b = (uint32_t)(t / 9), k = (uint32_t)(t % 9);
+    const float4* src = k < 3 ? pos_m : (k < 6 ? vel_rest : center_r);
+    const float4 v = src[first + b];
+    const uint32_t c = k % 3;
+    out[t] = c == 0 ? v.x : (c == 1 ? v.y : v.z);
+}
+
 // sharded collisions: collider centres of bodies integrated by OTHER ranks
 __global__ void __launch_bounds__(256) refresh_remote_centers(const float4* __restrict__ pos_m, float4* center_r,
                                                               const uint8_t* __restrict__ flags, uint32_t n,
@@ -297,35 +319,43 @@ static void set_owned_range(tr_world* w) {
     w->own_count = hi - lo;
 }
 
-// Is [host, host+bytes) the buffer this world page-locked for the per-frame host path?
+// Is [host, host+bytes) a buffer this world page-locked for the per-frame host paths?
 static bool is_registered(const tr_world* w, const void* host, size_t bytes) {
-    return w->reg_ptr && host == w->reg_ptr && bytes <= w->reg_bytes;
+    for (const HostReg& r : w->reg)
+        if (r.ptr && host == r.ptr && bytes <= r.bytes) return true;
+    return false;
+}
+
+static void unregister_slot(HostReg& r) {
+    if (r.ptr) cudaHostUnregister(r.ptr);
+    r.ptr = nullptr;
+    r.bytes = 0;
 }
 
 static void unregister_host(tr_world* w) {
-    if (w->reg_ptr) cudaHostUnregister(w->reg_ptr);
-    w->reg_ptr = nullptr;
-    w->reg_bytes = 0;
+    for (HostReg& r : w->reg) unregister_slot(r);
 }
 
-// tr_step_host is called once per frame with the SAME caller buffer (the shim's staging vector,
-// bench.py's array): from its second consecutive use on, that buffer is page-locked in place so
-// the transfers DMA straight from/to it and the two host-side staging copies disappear.
-static void note_host_buffer(tr_world* w, void* host, size_t bytes) {
-    if (is_registered(w, host, bytes)) return;
-    if (host == w->last_host_ptr && bytes == w->last_host_bytes && bytes >= (1u << 20)) {
-        unregister_host(w);
+// The per-frame calls (tr_step_host, tr_step_frame) are made once per frame with the SAME caller
+// buffers (the shim's staging vectors, bench.py's arrays): from its second consecutive use on, a
+// buffer is page-locked in place so the transfers DMA straight from/to it and the host-side staging
+// copies disappear.  slot: 0 = AoS descriptors, 1 = frame read-back, 2 = per-frame forces.
+static void note_host_buffer(tr_world* w, int slot, void* host, size_t bytes) {
+    HostReg& r = w->reg[slot];
+    if (r.ptr && host == r.ptr && bytes <= r.bytes) return;
+    if (host && host == r.last_ptr && bytes == r.last_bytes && bytes >= (1u << 20)) {
+        unregister_slot(r);
         if (cudaHostRegister(host, bytes, cudaHostRegisterDefault) == cudaSuccess) {
-            w->reg_ptr = host;
-            w->reg_bytes = bytes;
+            r.ptr = host;
+            r.bytes = bytes;
         } else {
             cudaGetLastError();   // not fatal: keep staging through the world's own pinned buffer
         }
-    } else if (w->reg_ptr && host != w->reg_ptr) {
-        unregister_host(w);
+    } else if (r.ptr && host != r.ptr) {
+        unregister_slot(r);
     }
-    w->last_host_ptr = host;
-    w->last_host_bytes = bytes;
+    r.last_ptr = host;
+    r.last_bytes = bytes;
 }
 
 // device <- bodies[first .. first+count) given as host AoS.  sig_out: hash of the
@@ -357,6 +387,15 @@ static int flush_created(tr_world* w) {
     if (!w->dirty_upload) return TR_OK;
     uint64_t total = w->host_bodies.size();
     if (total > w->n) {
+        if (w->nranks > 1 && w->n > 0 && w->ever_stepped) {
+            // Growing an already-stepped sharded world moves the block boundaries (ceil(N/R) targets
+            // per rank): a body may pass to a rank that has not integrated it so far and only ever
+            // received its position.  Bring every rank's copy of the per-body state a step mutates up
+            // to date under the OLD partition first (velocity, pending external force, collider centre).
+            TR_TRY(nccl_allgather_pos(w, w->vel_rest));
+            TR_TRY(nccl_allgather_pos(w, w->force));
+            TR_TRY(nccl_allgather_pos(w, w->center_r));
+        }
         TR_TRY(upload_range(w, w->n, total - w->n, w->host_bodies.data() + w->n));
         w->n = total;
     }
@@ -498,6 +537,7 @@ static int step_once(tr_world* w) {
     }
     if (coll) TR_TRY(collide_step(w));
     w->stats.steps += 1;
+    w->ever_stepped = true;
     return TR_OK;
 }
 
@@ -696,7 +736,7 @@ int tr_sync(tr_world* w) {
 int tr_step_host(tr_world* w, uint64_t n, tr_body_desc* bodies, int nsteps) {
     TR_TRY(check_world(w));
     if (!bodies && n) return TR_ERR_INVALID_ARG;
-    note_host_buffer(w, bodies, n * sizeof(tr_body_desc));
+    note_host_buffer(w, 0, bodies, n * sizeof(tr_body_desc));
     if (w->nranks > 1) {
         // sharded: `bodies` is this rank's owned block; positions are re-gathered so that
         // every rank sees every other rank's freshly uploaded sources
@@ -740,6 +780,51 @@ int tr_step_host(tr_world* w, uint64_t n, tr_body_desc* bodies, int nsteps) {
     }
     TR_TRY(tr_step(w, nsteps));
     TR_TRY(download_range(w, 0, n, bodies));
+    return tr_sync(w);
+}
+
+int tr_step_frame(tr_world* w, uint64_t n, const float* force_xyz, tr_frame_body* out, int nsteps) {
+    TR_TRY(check_world(w));
+    TR_TRY(flush_created(w));
+    const uint64_t first = w->nranks > 1 ? w->own_first : 0;
+    const uint64_t want = w->nranks > 1 ? w->own_count : w->n;
+    if (n != want) {
+        set_error("tr_step_frame: %llu bodies passed, %s %llu", (unsigned long long)n, w->nranks > 1 ? "this rank owns" : "world holds",
+                  (unsigned long long)want);
+        return TR_ERR_INVALID_ARG;
+    }
+    if (n == 0) return tr_step(w, nsteps);
+    TR_TRY(ensure_staging(w, n));   // staging is sized in 92-byte descriptors: room for 12 and 36 bytes per body
+    if (force_xyz) {
+        // the step's per-frame input: external forces (obj.force = ..., consumed and zeroed by the step)
+        const size_t bytes = (size_t)n * 3 * sizeof(float);
+        note_host_buffer(w, 2, (void*)force_xyz, bytes);
+        const void* src = force_xyz;
+        if (!is_registered(w, force_xyz, bytes)) {
+            TR_CUDA(cudaStreamSynchronize(w->stream));   // the pinned staging may still feed an earlier copy
+            memcpy(w->pinned, force_xyz, bytes);
+            src = w->pinned;
+        }
+        TR_CUDA(cudaMemcpyAsync(w->aos, src, bytes, cudaMemcpyHostToDevice, w->stream));
+        force_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, w->stream>>>((const float*)w->aos, (uint32_t)first, (uint32_t)n, w->force);
+        TR_CUDA(cudaGetLastError());
+        w->stats.kernel_launches += 1;
+    }
+    TR_TRY(tr_step(w, nsteps));
+    if (out) {
+        const size_t bytes = (size_t)n * sizeof(tr_frame_body);
+        note_host_buffer(w, 1, out, bytes);
+        const uint64_t words = n * 9;
+        frame_pack_kernel<<<(unsigned)((words + 255) / 256), 256, 0, w->stream>>>(w->pos_m[w->cur], w->vel_rest, w->center_r,
+                                                                                  (uint32_t)first, (uint32_t)n, (float*)w->aos);
+        TR_CUDA(cudaGetLastError());
+        w->stats.kernel_launches += 1;
+        const bool direct = is_registered(w, out, bytes);
+        TR_CUDA(cudaMemcpyAsync(direct ? (void*)out : (void*)w->pinned, w->aos, bytes, cudaMemcpyDeviceToHost, w->stream));
+        TR_TRY(tr_sync(w));
+        if (!direct) memcpy(out, w->pinned, bytes);
+        return TR_OK;
+    }
     return tr_sync(w);
 }
 

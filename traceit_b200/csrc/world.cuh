@@ -76,6 +76,14 @@ struct StepConsts {
 // ---- per-kernel timing ----------------------------------------------------------------
 enum TimerCat { T_GRAVITY = 0, T_BROAD, T_NARROW, T_RESPONSE, T_INTEGRATE, T_ALLGATHER, T_NCAT };
 
+// a caller buffer page-locked in place for the per-frame host paths (api.cu note_host_buffer)
+struct HostReg {
+    void* ptr = nullptr;       // registered (page-locked) buffer
+    size_t bytes = 0;
+    void* last_ptr = nullptr;  // buffer seen by the previous call
+    size_t last_bytes = 0;
+};
+
 struct PendingTimer {
     cudaEvent_t a, b;
     int cat;
@@ -97,6 +105,7 @@ struct tr_world {
     uint64_t cap = 0;        // allocated capacity (bodies)
     bool dirty_upload = false;
     bool classified = false; // grid / side-list split is current
+    bool ever_stepped = false;
 
     // sharding
     int rank = 0, nranks = 1;
@@ -119,10 +128,7 @@ struct tr_world {
     unsigned long long* d_sig = nullptr;    // classification hash of the last per-frame upload
     unsigned long long host_sig = 0;
     bool have_sig = false;
-    void* reg_ptr = nullptr;                // caller buffer page-locked for tr_step_host
-    size_t reg_bytes = 0;
-    void* last_host_ptr = nullptr;
-    size_t last_host_bytes = 0;
+    tr::HostReg reg[3];                     // caller buffers page-locked in place: AoS descriptors, frame read-back, forces
 
     // optional trajectory ring: traj[(slot*3 + c) * traj_stride + body], traj_cnt[body] = points pushed
     float* traj = nullptr;

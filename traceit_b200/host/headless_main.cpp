@@ -6,7 +6,11 @@
 // traceit_host.hpp.  Prints a state hash (FNV-1a over pos/vel bit patterns, the same hash the
 // golden vectors store) so tests can compare a whole run with the verbatim reference.
 //
-//   traceit_headless [--steps K] [--cloud N] [--gravity G] [--no-file] [--trace I]
+//   traceit_headless [--steps K] [--cloud N] [--pack] [--gravity G] [--no-file] [--trace I] [--time]
+//     --pack   with --cloud N: the config-5 shape (jittered lattice of radius-0.5 spheres, pitch 0.98) instead of the sparse cloud
+//     --time   print "TIME {json}": wall-clock ms per frame through updatePhysics (host pack + upload + step + read-back +
+//              host unpack), first two frames excluded (they create the device world and page-lock the staging buffer)
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -89,7 +93,7 @@ static object make_projectile(float mass, float Cd, float elev, float azim, floa
 int main(int argc, char** argv) {
     int steps = 1000, cloud = 0, trace = 1;
     float G = 0.0f;
-    bool file = true;
+    bool file = true, timeit = false, pack = false;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         if (a == "--steps" && i + 1 < argc) steps = std::atoi(argv[++i]);
@@ -97,6 +101,8 @@ int main(int argc, char** argv) {
         else if (a == "--gravity" && i + 1 < argc) G = (float)std::atof(argv[++i]);
         else if (a == "--trace" && i + 1 < argc) trace = std::atoi(argv[++i]);
         else if (a == "--no-file") file = false;
+        else if (a == "--time") timeit = true;
+        else if (a == "--pack") pack = true;
         else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
 
@@ -123,6 +129,26 @@ int main(int argc, char** argv) {
         // config 1 projectiles
         w.objects.push_back(make_projectile(10, 0.42f, 45, 0, 30, 1, {0, 0, 0}));
         w.objects.push_back(make_projectile(5, 0.42f, 60, 90, 20, 2, {5, 0, 0}));
+    } else if (pack) {
+        // config 5 shape: nx x ny x nz lattice (x fastest), pitch 0.98, jitter +-0.01, velocities in [-0.1,0.1]^3, unit mass
+        int e = 0;
+        while ((1 << (e + 1)) <= cloud) ++e;
+        const int ex = (e + 2) / 3, ey = (e - ex + 1) / 2, ez = e - ex - ey;
+        const int nx = 1 << ex, ny = 1 << ey, nz = 1 << ez;
+        std::mt19937 rng(0xC0FFEE05u);
+        std::uniform_real_distribution<float> uj(-0.01f, 0.01f), uv(-0.1f, 0.1f);
+        for (int i = 0; i < nx * ny * nz; ++i) {
+            const int ix = i % nx, iy = (i / nx) % ny, iz = i / (nx * ny);
+            object o{};
+            o.pos = {(ix - (nx - 1) * 0.5f) * 0.98f + uj(rng), (iy - (ny - 1) * 0.5f) * 0.98f + uj(rng), (iz - (nz - 1) * 0.5f) * 0.98f + uj(rng)};
+            o.vel = {uv(rng), uv(rng), uv(rng)};
+            o.mass = 1.0f;
+            o.Cd = 0.42f;
+            o.area = tr_area_from_size(0.5f);
+            o.col = {o.pos, {0.5f, 0.5f, 0.5f}, 0.5f, true, false, 0.5f};
+            o.stationary = false;
+            w.objects.push_back(o);
+        }
     } else {
         std::mt19937 rng(0xC0FFEE02u);
         float L = 4.0f * std::cbrt((float)cloud);
@@ -145,9 +171,16 @@ int main(int argc, char** argv) {
     traceit_b200::options().write_trajectory_file = file;
 
     std::ofstream coords;
+    double timed_ms = 0.0;
+    int timed_frames = 0;
     try {
         for (int s = 0; s < steps; ++s) {
+            const auto t0 = std::chrono::steady_clock::now();
             traceit_b200::updatePhysics(w, coords);   // the call of src/main.cpp:1589
+            if (s >= 2) {
+                timed_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                ++timed_frames;
+            }
             if ((s + 1 == 100 || s + 1 == steps) && trace >= 0 && trace < (int)w.objects.size()) {
                 const object& o = w.objects[trace];
                 std::printf("step %d body %d pos %.9g %.9g %.9g vel %.9g %.9g %.9g\n", s + 1, trace, o.pos.x, o.pos.y, o.pos.z,
@@ -158,6 +191,12 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "%s\n", e.what());
         return 1;
     }
+    if (timeit && timed_frames > 0)
+        std::printf("TIME {\"api\": \"traceit_b200::updatePhysics(world&, ofstream&) on 232-byte reference-shaped objects\", "
+                    "\"n_bodies\": %zu, \"frames\": %d, \"ms_per_frame\": %.4f, \"shape\": \"%s\", \"h2d_bytes_per_frame\": %llu, "
+                    "\"d2h_bytes_per_frame\": %llu}\n",
+                    w.objects.size(), timed_frames, timed_ms / timed_frames, cloud <= 0 ? "default scene" : (pack ? "cfg5 pack" : "sparse cloud"),
+                    (unsigned long long)traceit_b200::last_frame_h2d_bytes(), (unsigned long long)traceit_b200::last_frame_d2h_bytes());
     std::printf("bodies %zu steps %d hash 0x%016llx\n", w.objects.size(), steps, (unsigned long long)state_hash(w));
     traceit_b200::release(w);
     return 0;

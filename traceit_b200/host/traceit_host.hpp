@@ -12,22 +12,32 @@
 //             col { center, size {x,y,z}, radius, isSphere, isStatic, rest }
 // optional (used when present): trajectory, maxTrajectoryPoints, trajWritten, transform.
 //
-// Per call: AoS objects -> tr_body_desc -> tr_step_host (upload, one step on the B200,
-// read back) -> AoS.  The world's side effects are reproduced on the host:
+// The world lives on the device between frames.  Per call:
+//   1. every object's hot fields are packed and compared with the shim's shadow copy (what the
+//      device holds); bodies the host code changed since the last frame - a force it set, a body
+//      it moved - are re-uploaded (tr_write_bodies, 92 B each); usually that is nothing;
+//   2. tr_step_frame runs one step on the B200 and reads back what a step changes: pos, vel and
+//      the collider centre (36 B per body);
+//   3. those are written into the objects (force is zeroed for non-stationary bodies as
+//      main.cpp:811 does) and the world's side effects are reproduced on the host:
 //   * trajectory history + one-shot dump to "Координаты.txt"   src/main.cpp:754-761,793-808,814
 //     (the reference pushes the position right after integration, i.e. before the collision
 //      nudges; that value is the refreshed collider centre, src/main.cpp:791)
 //   * object.transform = translation(pos)                      src/main.cpp:641-644,810
+// Steps 1 and 3 run on a few host threads for large worlds (each object is touched by one thread).
 // Error behaviour: the reference step returns void and cannot fail; here a failure (no
 // B200, CUDA error, contact-buffer overflow) throws std::runtime_error with tr_last_error()
 // - there is no CPU fallback to fall into.
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
+#include <cstring>
 #include <fstream>
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -51,10 +61,36 @@ inline void check(int rc, const char* what) {
 
 struct Session {
     tr_world* w = nullptr;
-    std::vector<tr_body_desc> staging;
+    std::vector<tr_body_desc> shadow;    // the device's copy of every body, as the host last saw / wrote it
+    std::vector<tr_frame_body> frame;    // per-frame read-back
     size_t n = 0;
     ~Session() { if (w) tr_world_destroy(w); }
 };
+
+struct FrameBytes { unsigned long long h2d = 0, d2h = 0; };
+inline FrameBytes& frame_bytes() {
+    static FrameBytes b;
+    return b;
+}
+
+// fn(lo, hi, thread) over [0, n) on up to 16 host threads (serial for small worlds)
+template <class Fn>
+inline void parallel_for(size_t n, Fn fn) {
+    unsigned t = std::thread::hardware_concurrency();
+    t = t < 1 ? 1 : (t > 16 ? 16 : t);
+    if (n < 32768 || t == 1) {
+        fn((size_t)0, n, 0u);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const size_t per = (n + t - 1) / t;
+    for (unsigned k = 0; k < t; ++k) {
+        const size_t lo = per * k, hi = std::min(n, lo + per);
+        if (lo >= hi) break;
+        pool.emplace_back([=] { fn(lo, hi, k); });
+    }
+    for (std::thread& th : pool) th.join();
+}
 
 // One device world per host world object (keyed by address), created on first use.
 inline std::map<const void*, Session>& sessions() {
@@ -77,12 +113,16 @@ inline void to_desc(const Object& o, tr_body_desc& d) {
     d.rest = o.col.rest;
 }
 
+// what one step changes, into the object and into the shadow copy of it
 template <class Object>
-inline void from_desc(const tr_body_desc& d, Object& o) {
-    o.pos.x = d.pos[0]; o.pos.y = d.pos[1]; o.pos.z = d.pos[2];
-    o.vel.x = d.vel[0]; o.vel.y = d.vel[1]; o.vel.z = d.vel[2];
-    o.force.x = d.force[0]; o.force.y = d.force[1]; o.force.z = d.force[2];
-    o.col.center.x = d.center[0]; o.col.center.y = d.center[1]; o.col.center.z = d.center[2];
+inline void from_frame(const tr_frame_body& f, Object& o, tr_body_desc& d) {
+    o.pos.x = d.pos[0] = f.pos[0]; o.pos.y = d.pos[1] = f.pos[1]; o.pos.z = d.pos[2] = f.pos[2];
+    o.vel.x = d.vel[0] = f.vel[0]; o.vel.y = d.vel[1] = f.vel[1]; o.vel.z = d.vel[2] = f.vel[2];
+    o.col.center.x = d.center[0] = f.center[0]; o.col.center.y = d.center[1] = f.center[1]; o.col.center.z = d.center[2] = f.center[2];
+    if (!o.stationary) {   // obj.force = {0,0,0} at the end of the non-stationary branch (main.cpp:764,811)
+        o.force.x = o.force.y = o.force.z = 0.0f;
+        d.force[0] = d.force[1] = d.force[2] = 0.0f;
+    }
 }
 
 }  // namespace detail
@@ -123,6 +163,7 @@ void updatePhysics(World& w, std::ofstream& coords) {
     if (s.w && s.n != n) {                   // bodies were pushed or erased: rebuild the device world
         tr_world_destroy(s.w);
         s.w = nullptr;
+        s.shadow.clear();
     }
     if (!s.w) {
         detail::check(tr_world_create(&p, opt.device, &s.w), "tr_world_create");
@@ -140,40 +181,91 @@ void updatePhysics(World& w, std::ofstream& coords) {
         }
     }
 
+    detail::FrameBytes& fb = detail::frame_bytes();
+    fb = detail::FrameBytes{};
     if (n) {
-        s.staging.resize(n);
-        for (size_t i = 0; i < n; ++i) detail::to_desc(w.objects[i], s.staging[i]);
-        detail::check(tr_step_host(s.w, n, s.staging.data(), 1), "tr_step_host");
-        for (size_t i = 0; i < n; ++i) {
-            Object& o = w.objects[i];
-            const bool moved = !o.stationary;
-            detail::from_desc(s.staging[i], o);
-            if (!moved) continue;            // the reference touches only non-stationary bodies below
-            if constexpr (detail::has_trajectory<Object>::value) {
-                // position right after integration == refreshed collider centre
-                o.trajectory.push_back(o.col.center);
-                if (o.trajectory.size() == (size_t)o.maxTrajectoryPoints && !o.trajWritten) {
-                    if (opt.write_trajectory_file) {
-                        coords << "\nТраектория объекта [" << "obj.id" << "]:\n";
-                        for (const auto& pt : o.trajectory) coords << pt.x << "(м)\t" << pt.y << "(м)\t" << pt.z << "(м)\n";
-                    }
-                    o.trajWritten = true;
+        if (s.shadow.size() != n) {
+            // first frame of this world: create every body on the device
+            s.shadow.resize(n);
+            s.frame.resize(n);
+            detail::parallel_for(n, [&](size_t lo, size_t hi, unsigned) {
+                for (size_t i = lo; i < hi; ++i) {
+                    std::memset(&s.shadow[i], 0, sizeof(tr_body_desc));
+                    detail::to_desc(w.objects[i], s.shadow[i]);
                 }
-                if (o.trajectory.size() > (size_t)o.maxTrajectoryPoints) o.trajectory.erase(o.trajectory.begin());
+            });
+            detail::check(tr_bodies_add(s.w, n, s.shadow.data(), nullptr), "tr_bodies_add");
+            fb.h2d += n * sizeof(tr_body_desc);
+        } else {
+            // what did the host code change since the last frame?  (bit compare: NaNs and signed zeros included)
+            std::vector<std::pair<size_t, size_t>> dirty(17, {n, 0});
+            detail::parallel_for(n, [&](size_t lo, size_t hi, unsigned k) {
+                size_t dlo = n, dhi = 0;
+                for (size_t i = lo; i < hi; ++i) {
+                    tr_body_desc d;
+                    std::memset(&d, 0, sizeof(d));
+                    detail::to_desc(w.objects[i], d);
+                    if (std::memcmp(&d, &s.shadow[i], sizeof(d)) != 0) {
+                        s.shadow[i] = d;
+                        dlo = std::min(dlo, i);
+                        dhi = std::max(dhi, i + 1);
+                    }
+                }
+                dirty[k] = {dlo, dhi};
+            });
+            size_t dlo = n, dhi = 0;
+            for (const auto& d : dirty) {
+                dlo = std::min(dlo, d.first);
+                dhi = std::max(dhi, d.second);
             }
-            if constexpr (detail::has_transform<Object>::value) {
-                // createTranslationMatrix(centre) - note: the reference builds it from the
-                // post-integration, pre-collision position (main.cpp:810 runs before 816)
-                for (int r = 0; r < 4; ++r)
-                    for (int c = 0; c < 4; ++c) o.transform.m[r][c] = (r == c) ? 1.0f : 0.0f;
-                o.transform.m[0][3] = o.col.center.x;   // translation sits in the 4th column (main.cpp:483-493)
-                o.transform.m[1][3] = o.col.center.y;
-                o.transform.m[2][3] = o.col.center.z;
+            if (dlo < dhi) {
+                detail::check(tr_write_bodies(s.w, dlo, dhi - dlo, s.shadow.data() + dlo), "tr_write_bodies");
+                fb.h2d += (dhi - dlo) * sizeof(tr_body_desc);
             }
+        }
+        detail::check(tr_step_frame(s.w, n, nullptr, s.frame.data(), 1), "tr_step_frame");
+        fb.d2h += n * sizeof(tr_frame_body);
+        std::vector<std::vector<size_t>> dump(17);
+        detail::parallel_for(n, [&](size_t lo, size_t hi, unsigned k) {
+            for (size_t i = lo; i < hi; ++i) {
+                Object& o = w.objects[i];
+                detail::from_frame(s.frame[i], o, s.shadow[i]);
+                if (o.stationary) continue;      // the reference touches only non-stationary bodies below (main.cpp:764)
+                if constexpr (detail::has_trajectory<Object>::value) {
+                    // position right after integration == refreshed collider centre
+                    o.trajectory.push_back(o.col.center);
+                    if (o.trajectory.size() == (size_t)o.maxTrajectoryPoints && !o.trajWritten) {
+                        dump[k].push_back(i);    // written below, in object order, by one thread
+                        o.trajWritten = true;
+                    }
+                    if (o.trajectory.size() > (size_t)o.maxTrajectoryPoints) o.trajectory.erase(o.trajectory.begin());
+                }
+                if constexpr (detail::has_transform<Object>::value) {
+                    // createTranslationMatrix(centre) - note: the reference builds it from the
+                    // post-integration, pre-collision position (main.cpp:810 runs before 816)
+                    for (int r = 0; r < 4; ++r)
+                        for (int c = 0; c < 4; ++c) o.transform.m[r][c] = (r == c) ? 1.0f : 0.0f;
+                    o.transform.m[0][3] = o.col.center.x;   // translation sits in the 4th column (main.cpp:483-493)
+                    o.transform.m[1][3] = o.col.center.y;
+                    o.transform.m[2][3] = o.col.center.z;
+                }
+            }
+        });
+        if constexpr (detail::has_trajectory<Object>::value) {
+            if (opt.write_trajectory_file)
+                for (const auto& list : dump)          // thread ranges are ascending: object order, as the reference's loop
+                    for (size_t i : list) {
+                        coords << "\nТраектория объекта [" << "obj.id" << "]:\n";
+                        for (const auto& pt : w.objects[i].trajectory) coords << pt.x << "(м)\t" << pt.y << "(м)\t" << pt.z << "(м)\n";
+                    }
         }
     }
     if (opt.write_trajectory_file) coords.close();
 }
+
+// bytes the last updatePhysics call moved over PCIe (observability for the harness / bench.py)
+inline unsigned long long last_frame_h2d_bytes() { return detail::frame_bytes().h2d; }
+inline unsigned long long last_frame_d2h_bytes() { return detail::frame_bytes().d2h; }
 
 // toSpherical of the creation form (src/main.cpp:1080-1089), any {x,y,z} aggregate.
 template <class Vec3>
