@@ -477,7 +477,7 @@ def measure(ctx: Ctx, name: str, n: int | None, steps: int, warmup: int, *, shar
     return res
 
 
-def shim_frame_time(n: int, frames: int = 6):
+def shim_frame_time(n: int, frames: int = 6, pack: bool = True):
     """ms per frame through the REAL drop-in path: traceit_headless drives the C++ shim
     traceit_b200::updatePhysics(world&, ofstream&) on reference-shaped 232-byte objects
     (pack -> tr_step_host -> unpack on the host, every frame).  Reference call site: src/main.cpp:1589."""
@@ -485,8 +485,8 @@ def shim_frame_time(n: int, frames: int = 6):
     if not os.path.exists(exe):
         return {"error": "traceit_headless not built"}
     with tempfile.TemporaryDirectory() as d:
-        r = subprocess.run([exe, "--cloud", str(n), "--steps", str(frames), "--no-file", "--time", "--spheres"], capture_output=True,
-                           text=True, cwd=d, timeout=600)
+        r = subprocess.run([exe, "--cloud", str(n), "--steps", str(frames), "--no-file", "--time"] + (["--pack"] if pack else []),
+                           capture_output=True, text=True, cwd=d, timeout=600)
     if r.returncode != 0:
         return {"error": (r.stderr or r.stdout)[-300:]}
     for ln in r.stdout.splitlines():
@@ -554,7 +554,8 @@ def main():
             # T1 of SURVEY.md 8d config 4: the 4M cloud on ONE GPU (the denominator of the same-N efficiency)
             guarded("cfg4_t1", lambda: measure(ctx, "cfg4", None, 2, 1, sharded=False, want_e2e=False))
             if rank == 0:
-                guarded("e2e_shim", lambda: {"cfg5_1m": shim_frame_time(1 << 20), "default_scene_like_4k": shim_frame_time(4096, 50)})
+                guarded("e2e_shim", lambda: {"cfg5_1m": shim_frame_time(1 << 20), "sparse_cloud_4k": shim_frame_time(4096, 200, pack=False),
+                                             "default_scene": shim_frame_time(0, 500)})
         else:
             # T1 at the SAME N on one GPU (rank 0, unsharded world; the other ranks wait at the barrier)
             if rank == 0:

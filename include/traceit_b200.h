@@ -58,7 +58,8 @@ typedef struct tr_world_params {
     /* Uniform-grid broad phase (no reference counterpart; the reference is brute force).
      * 0 / zeros = automatic.  cell edge defaults to 2*rmax*(1+2^-7) where rmax is the
      * largest radius among grid bodies; grid_bits is bits per axis of the wrapped key
-     * (2..10, the same on x, y, z); automatic = the smallest table with 2 cells per body,
+     * (2..10, the same on x, y, z); a grid_cell below 2*rmax*(1+2^-7) would make the 27-cell
+     * stencil miss contacts and is raised to that; automatic bits = the smallest table with 2 cells per body,
      * its bits spread over the axes (x first).  Spheres and boxes share the grid (a body's
      * extent is |radius|, and max|size| as soon as boxes exist); oversize bodies go to a
      * side list tested against every body, bodies outside the grid domain to a far list
@@ -66,7 +67,12 @@ typedef struct tr_world_params {
     float grid_origin[3];
     float grid_cell;
     int32_t grid_bits;
-    uint64_t max_contacts;       /* 0 = 8*N + 4096 */
+    uint64_t max_contacts;       /* 0 = automatic: the contact buffers (~100 bytes per slot) start at
+                                    N + 32768 slots and grow when a step finds more (the step is
+                                    completed with the larger buffers, nothing is lost).  Non-zero =
+                                    hard cap: a step that finds more reports TR_ERR_CAPACITY at the
+                                    next synchronisation and leaves the world as that step's
+                                    integration left it (no response applied, later steps not run). */
     /* Largest extent admitted to the grid; 0 = automatic: the largest extent that is
      * <= 8x the median extent.                                           */
     float grid_max_radius;
@@ -76,8 +82,13 @@ typedef struct tr_world_params {
      * to whole warps / single-lane workers.  All replay the reference's Gauss-Seidel order exactly
      * and give identical bits; see DESIGN.md K6.                                          */
     uint32_t response_mode;
-    uint32_t reserved[2];
+    /* Test / debugging knobs, 0 in production.  TR_DEBUG_NO_TINY: worlds of up to 256 bodies normally
+     * run whole steps in ONE single-CTA kernel (the reference's own algorithm, detection spread over the
+     * CTA's threads; see DESIGN.md "small worlds"); the flag sends them through the general grid pipeline. */
+    uint32_t debug_flags;
+    uint32_t reserved;
 } tr_world_params;
+#define TR_DEBUG_NO_TINY 1u
 
 /* Body descriptor = hot fields of the reference's `object` + `collider`
  * (src/main.cpp:79-105), same names and meaning.  The UI-side parameter contract
@@ -151,8 +162,10 @@ int tr_to_spherical(float elev_deg, float azim_deg, float magnitude, float out_v
 float tr_area_from_size(float size);
 
 /* ---- the step: replaces updatePhysics(w, coords) (src/main.cpp:748, call site 1589) - */
-int tr_step(tr_world* w, int nsteps);            /* asynchronous on the world's stream    */
-int tr_sync(tr_world* w);                        /* wait; reports deferred device errors  */
+int tr_step(tr_world* w, int nsteps);            /* asynchronous on the world's stream: nothing in a
+                                                    step waits for the host, collisions included */
+int tr_sync(tr_world* w);                        /* wait; reports deferred device errors; completes a
+                                                    step whose contact list outgrew its buffers */
 /* Host-buffer round trip used by the C++ shim: upload bodies[0..n) (AoS), run nsteps,
  * read them back.  n must equal the world size (bodies are created on first use); on a
  * sharded world n is this rank's owned count.  When the SAME buffer is passed on

@@ -7,7 +7,7 @@
  *
  * PINNING: with pair gravity off and default constants this restatement must equal the
  * verbatim reference (oracle/_ref/libtraceit_ref.so, built in place from the reference
- * TU) BIT FOR BIT on pos/vel/force over K steps - tests/test_oracle_chain.py, and the
+ * TU) BIT FOR BIT on pos/vel/force over K steps - tests/test_oracle.py, and the
  * committed golden vectors under tests/golden/ were produced by the verbatim build.
  * Pair gravity is DEAD CODE in the reference (main.cpp:679-693), so that one term is
  * "parity unpinned by live code": it follows the commented formula with the deviations

@@ -71,10 +71,27 @@ def test_default_scene_golden_gpu(tr):
     """Config 1 on the GPU: the two box projectiles live in the grid (AABB predicate), the
     10000x5x10000 slab is oversize and sits in the side list; 1000 steps."""
     g = load_golden("default_scene.npz")
-    got, contacts, st = gpu_run(tr, g["initial"].copy(), 1000)
+    # through the general pipeline (a 3-body world normally takes the single-CTA path, tested below)
+    got, contacts, st = gpu_run(tr, g["initial"].copy(), 1000, debug_flags=tr.DEBUG_NO_TINY)
     check_state(got, g["final"], "default scene")
     assert np.array_equal(contacts, g["contacts"])
     assert st.side_list_size == 1
+
+
+def test_default_scene_golden_single_cta_path(tr):
+    """The same 1000 steps the way a 3-body world really runs: whole steps inside ONE kernel of one CTA
+    (tiny.cuh), here as one launch of 1000 steps and as 1000 launches of one."""
+    g = load_golden("default_scene.npz")
+    got, contacts, st = gpu_run(tr, g["initial"].copy(), 1000)
+    check_state(got, g["final"], "default scene, tr_step(w, 1000)")
+    assert np.array_equal(contacts, g["contacts"])
+    assert st.kernel_launches <= 3 and st.steps == 1000
+    with tr.World(tr.default_params()) as w:
+        w.add(g["initial"].copy())
+        for _ in range(1000):
+            w.step(1, sync=False)
+        check_state(w.read_bodies(), g["final"], "default scene, 1000 x tr_step(w, 1)")
+        assert np.array_equal(w.contacts(), g["contacts"])
 
 
 @pytest.mark.parametrize("name,steps", [("sphere_cloud_2048_s1.npz", 1), ("sphere_cloud_2048_s50.npz", 50),
@@ -706,3 +723,159 @@ def test_all_box_world_uses_the_grid(tr, oracle):
     check_state(got, want, "box world")
     assert np.array_equal(contacts, oracle.contacts(want)) and len(contacts) > 1000
     assert st.side_list_size == 0
+
+
+# ---------------------------------------------------------------- small worlds: the single-CTA step
+@pytest.mark.parametrize("n,dens,steps", [(2, 0.3, 5), (37, 0.45, 40), (256, 0.5, 25), (256, 0.25, 6)])
+def test_small_world_single_cta_step_bit_exact(tr, oracle, n, dens, steps):
+    """Worlds of up to 256 bodies run whole steps in one kernel (integrate, brute-force detection with the
+    reference's guards and predicates, sequential Gauss-Seidel replay): spheres, boxes, static, stationary and
+    zero-mass bodies, pending forces - every field bit for bit, the contact list in the reference's order, and
+    identical to the general grid pipeline on the same world."""
+    rs = np.random.RandomState(n * 7 + steps)
+    b = scenes.random_cloud(n, 100 + n, spheres=True, density_l=dens)
+    b["isSphere"][::3] = 0
+    b["size"][::3] = (0.6, 0.4, 0.5)
+    b["isStatic"][::7] = 1
+    b["stationary"][::5] = 1
+    b["mass"][::13] = 0
+    b["force"] = rs.uniform(-20, 20, size=(n, 3)).astype(np.float32)
+    want = b.copy()
+    oracle.step(want, oracle.default_params(), steps)
+    got, contacts, st = gpu_run(tr, b, steps)
+    check_state(got, want, "single CTA")
+    assert np.array_equal(contacts, oracle.contacts(want))
+    assert st.kernel_launches <= 3, "a small world is one launch per tr_step call"
+    got2, contacts2, st2 = gpu_run(tr, b, steps, debug_flags=tr.DEBUG_NO_TINY)
+    check_state(got2, want, "general pipeline on a small world")
+    assert np.array_equal(contacts2, contacts) and st2.kernel_launches > steps
+
+
+def test_small_world_trajectory_ring_and_growth_past_the_limit(tr, oracle):
+    """History ring on the single-CTA path, and a world that grows from 200 to 300 bodies mid-run (switching
+    to the grid pipeline) against the oracle doing the same."""
+    b = scenes.random_cloud(300, 5, spheres=True, density_l=0.5)
+    want = b[:200].copy()
+    with tr.World(tr.default_params()) as w:
+        w.enable_trajectory(8)
+        w.add(b[:200])
+        w.step(12)
+        oracle.step(want, oracle.default_params(), 12)
+        hist = w.trajectory(3)
+        assert hist.shape == (8, 3)
+        w.add(b[200:])
+        want = np.concatenate([want, b[200:]])
+        w.step(6)
+        oracle.step(want, oracle.default_params(), 6)
+        check_state(w.read_bodies(), want, "grown world")
+        assert np.array_equal(w.contacts(), oracle.contacts(want))
+    # the ring holds the post-integration positions of the last 8 of the first 12 steps
+    ref = b[:200].copy()
+    pts = []
+    for _ in range(12):
+        tmp = ref.copy()
+        oracle.step(tmp, oracle.default_params(flags=0), 1)      # integration only: the pushed point
+        pts.append(tmp["pos"][3].copy())
+        oracle.step(ref, oracle.default_params(), 1)
+    assert_bits_equal(hist, np.array(pts[-8:]), "ring on the single-CTA path")
+
+
+# ---------------------------------------------------------------- hub-shaped contact graphs
+def test_hub_scene_slab_with_100k_boxes(tr, oracle):
+    """Config 1's shape scaled up: the reference's 10000 x 5 x 10000 `earth` slab (main.cpp:1482-1491, stationary,
+    not static) with 100,000 boxes inside its AABB at once.  Every box is in contact with the slab, so the slab's
+    contact list has 10^5 entries (sorted by a CTA, not ranked entry against entry) and the reference's order makes
+    its 10^5 contacts one sequential chain.  3 steps, bit for bit; the oracle replays the brute-force contact list."""
+    n = 100_000
+    rs = np.random.RandomState(9)
+    b = scenes.random_cloud(n + 1, 91, spheres=False)
+    b["pos"][1:, 0] = rs.uniform(-900, 900, n)
+    b["pos"][1:, 1] = rs.uniform(-24.5, -15.5, n)
+    b["pos"][1:, 2] = rs.uniform(-900, 900, n)
+    b["size"][1:] = rs.uniform(0.3, 1.0, size=(n, 3)).astype(np.float32)
+    b["mass"][1:] = rs.uniform(1, 10, n).astype(np.float32)
+    b[0] = scenes.default_scene()[0]
+    b["center"] = b["pos"]
+    want = b.copy()
+    op = oracle.default_params(flags=0)
+    with tr.World(tr.default_params()) as w:
+        w.add(b)
+        for s in range(3):
+            w.step(1)
+            oracle.step(want, op, 1)                 # drag + uniform gravity + integration
+            c = oracle.contacts(want)                # brute force, parallel over i
+            oracle.resolve_list(want, c)             # == the sequential sweep
+            assert np.array_equal(w.contacts(), c) and (c[:, 0] == 0).sum() >= n - 5
+        st = w.stats()
+        check_state(w.read_bodies(), want, "hub scene")
+    assert st.side_list_size == 1 and st.last_contacts >= n
+
+
+def test_static_hub_orders_nothing(tr, oracle):
+    """The same slab as an isStatic body: its contacts never change it, so they carry no dependency through it
+    (the executor runs them concurrently) - and the result is still the sequential sweep's."""
+    n = 30_000
+    rs = np.random.RandomState(10)
+    b = scenes.random_cloud(n + 1, 92, spheres=True, density_l=0.5)
+    b[0] = scenes.default_scene()[0]
+    b["isStatic"][0] = 1
+    b["pos"][0] = (0, -30, 0)
+    b["pos"][1:, 0] = rs.uniform(-60, 60, n)
+    b["pos"][1:, 1] = rs.uniform(-34, -26, n)
+    b["pos"][1:, 2] = rs.uniform(-60, 60, n)
+    b["center"] = b["pos"]
+    want = b.copy()
+    oracle.step(want, oracle.default_params(), 4)
+    got, contacts, st = gpu_run(tr, b, 4)
+    check_state(got, want, "static hub")
+    assert np.array_equal(contacts, oracle.contacts(want)) and (contacts[:, 0] == 0).sum() > n // 2
+    assert st.last_response_rounds < 2000, "no chain through the static slab"
+
+
+# ---------------------------------------------------------------- contact buffers grow on demand
+def test_contact_buffers_grow_and_the_step_is_completed(tr, oracle):
+    """32,768 packed spheres make ~100K contacts, more than the initial N + 32768 slots: the step that
+    finds them skips its response on the device, the later steps of the same asynchronous batch become
+    no-ops, and the next synchronisation grows the buffers and re-runs them - same bits as the oracle."""
+    b = scenes.dense_lattice(32)
+    want = b.copy()
+    first = None
+    for _ in range(3):
+        oracle.step(want, oracle.default_params(flags=0, g=(0, 0, 0)), 1)
+        c = oracle.contacts(want)
+        oracle.resolve_list(want, c)
+        first = len(c) if first is None else first
+    assert first > 32768 + 32768, "the first step must not fit the initial buffers"
+    with tr.World(tr.default_params(g=(0, 0, 0))) as w:
+        w.add(b)
+        for _ in range(3):
+            w.step(1, sync=False)             # three steps in flight, the first one overflows
+        got = w.read_bodies()
+        assert np.array_equal(w.contacts(), c)
+        assert w.stats().steps == 3
+    check_state(got, want, "after overflow recovery")
+
+
+@pytest.mark.parametrize("n_side,steps", [(64, 200), (101, 20)])
+def test_response_modes_soak(tr, n_side, steps):
+    """Soak of the version-stamped hand-off: a packed lattice (262,144 bodies x 200 steps; 1,030,301 x 20) stepped
+    by the dataflow executors (single-lane and whole-warp workers) and by the level-synchronous executor, whose
+    only synchronisation is a grid barrier per wavefront - the in-GPU arbiter where the CPU oracle is too slow.
+    Every position and velocity must be bit-identical after every 10th step and at the end."""
+    b = scenes.dense_lattice(n_side)
+    worlds = [tr.World(tr.default_params(g=(0, 0, 0), response_mode=m)) for m in (1, 3, 2, 0)]
+    try:
+        for w in worlds:
+            w.add(b)
+        for s0 in range(0, steps, 10):
+            for w in worlds:
+                w.step(10, sync=False)
+            ref_pos, ref_vel = worlds[0].read_state()
+            for m, w in zip((3, 2, 0), worlds[1:]):
+                pos, vel = w.read_state()
+                assert_bits_equal(pos, ref_pos, f"step {s0 + 10}: mode {m} pos vs level-synchronous")
+                assert_bits_equal(vel, ref_vel, f"step {s0 + 10}: mode {m} vel vs level-synchronous")
+        assert worlds[0].stats().last_contacts > 0
+    finally:
+        for w in worlds:
+            w.close()

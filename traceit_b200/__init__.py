@@ -27,6 +27,7 @@ ROOT = os.path.dirname(HERE)
 
 PAIR_GRAVITY = 1
 COLLISIONS = 2
+DEBUG_NO_TINY = 1
 
 ERRORS = {
     0: "TR_OK", 1: "TR_ERR_INVALID_ARG", 2: "TR_ERR_NO_DEVICE", 3: "TR_ERR_CUDA", 4: "TR_ERR_NCCL",
@@ -53,7 +54,7 @@ class Params(C.Structure):
         ("g", C.c_float * 3), ("G", C.c_float), ("dt", C.c_float), ("atm_density", C.c_float),
         ("flags", C.c_uint32), ("grid_origin", C.c_float * 3), ("grid_cell", C.c_float),
         ("grid_bits", C.c_int32), ("max_contacts", C.c_uint64), ("grid_max_radius", C.c_float),
-        ("response_mode", C.c_uint32), ("reserved", C.c_uint32 * 2),
+        ("response_mode", C.c_uint32), ("debug_flags", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 

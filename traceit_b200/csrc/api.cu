@@ -74,6 +74,13 @@ void timers_collect(tr_world* w) {
     w->pending.clear();
 }
 
+// Host code that is about to read or change the world's state first lets every enqueued step finish (and be made
+// good, see settle() below).  A no-op when nothing is in flight.
+static int settle_if_pending(tr_world* w) {
+    if (!w->pending_steps.empty() || w->coll_seq != w->ring_consumed) return settle(w);
+    return TR_OK;
+}
+
 // ---- AoS <-> SoA ------------------------------------------------------------------------
 struct SoA {
     float4* pos_m;
@@ -183,9 +190,9 @@ __global__ void __launch_bounds__(256) frame_pack_kernel(const float4* __restric
 // sharded collisions: collider centres of bodies integrated by OTHER ranks
 __global__ void __launch_bounds__(256) refresh_remote_centers(const float4* __restrict__ pos_m, float4* center_r,
                                                               const uint8_t* __restrict__ flags, uint32_t n,
-                                                              uint32_t own_first, uint32_t own_count) {
+                                                              uint32_t own_first, uint32_t own_count, const uint32_t* ctl) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || (i >= own_first && i < own_first + own_count)) return;
+    if (i >= n || (i >= own_first && i < own_first + own_count) || ctl[CTL_ABORT] != 0) return;
     if (flags[i] & F_STATIONARY) return;
     float4 p = pos_m[i];
     float4 c = center_r[i];
@@ -196,9 +203,9 @@ __global__ void __launch_bounds__(256) refresh_remote_centers(const float4* __re
 // post-integration position is the refreshed collider centre
 __global__ void __launch_bounds__(256) traj_record_kernel(const float4* __restrict__ center_r, const uint8_t* __restrict__ flags,
                                                           uint32_t first, uint32_t count, float* traj, uint32_t* traj_cnt,
-                                                          uint32_t max_points, uint64_t stride) {
+                                                          uint32_t max_points, uint64_t stride, const uint32_t* ctl) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
+    if (t >= count || ctl[CTL_ABORT] != 0) return;
     const uint32_t i = first + t;
     if (flags[i] & F_STATIONARY) return;
     const float4 c = center_r[i];
@@ -239,7 +246,7 @@ static int record_trajectory(tr_world* w) {
     TR_TRY(ensure_traj(w));
     unsigned blocks = (unsigned)((w->own_count + 255) / 256);
     traj_record_kernel<<<blocks, 256, 0, w->stream>>>(w->center_r, w->flags, (uint32_t)w->own_first, (uint32_t)w->own_count,
-                                                      w->traj, w->traj_cnt, w->traj_max, w->traj_stride);
+                                                      w->traj, w->traj_cnt, w->traj_max, w->traj_stride, w->d_ctl);
     TR_CUDA(cudaGetLastError());
     w->stats.kernel_launches += 1;
     return TR_OK;
@@ -364,6 +371,7 @@ static int upload_range(tr_world* w, uint64_t first, uint64_t count, const tr_bo
                         unsigned long long* sig_out = nullptr) {
     if (sig_out) *sig_out = 0;
     if (count == 0) return TR_OK;
+    TR_TRY(settle_if_pending(w));
     if (sig_out && !w->d_sig) TR_CUDA(cudaMalloc(&w->d_sig, sizeof(unsigned long long)));
     if (sig_out) TR_CUDA(cudaMemsetAsync(w->d_sig, 0, sizeof(unsigned long long), w->stream));
     TR_TRY(ensure_capacity(w, first + count));
@@ -385,6 +393,7 @@ static int upload_range(tr_world* w, uint64_t first, uint64_t count, const tr_bo
 
 static int flush_created(tr_world* w) {
     if (!w->dirty_upload) return TR_OK;
+    TR_TRY(settle_if_pending(w));
     uint64_t total = w->host_bodies.size();
     if (total > w->n) {
         if (w->nranks > 1 && w->n > 0 && w->ever_stepped) {
@@ -407,6 +416,7 @@ static int flush_created(tr_world* w) {
 
 static int download_range(tr_world* w, uint64_t first, uint64_t count, tr_body_desc* host) {
     if (count == 0) return TR_OK;
+    TR_TRY(settle_if_pending(w));
     TR_TRY(ensure_staging(w, count));
     unsigned blocks = (unsigned)((count + 255) / 256);
     pack_kernel<<<blocks, 256, 0, w->stream>>>(w->aos, (uint32_t)first, (uint32_t)count, soa_of(w));
@@ -488,9 +498,20 @@ static int create_common(const tr_world_params* p, int device, int rank, int nra
     w->rank = rank;
     w->nranks = nranks;
     cudaError_t se = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+    // device-side step bookkeeping: control words in device memory, the step records in mapped pinned host memory
+    if (se == cudaSuccess) se = cudaMalloc(&w->d_ctl, CTL_WORDS * sizeof(uint32_t));
+    if (se == cudaSuccess) se = cudaMemset(w->d_ctl, 0, CTL_WORDS * sizeof(uint32_t));
+    if (se == cudaSuccess) se = cudaHostAlloc(&w->h_ring, STEP_RING * sizeof(StepRecord), cudaHostAllocMapped);
+    if (se == cudaSuccess) {
+        memset(w->h_ring, 0, STEP_RING * sizeof(StepRecord));
+        se = cudaHostGetDevicePointer((void**)&w->d_ring, w->h_ring, 0);
+    }
     if (se != cudaSuccess) {
+        if (w->stream) cudaStreamDestroy(w->stream);
+        cudaFree(w->d_ctl);
+        if (w->h_ring) cudaFreeHost(w->h_ring);
         delete w;
-        return cuda_fail(se, "cudaStreamCreate", __FILE__, __LINE__);
+        return cuda_fail(se, "world creation (stream / control block)", __FILE__, __LINE__);
     }
     *out = w;
     return TR_OK;
@@ -507,6 +528,7 @@ static StepConsts consts_of(const tr_world* w) {
     return c;
 }
 
+// One step, enqueued.  Nothing here waits for the GPU.
 static int step_once(tr_world* w) {
     const StepConsts c = consts_of(w);
     const bool grav = (w->params.flags & TR_PAIR_GRAVITY) != 0;
@@ -531,14 +553,77 @@ static int step_once(tr_world* w) {
         TR_TRY(nccl_allgather_pos(w, w->vel_rest));
         unsigned blocks = (unsigned)((w->n + 255) / 256);
         refresh_remote_centers<<<blocks, 256, 0, w->stream>>>(w->pos_m[w->cur], w->center_r, w->flags, (uint32_t)w->n,
-                                                              (uint32_t)w->own_first, (uint32_t)w->own_count);
+                                                              (uint32_t)w->own_first, (uint32_t)w->own_count, w->d_ctl);
         TR_CUDA(cudaGetLastError());
         w->stats.kernel_launches += 1;
     }
-    if (coll) TR_TRY(collide_step(w));
+    tr_world::PendingStep ps{~0u, 0};
+    if (coll) {
+        ps.coll_seq = w->coll_seq;
+        TR_TRY(collide_step(w));
+    }
+    ps.cur_after = w->cur;
+    w->pending_steps.push_back(ps);
     w->stats.steps += 1;
     w->ever_stepped = true;
     return TR_OK;
+}
+
+// nsteps steps, enqueued: small worlds in one launch (tiny.cuh), everything else step by step
+static int enqueue_steps(tr_world* w, int nsteps) {
+    if (w->n == 0 || nsteps <= 0) return TR_OK;
+    if (w->traj_max) TR_TRY(ensure_traj(w));
+    bool taken = false;
+    TR_TRY(tiny_steps(w, consts_of(w), nsteps, &taken));
+    if (taken) {
+        w->stats.steps += (uint64_t)nsteps;
+        w->ever_stepped = true;
+        return TR_OK;
+    }
+    for (int s = 0; s < nsteps; ++s) TR_TRY(step_once(w));
+    return TR_OK;
+}
+
+// Wait for everything enqueued, fold the device's step records into the statistics, and - should a step
+// have found more contacts than its buffers hold - make that good: on the device that step's response was
+// skipped and every later kernel did nothing (d_ctl[CTL_ABORT]), so the state is exactly what the step's
+// integration left; detection depends only on collider centres, which the response never writes
+// (main.cpp:655-659 vs 725-741).  Grow the buffers, re-run detection + response of that step, re-run the
+// steps behind it.
+int settle(tr_world* w) {
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        TR_CUDA(cudaStreamSynchronize(w->stream));
+        timers_collect(w);
+        bool overflow = false;
+        uint32_t seq = 0;
+        uint64_t found = 0;
+        TR_TRY(collide_consume_records(w, &overflow, &seq, &found));
+        if (!overflow) {
+            w->pending_steps.clear();
+            TR_TRY(collide_headroom(w));
+            return TR_OK;
+        }
+        // which of the steps enqueued since the last synchronisation was it?
+        size_t k = 0;
+        while (k < w->pending_steps.size() && w->pending_steps[k].coll_seq != seq) ++k;
+        const std::vector<tr_world::PendingStep> pending = w->pending_steps;
+        w->pending_steps.clear();
+        int rc = collide_grow_contacts(w, found);
+        TR_CUDA(cudaMemsetAsync(w->d_ctl + CTL_ABORT, 0, sizeof(uint32_t), w->stream));
+        if (k == pending.size()) {
+            set_error("internal: overflowed step %u is not among the %zu pending steps", seq, pending.size());
+            return TR_ERR_STATE;
+        }
+        const size_t behind = pending.size() - 1 - k;
+        w->cur = pending[k].cur_after;
+        w->stats.steps -= behind;
+        if (rc != TR_OK) return rc;      // max_contacts is the caller's hard cap: the world stands after that step's integration
+        TR_TRY(collide_step(w));          // detection + response of the step that overflowed
+        w->pending_steps.push_back(tr_world::PendingStep{w->coll_seq - 1, w->cur});
+        for (size_t s = 0; s < behind; ++s) TR_TRY(step_once(w));
+    }
+    set_error("contact buffers still too small after 8 attempts");
+    return TR_ERR_CAPACITY;
 }
 
 }  // namespace tr
@@ -622,6 +707,8 @@ int tr_world_destroy(tr_world* w) {
     cudaFree(w->d_sig);
     cudaFree(w->traj);
     cudaFree(w->traj_cnt);
+    cudaFree(w->d_ctl);
+    if (w->h_ring) cudaFreeHost(w->h_ring);
     if (w->own_stream && w->stream) cudaStreamDestroy(w->stream);
     delete w;
     return TR_OK;
@@ -630,6 +717,7 @@ int tr_world_destroy(tr_world* w) {
 int tr_world_set_params(tr_world* w, const tr_world_params* p) {
     TR_TRY(check_world(w));
     TR_TRY(validate_params(p));
+    TR_TRY(settle_if_pending(w));   // steps already enqueued run (and, after an overflow, re-run) with the old parameters
     bool grid_changed = p->grid_cell != w->params.grid_cell || p->grid_bits != w->params.grid_bits ||
                         p->grid_max_radius != w->params.grid_max_radius ||
                         memcmp(p->grid_origin, w->params.grid_origin, sizeof(p->grid_origin)) != 0;
@@ -646,8 +734,7 @@ int tr_world_get_params(tr_world* w, tr_world_params* p) {
 
 int tr_world_set_stream(tr_world* w, void* cuda_stream) {
     TR_TRY(check_world(w));
-    TR_CUDA(cudaStreamSynchronize(w->stream));
-    timers_collect(w);
+    TR_TRY(settle(w));
     if (w->own_stream && w->stream) cudaStreamDestroy(w->stream);
     // the handle is used as given; NULL is CUDA's legacy default stream
     w->stream = (cudaStream_t)cuda_stream;
@@ -713,16 +800,12 @@ int tr_step(tr_world* w, int nsteps) {
         return TR_ERR_INVALID_ARG;
     }
     TR_TRY(flush_created(w));
-    if (w->n == 0) return TR_OK;
-    for (int s = 0; s < nsteps; ++s) TR_TRY(step_once(w));
-    return TR_OK;
+    return enqueue_steps(w, nsteps);
 }
 
 int tr_sync(tr_world* w) {
     TR_TRY(check_world(w));
-    TR_CUDA(cudaStreamSynchronize(w->stream));
-    timers_collect(w);
-    collide_poll_stats(w);
+    TR_TRY(settle(w));
     if (w->deferred_error != TR_OK) {
         int rc = w->deferred_error;
         set_error("%s", w->deferred_msg.c_str());
@@ -812,6 +895,7 @@ int tr_step_frame(tr_world* w, uint64_t n, const float* force_xyz, tr_frame_body
     }
     TR_TRY(tr_step(w, nsteps));
     if (out) {
+        TR_TRY(settle_if_pending(w));
         const size_t bytes = (size_t)n * sizeof(tr_frame_body);
         note_host_buffer(w, 1, out, bytes);
         const uint64_t words = n * 9;
@@ -841,6 +925,7 @@ int tr_read_state(tr_world* w, uint64_t first, uint64_t count, float* pos_xyz, f
         return TR_ERR_INVALID_ARG;
     }
     if (count == 0) return TR_OK;
+    TR_TRY(settle_if_pending(w));
     float* d = nullptr;
     size_t bytes = (size_t)count * 3 * sizeof(float);
     TR_CUDA(cudaMalloc(&d, bytes * (vel_xyz ? 2 : 1)));
@@ -891,6 +976,7 @@ int tr_set_force(tr_world* w, uint32_t id, float fx, float fy, float fz) {
         set_error("tr_set_force: id %u out of range", id);
         return TR_ERR_INVALID_ARG;
     }
+    TR_TRY(settle_if_pending(w));
     float4 f = make_float4(fx, fy, fz, 0.f);
     TR_CUDA(cudaMemcpyAsync(w->force + id, &f, sizeof(f), cudaMemcpyHostToDevice, w->stream));
     TR_CUDA(cudaStreamSynchronize(w->stream));
@@ -899,7 +985,7 @@ int tr_set_force(tr_world* w, uint32_t id, float fx, float fy, float fz) {
 
 int tr_world_enable_trajectory(tr_world* w, uint32_t max_points) {
     TR_TRY(check_world(w));
-    TR_CUDA(cudaStreamSynchronize(w->stream));
+    TR_TRY(settle(w));
     if (max_points != w->traj_max) {
         cudaFree(w->traj);
         cudaFree(w->traj_cnt);
@@ -924,6 +1010,7 @@ int tr_read_trajectory(tr_world* w, uint32_t id, float* xyz, uint64_t cap_points
     }
     if (n_points) *n_points = 0;
     if (!w->traj) return TR_OK;   // enabled but no step recorded yet
+    TR_TRY(settle_if_pending(w));
     uint32_t cnt = 0;
     TR_CUDA(cudaMemcpyAsync(&cnt, w->traj_cnt + id, sizeof(cnt), cudaMemcpyDeviceToHost, w->stream));
     TR_CUDA(cudaStreamSynchronize(w->stream));
@@ -948,6 +1035,7 @@ int tr_read_trajectory(tr_world* w, uint32_t id, float* xyz, uint64_t cap_points
 
 int tr_read_contacts(tr_world* w, int32_t* pairs_ij, uint64_t cap, uint64_t* n) {
     TR_TRY(check_world(w));
+    TR_TRY(settle_if_pending(w));
     return collide_read_contacts(w, pairs_ij, cap, n);
 }
 
@@ -955,12 +1043,14 @@ int tr_debug_grid(tr_world* w, uint32_t* keys, uint32_t* sorted_ids, uint64_t* m
                   int32_t* bits) {
     TR_TRY(check_world(w));
     TR_TRY(flush_created(w));
+    TR_TRY(settle_if_pending(w));
     return collide_debug_grid(w, keys, sorted_ids, m, cell, inv_cell, bits);
 }
 
 int tr_debug_candidates(tr_world* w, int32_t* pairs_ij, uint64_t cap, uint64_t* n) {
     TR_TRY(check_world(w));
     TR_TRY(flush_created(w));
+    TR_TRY(settle_if_pending(w));
     return collide_debug_candidates(w, pairs_ij, cap, n);
 }
 
@@ -969,6 +1059,7 @@ int tr_debug_gravity(tr_world* w, float* force_xyz) {
     TR_TRY(flush_created(w));
     if (!force_xyz) return TR_ERR_INVALID_ARG;
     if (w->own_count == 0) return TR_OK;
+    TR_TRY(settle_if_pending(w));
     float4* d = nullptr;
     TR_CUDA(cudaMalloc(&d, w->own_count * sizeof(float4)));
     int rc = gravity_step(w, consts_of(w), false, d);
@@ -993,18 +1084,14 @@ int tr_get_stats(tr_world* w, tr_stats* s) {
     if (!w || !s) return TR_ERR_INVALID_ARG;
     // only completed work is folded in; call tr_sync first for exact numbers
     cudaSetDevice(w->device);
-    if (cudaStreamQuery(w->stream) == cudaSuccess) {
-        timers_collect(w);
-        collide_poll_stats(w);
-    }
+    if (cudaStreamQuery(w->stream) == cudaSuccess) settle(w);
     *s = w->stats;
     return TR_OK;
 }
 
 int tr_reset_stats(tr_world* w) {
     TR_TRY(check_world(w));
-    TR_CUDA(cudaStreamSynchronize(w->stream));
-    timers_collect(w);
+    TR_TRY(settle(w));
     uint32_t side = w->stats.side_list_size;
     w->stats = tr_stats{};
     w->stats.side_list_size = side;
@@ -1013,8 +1100,7 @@ int tr_reset_stats(tr_world* w) {
 
 int tr_enable_timing(tr_world* w, int on) {
     TR_TRY(check_world(w));
-    TR_CUDA(cudaStreamSynchronize(w->stream));
-    timers_collect(w);
+    TR_TRY(settle(w));
     w->timing = on != 0;
     return TR_OK;
 }

@@ -4,7 +4,7 @@
 // i<j sweep with checkSphereCollision / checkAABBCollision (src/main.cpp:648-660) and a
 // Gauss-Seidel impulse + positional nudge (src/main.cpp:709-742).
 //
-// Broad phase = ONE-DIGIT radix sort of the wrapped cell keys (radix = number of cells):
+// One collision step = ONE CUDA graph, no host round trip anywhere in it (collide_step below):
 //   K2  keys_kernel          one thread per body: cell key from the collider centre, per-cell
 //                            histogram by atomics; bodies that cannot live in the grid (oversize,
 //                            out-of-domain, non-finite) go to the side / far lists; mass<=0
@@ -12,27 +12,29 @@
 //   K3a tile_sums + scan     exclusive scan of the histogram in two unchained kernels
 //                            -> dense cell_start[ncell+1] table.
 //   K3b scatter_kernel       one 32-byte record per body (centre+radius, id|flags, half extents)
-//                            into its cell's segment: the bodies in cell order.  Inside a cell
-//                            the records are in arrival order; nothing downstream depends on it
-//                            (pairs are reported as (min id, max id) and re-sorted for K6).
-//   K4  canon_kernel         ON DEMAND (tr_debug_grid): the stable (key,id) order - rank of each id
-//                            inside its cell - as the list of sorted ids.
-//   K5  narrow_kernel        half of the 27-cell stencil (each pair reached once) as 5 contiguous
-//                            key ranges, exact reference predicate (no FMA contraction).
-//   K5b side_kernel          every side-list body (oversize / non-finite extent) against every live body.
-//   K5c far_kernel           bodies outside the grid domain against each other and against the
-//                            grid bodies next to the domain boundary.
-//   K6  ordered response     contacts counting-sorted into (i,j) and (j,i) order give each contact
-//                            its two predecessors / successors; the executor replays the
-//                            reference's Gauss-Seidel order exactly: a contact runs when
-//                            the previous contact of BOTH its bodies has run, so results
-//                            are bit-identical to the sequential sweep.
+//                            into its cell's segment: the bodies in cell order (a ONE-DIGIT radix
+//                            sort of the wrapped cell keys, radix = number of cells).
+//   K4  canon_kernel         ON DEMAND (tr_debug_grid): the stable (key,id) order.
+//   K5  narrow_kernel        half of the 27-cell stencil (each pair reached once); the (body, candidate)
+//                            pairs of 32 consecutive slots are flattened into a per-warp list so that every
+//                            lane tests a pair every iteration; exact reference predicate.  The trailing
+//                            CTAs of the same launch are the side-list / far-list workers (K5b / K5c).
+//   K6  prep_kernel          half-edge sort of the contact list by (body, partner): each contact's
+//                            predecessors / successors in the reference's Gauss-Seidel order.
+//       response_flow_kernel the ordered replay: a contact runs when the previous contact of BOTH its
+//                            bodies has run, so results are bit-identical to the sequential sweep.
+//       epilogue_kernel      the step's record for the host (mapped pinned ring), counters re-armed.
+// Worlds of up to TINY_MAX bodies skip all of that: tiny_step_kernel (tiny.cuh) runs whole steps in one CTA.
 //
 // The contact SET is a pure function of collider centres/radii (the sweep never writes
-// them: main.cpp:655-659 vs 725-741), which is what makes detection parallel and K6 legal.
+// them: main.cpp:655-659 vs 725-741), which is what makes detection parallel and K6 legal -
+// and what makes a contact-buffer overflow recoverable: the response of that step is skipped on the
+// device, every later kernel becomes a no-op (tr_world::d_ctl), and the host re-runs detection +
+// response with larger buffers at its next synchronisation (api.cu settle()).
 #include "collide_common.cuh"
 #include "collide_broad.cuh"
 #include "collide_response.cuh"
+#include "tiny.cuh"
 
 namespace tr {
 
@@ -98,20 +100,11 @@ int collide_classify(tr_world* w) {
         }
     }
     c->rmax_grid = rmax;
-    // can any body be outside the grid for a reason known at creation time?
-    c->may_have_side = false;
-    for (const tr_body_desc& b : w->host_bodies) {
-        if (b.mass <= 0) continue;
-        if ((!mixed && !b.isSphere) || !(body_extent(b, mixed) <= rmax)) {
-            c->may_have_side = true;
-            break;
-        }
-    }
-    float cell = p.grid_cell;
-    if (cell <= 0.f) {
-        cell = (2.0f * rmax) * 1.0078125f;   // 2*rmax*(1+2^-7): margin analysed in DESIGN.md
-        if (!(cell > 0.f) || !std::isfinite(cell)) cell = 1.0f;
-    }
+    // 2*rmax*(1+2^-7) is the SMALLEST conservative cell (margin analysed in DESIGN.md): with a smaller one the
+    // 27-cell stencil would silently miss contacts, so a smaller request is raised to it
+    float cell = (2.0f * rmax) * 1.0078125f;
+    if (p.grid_cell > cell) cell = p.grid_cell;
+    if (!(cell > 0.f) || !std::isfinite(cell)) cell = 1.0f;
     c->cell = cell;
     c->inv_cell = 1.0f / cell;
     memcpy(c->origin, p.grid_origin, sizeof(c->origin));
@@ -131,6 +124,37 @@ int collide_classify(tr_world* w) {
     return TR_OK;
 }
 
+static uint64_t default_contact_capacity(uint64_t n) {
+    // grown on demand (overflow recovery, api.cu settle()): start near one contact per body
+    return n + 32768;
+}
+
+static int free_contact_buffers(Collide* c) {
+    cudaFree(c->ckeys); cudaFree(c->arank); cudaFree(c->he); cudaFree(c->dep); cudaFree(c->crec); cudaFree(c->cver);
+    cudaFree(c->cgeo); cudaFree(c->frontier[0]); cudaFree(c->frontier[1]);
+    c->ckeys = nullptr; c->arank = nullptr; c->he = nullptr; c->dep = nullptr; c->crec = nullptr; c->cver = nullptr;
+    c->cgeo = nullptr; c->frontier[0] = c->frontier[1] = nullptr;
+    c->cap_contacts = 0;
+    return TR_OK;
+}
+
+static int alloc_contact_buffers(tr_world* w, uint64_t want_c) {
+    Collide* c = state(w);
+    if (want_c > 0xFFFFFFF0ull) want_c = 0xFFFFFFF0ull;
+    free_contact_buffers(c);
+    TR_TRY(realloc_dev(&c->ckeys, want_c));
+    TR_TRY(realloc_dev(&c->arank, want_c));
+    TR_TRY(realloc_dev(&c->he, 2 * want_c));
+    TR_TRY(realloc_dev(&c->dep, want_c));
+    TR_TRY(realloc_dev(&c->crec, want_c));
+    TR_TRY(realloc_dev(&c->cver, want_c));
+    TR_TRY(realloc_dev((ContactGeo**)&c->cgeo, want_c));
+    TR_TRY(realloc_dev(&c->frontier[0], want_c));
+    if (w->params.response_mode == 1) TR_TRY(realloc_dev(&c->frontier[1], want_c));
+    c->cap_contacts = want_c;
+    return TR_OK;
+}
+
 static int ensure_buffers(tr_world* w) {
     Collide* c = state(w);
     const uint64_t n = w->n;
@@ -146,8 +170,8 @@ static int ensure_buffers(tr_world* w) {
         TR_TRY(realloc_dev(&c->far_c, cap));
         TR_TRY(realloc_dev(&c->bnd_c, cap));
         TR_TRY(realloc_dev(&c->klass, cap));
-        TR_TRY(realloc_dev(&c->row_start, cap + 1));
-        TR_TRY(realloc_dev(&c->col_start, cap + 1));
+        TR_TRY(realloc_dev(&c->seg, cap));
+        TR_TRY(realloc_dev(&c->long_list, cap));
         TR_TRY(realloc_dev(&c->body_cnt, cap));
         TR_CUDA(cudaMemsetAsync(c->body_cnt, 0, cap * sizeof(uint32_t), w->stream));
         c->cap_bodies = cap;
@@ -161,329 +185,321 @@ static int ensure_buffers(tr_world* w) {
         c->ncell_alloc = ncell;
     }
     {
-        const uint64_t longest = ncell > c->cap_bodies + 1 ? ncell : c->cap_bodies + 1;
-        const uint64_t tiles = (longest + SCAN_TILE - 1) / SCAN_TILE;
+        const uint64_t tiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
         if (tiles > c->tile_sum_cap) {
             TR_TRY(realloc_dev(&c->tile_sum, tiles));
             c->tile_sum_cap = tiles;
         }
     }
-    uint64_t want_c = w->params.max_contacts ? w->params.max_contacts : 8 * n + 4096;
-    if (want_c > 0xFFFFFFF0ull) want_c = 0xFFFFFFF0ull;
-    if (want_c != c->cap_contacts) {
-        TR_TRY(realloc_dev(&c->ckeys, want_c));
-        TR_TRY(realloc_dev(&c->ckeys_alt, want_c));
-        TR_TRY(realloc_dev(&c->colkeys, want_c));
-        TR_TRY(realloc_dev(&c->colc, want_c));
-        TR_TRY(realloc_dev(&c->col_pos, want_c));
-        TR_TRY(realloc_dev(&c->dep, want_c));
-        TR_TRY(realloc_dev(&c->succ_i, want_c));
-        TR_TRY(realloc_dev(&c->succ_j, want_c));
-        TR_TRY(realloc_dev(&c->crec, want_c));
-        TR_TRY(realloc_dev(&c->cver, want_c));
-        TR_TRY(realloc_dev((ContactGeo**)&c->cgeo, want_c));
-        TR_TRY(realloc_dev(&c->frontier[0], want_c));
-        TR_TRY(realloc_dev(&c->frontier[1], want_c));
-        c->cap_contacts = want_c;
+    // Contact buffers (~100 bytes per slot) are sized on demand: the caller's max_contacts is a hard cap,
+    // otherwise they start near one contact per body and grow when a step needs more (overflow recovery).
+    c->cap_fixed = w->params.max_contacts != 0;
+    uint64_t want_c = c->cap_contacts;
+    if (c->cap_fixed) {
+        want_c = w->params.max_contacts;
+        if (n <= (uint64_t)TINY_MAX && want_c < 32768) want_c = 32768;   // a tiny world's list is never capped (N(N-1)/2 <= 32640 pairs)
+    } else if (want_c < default_contact_capacity(n)) {
+        want_c = default_contact_capacity(n);
     }
+    const bool need_f1 = w->params.response_mode == 1 && !c->frontier[1];
+    if (want_c != c->cap_contacts || need_f1) TR_TRY(alloc_contact_buffers(w, want_c));
     if (!c->counters) {
         TR_CUDA(cudaMalloc(&c->counters, (C_NCOUNTERS + 32) * sizeof(uint32_t)));   // + statistics of TR_FLOW_STATS builds
         TR_CUDA(cudaMemset(c->counters, 0, (C_NCOUNTERS + 32) * sizeof(uint32_t)));
-        TR_CUDA(cudaMallocHost(&c->h_counters, C_NHOST * sizeof(uint32_t)));
-        TR_CUDA(cudaMallocHost(&c->h_rounds, 8 * sizeof(uint32_t)));
-        memset(c->h_rounds, 0, 8 * sizeof(uint32_t));
     }
     return TR_OK;
 }
 
-// K2-K3b.  `ev` (debug, TR_BP_PROFILE=1): 5 events recorded around the four kernels.
-static int launch_broad(tr_world* w, cudaStream_t st, cudaEvent_t* ev = nullptr) {
+// Grow the contact buffers after a step found `found` contacts (overflow recovery / head-room policy).
+int collide_grow_contacts(tr_world* w, uint64_t found) {
+    Collide* c = state(w);
+    if (c->cap_fixed) {
+        set_error("contact buffer overflow: %llu contacts, capacity %llu (raise tr_world_params.max_contacts, or leave it 0 to let the library grow the buffers)",
+                  (unsigned long long)found, (unsigned long long)c->cap_contacts);
+        return TR_ERR_CAPACITY;
+    }
+    uint64_t want = found + found / 2 + 32768;
+    if (want <= c->cap_contacts) return TR_OK;
+    return alloc_contact_buffers(w, want);
+}
+
+// K2-K3b on the stream (used inside the step's graph capture and by the debug entry points).
+static int launch_broad(tr_world* w, cudaStream_t st) {
     Collide* c = state(w);
     const uint32_t n = (uint32_t)w->n;
     const uint32_t blocks = (n + 255) / 256;
     const uint32_t ncell = 1u << (c->bx + c->by + c->bz);
     const uint32_t ntiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
     const GridParams g = grid_params(c);
-    TR_CUDA(cudaMemsetAsync(c->counters, 0, C_NCOUNTERS * sizeof(uint32_t), st));
-    if (ev) cudaEventRecord(ev[0], st);
     keys_kernel<<<blocks, 256, 0, st>>>(w->center_r, w->half_ext, w->flags, n, g, c->keys, c->klass, c->side_list, c->far_list, c->far_c,
                                         c->bnd_list, c->bnd_c, c->cell_count, c->counters);
-    if (ev) cudaEventRecord(ev[1], st);
     tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, ncell, c->tile_sum);
-    if (ev) cudaEventRecord(ev[2], st);
     scan_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, c->tile_sum, c->cell_start, ncell, c->counters, C_GRID);
-    if (ev) cudaEventRecord(ev[3], st);
     scatter_kernel<<<blocks, 256, 0, st>>>(c->keys, ncell, w->flags, w->center_r, c->mixed ? w->half_ext : nullptr, n, c->cell_start,
                                            c->cell_count, (SlotRec*)c->recs);
-    if (ev) cudaEventRecord(ev[4], st);
     TR_CUDA(cudaGetLastError());
     return TR_OK;
 }
 
-// Broad phase K2-K3b.  Leaves counters[C_SIDE] / [C_FAR] / [C_BND] / [C_GRID] on the device; no host sync.
-static int broad_phase(tr_world* w) {
-    Collide* c = state(w);
-    const uint32_t n = (uint32_t)w->n;
-    PendingTimer t;
-    static const bool bp_profile = getenv("TR_BP_PROFILE") != nullptr;
-    if (bp_profile) {
-        // debug: plain launches with an event between the kernels, per-kernel times to stderr
-        // (event gaps include the launch gap a graph does not have: ~2 us per kernel)
-        cudaEvent_t ev[5];
-        for (auto& e : ev) TR_CUDA(cudaEventCreate(&e));
-        timer_begin(w, T_BROAD, &t);
-        TR_TRY(launch_broad(w, w->stream, ev));
-        timer_end(w, &t);
-        TR_CUDA(cudaEventSynchronize(ev[4]));
-        float ms[4];
-        for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
-        fprintf(stderr, "[TR_BP_PROFILE] n=%u keys %.1f us, tile sums %.1f us, scan %.1f us, scatter %.1f us\n", n, ms[0] * 1e3f,
-                ms[1] * 1e3f, ms[2] * 1e3f, ms[3] * 1e3f);
-        for (auto& e : ev) cudaEventDestroy(e);
-    } else if (w->stream == nullptr) {
-        // the legacy default stream cannot be captured: plain launches
-        timer_begin(w, T_BROAD, &t);
-        TR_TRY(launch_broad(w, w->stream));
-        timer_end(w, &t);
-    } else {
-        // signature of everything the captured launches depend on
-        uint64_t sig[8] = {(uint64_t)(uintptr_t)w->center_r, (uint64_t)(uintptr_t)w->flags, (uint64_t)(uintptr_t)c->keys,
-                           (uint64_t)(uintptr_t)c->cell_count, (uint64_t)(uintptr_t)c->ckeys ^ (uint64_t)(uintptr_t)c->recs,
-                           ((uint64_t)n << 16) | ((uint64_t)(c->mixed ? 1 : 0) << 15) | (uint64_t)(c->bx | (c->by << 5) | (c->bz << 10)), 0, 0};
-        memcpy(&sig[6], &c->inv_cell, 4);
-        memcpy((char*)&sig[6] + 4, &c->rmax_grid, 4);
-        memcpy(&sig[7], &c->origin[0], 8);
-        uint32_t oz = 0;
-        memcpy(&oz, &c->origin[2], 4);
-        sig[7] ^= (uint64_t)oz << 13;
-        if (!c->bp_graph || memcmp(sig, c->bp_sig, sizeof(sig)) != 0) {
-            if (c->bp_graph) cudaGraphExecDestroy(c->bp_graph);
-            c->bp_graph = nullptr;
-            cudaGraph_t graph = nullptr;
-            TR_CUDA(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal));
-            int rc = launch_broad(w, w->stream);
-            cudaError_t e = cudaStreamEndCapture(w->stream, &graph);
-            if (rc != TR_OK) return rc;
-            if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
-            e = cudaGraphInstantiate(&c->bp_graph, graph, 0);
-            cudaGraphDestroy(graph);
-            if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
-            memcpy(c->bp_sig, sig, sizeof(sig));
-        }
-        timer_begin(w, T_BROAD, &t);
-        TR_CUDA(cudaGraphLaunch(c->bp_graph, w->stream));
-        timer_end(w, &t);
-    }
-    w->stats.kernel_launches += 4;
-    TR_CUDA(cudaGetLastError());
-    return TR_OK;
-}
-
-static int read_counters(tr_world* w) {
-    Collide* c = state(w);
-    TR_CUDA(cudaMemcpyAsync(c->h_counters, c->counters, C_NHOST * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
-    TR_CUDA(cudaStreamSynchronize(w->stream));
-    return TR_OK;
-}
-
-static int launch_side(tr_world* w, unsigned long long* out, uint64_t cap, unsigned long long* counter) {
-    Collide* c = state(w);
-    // rows of the launch loop over the side list with stride gridDim.y, so any row count is correct;
-    // last step's side count is the best guess for this one
-    uint32_t rows = c->last_side ? c->last_side : 1;
-    if (rows > 64) rows = 64;
-    dim3 grid((uint32_t)((w->n + 255) / 256), rows);
-    side_kernel<<<grid, 256, 0, w->stream>>>(c->side_list, c->counters, w->center_r, w->half_ext, w->flags, c->klass,
-                                             (uint32_t)w->n, out, cap, counter);
-    TR_CUDA(cudaGetLastError());
-    w->stats.kernel_launches += 1;
-    return TR_OK;
-}
-
-static int launch_far(tr_world* w, unsigned long long* out, uint64_t cap, unsigned long long* counter) {
-    Collide* c = state(w);
-    // sized from the previous step's counts; the kernel strides, so any geometry is correct
-    uint32_t gx = (c->last_far + 255) / 256;
-    if (gx < 1) gx = 1;
-    if (gx > 1024) gx = 1024;
-    uint32_t gy = (c->last_far + c->last_bnd + 255) / 256;
-    if (gy < 1) gy = 1;
-    if (gy > 64) gy = 64;
-    far_kernel<<<dim3(gx, gy), 256, 0, w->stream>>>(c->far_list, c->far_c, c->bnd_list, c->bnd_c, c->counters, w->half_ext, out, cap,
-                                                    counter);
-    TR_CUDA(cudaGetLastError());
-    w->stats.kernel_launches += 1;
-    return TR_OK;
-}
-
-// Detection: broad phase + narrow phase + side list, ONE host read-back at the end.  On return
-// the UNSORTED pairs are in `out` and *count is their number (may exceed cap => overflow).
+// K5 (+ K5b, K5c in the trailing CTAs of the same launch)
 template <bool CANDIDATES>
-static int detect(tr_world* w, unsigned long long* out, uint64_t cap, uint64_t* count) {
+static int launch_narrow(tr_world* w, cudaStream_t st, unsigned long long* out, uint64_t cap) {
     Collide* c = state(w);
-    TR_TRY(broad_phase(w));
     unsigned long long* counter = (unsigned long long*)(c->counters + (CANDIDATES ? C_CAND : C_CONTACTS));
-    PendingTimer t;
-    timer_begin(w, T_NARROW, &t);
-    const uint32_t nb = (uint32_t)((w->n + NARROW_THREADS - 1) / NARROW_THREADS);
+    const uint32_t slot_blocks = (uint32_t)((w->n + NARROW_THREADS - 1) / NARROW_THREADS);
+    const uint32_t outside_blocks = CANDIDATES ? 0u : (uint32_t)w->num_sms * 8u;
     const GridParams g = grid_params(c);
+    OutsideArgs oa{c->side_list, c->far_list, c->far_c, c->bnd_list, c->bnd_c, w->center_r, w->half_ext, w->flags, c->klass, (uint32_t)w->n};
     if (c->mixed)
-        narrow_kernel<CANDIDATES, true><<<nb, NARROW_THREADS, 0, w->stream>>>((const SlotRec*)c->recs, c->cell_start, c->counters, g, out, cap, counter);
+        narrow_kernel<CANDIDATES, true><<<slot_blocks + outside_blocks, NARROW_THREADS, 0, st>>>((const SlotRec*)c->recs, c->cell_start, c->counters,
+                                                                                                g, slot_blocks, oa, out, cap, counter);
     else
-        narrow_kernel<CANDIDATES, false><<<nb, NARROW_THREADS, 0, w->stream>>>((const SlotRec*)c->recs, c->cell_start, c->counters, g, out, cap, counter);
-    w->stats.kernel_launches += 1;
-    const bool side_launched = c->may_have_side && !CANDIDATES;
-    if (side_launched) TR_TRY(launch_side(w, out, cap, counter));
-    const bool far_launched = c->last_far > 0 && !CANDIDATES;
-    if (far_launched) TR_TRY(launch_far(w, out, cap, counter));
-    timer_end(w, &t);
+        narrow_kernel<CANDIDATES, false><<<slot_blocks + outside_blocks, NARROW_THREADS, 0, st>>>((const SlotRec*)c->recs, c->cell_start, c->counters,
+                                                                                                 g, slot_blocks, oa, out, cap, counter);
     TR_CUDA(cudaGetLastError());
-    TR_TRY(read_counters(w));
-    bool again = false;
-    if (!CANDIDATES && !side_launched && c->h_counters[C_SIDE] > 0) {
-        // a body's extent became oversize / non-finite at run time: test it now (rare path, one more read-back)
-        c->may_have_side = true;
-        TR_TRY(launch_side(w, out, cap, counter));
-        again = true;
-    }
-    if (!CANDIDATES && !far_launched && c->h_counters[C_FAR] > 0) {
-        // bodies left the grid domain at run time: first step with a far list
-        c->last_far = c->h_counters[C_FAR];
-        c->last_bnd = c->h_counters[C_BND];
-        TR_TRY(launch_far(w, out, cap, counter));
-        again = true;
-    }
-    if (again) TR_TRY(read_counters(w));
-    c->last_side = c->h_counters[C_SIDE];
-    c->last_far = c->h_counters[C_FAR];
-    c->last_bnd = c->h_counters[C_BND];
-    c->last_grid = c->h_counters[C_GRID];
-    const int k = CANDIDATES ? C_CAND : C_CONTACTS;
-    *count = ((uint64_t)c->h_counters[k + 1] << 32) | c->h_counters[k];
     return TR_OK;
 }
 
-void collide_poll_stats(tr_world* w) {
-    Collide* c = w->col;
-    if (c && c->rounds_pending) {
-        if (c->flow_pending) {
-            w->stats.last_response_rounds = c->h_rounds[0];   // dataflow: lock-step iterations of the longest warp
-            if (c->h_rounds[C_ABORT - C_ROUNDS] != 0 && w->deferred_error == TR_OK) {
-                w->deferred_error = TR_ERR_CUDA;
-                w->deferred_msg = "ordered response: dataflow watchdog fired (dependency graph did not drain)";
-            }
-            c->flow_pending = false;
-        } else {
-            w->stats.last_response_rounds = *c->h_rounds;
-        }
-        c->rounds_pending = false;
-    }
+static bool executor_wide(const tr_world* w, const Collide* c) {
+    // Executor width.  Deep graphs (a packed lattice: ~800 dependent hand-offs) are latency bound: single-lane
+    // workers.  Wide shallow graphs are throughput bound: whole warps.  The last step the host has seen tells
+    // which: contacts per lock-step iteration of its longest worker.
+    if (w->params.response_mode == 2) return true;
+    if (w->params.response_mode == 0 && c->prev_rounds > 0) return c->prev_contacts / c->prev_rounds > 16384;
+    return false;
 }
 
+// K6 + epilogue on the stream.
+static int launch_response(tr_world* w, cudaStream_t st) {
+    Collide* c = state(w);
+    const bool flow = w->params.response_mode != 1;   // 1 selects the level-synchronous kernel
+    if (c->prep_blocks == 0) {
+        int per_sm = 0;
+        TR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prep_kernel, PREP_THREADS, 0));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 4) per_sm = 4;               // every CTA must be resident: prep_kernel synchronises the grid itself
+        c->prep_blocks = w->num_sms * per_sm;
+    }
+    PrepArgs pa{c->ckeys, c->cap_contacts, c->counters, w->d_ctl, c->body_cnt, c->seg, c->arank, c->he, c->long_list, c->dep, c->crec,
+                c->cver, (ContactGeo*)c->cgeo, flow ? (BodyRec*)c->brec : nullptr, c->frontier[0], flow ? C_QTAIL : C_FRONT,
+                w->pos_m[w->cur], w->vel_rest, w->center_r, w->half_ext, w->flags};
+    prep_kernel<<<c->prep_blocks, PREP_THREADS, 0, st>>>(pa);
+    TR_CUDA(cudaGetLastError());
+    if (flow) {
+        FlowArgs ra{w->pos_m[w->cur], w->vel_rest, w->pos_m[w->cur], w->vel_rest, (BodyRec*)c->brec, c->cver, (const ContactGeo*)c->cgeo};
+        if (executor_wide(w, c)) {
+            response_flow_kernel<32><<<w->num_sms, 128, 0, st>>>(ra, c->crec, c->dep, c->frontier[0], w->d_ctl, c->counters, 0u);
+        } else {
+            // 5 CTAs of 4 single-lane warps per SM (3, 4, 6, 7, 8, 9 per SM: 1.59, 1.39, 1.36, 1.38, 1.40, 1.42 ms against 1.34 on
+            // the packed 1M scene: beyond ~3K workers the extra pollers cost more than the extra hands bring);
+            // idle back-off 200 / 500 / 1000 / 1500 ns -> 1.34 / 1.33 / 1.38 / 1.52 ms
+            response_flow_kernel<1><<<w->num_sms * 5, 128, 0, st>>>(ra, c->crec, c->dep, c->frontier[0], w->d_ctl, c->counters, 500u);
+        }
+        TR_CUDA(cudaGetLastError());
+    } else {
+        if (c->coop_blocks == 0) c->coop_blocks = w->num_sms;   // one CTA per SM: the grid barrier cost grows with the CTA count
+        RespArgs ra{w->pos_m[w->cur], w->vel_rest, w->center_r, w->half_ext, w->flags};
+        const uint4* cr = c->crec;
+        uint32_t* dep = c->dep;
+        uint32_t* f0 = c->frontier[0];
+        uint32_t* f1 = c->frontier[1];
+        uint32_t* cnt = c->counters;
+        const uint32_t* ctl = w->d_ctl;
+        void* args[] = {&ra, &cr, &dep, &f0, &f1, &cnt, &ctl};
+        TR_CUDA(cudaLaunchCooperativeKernel((void*)response_kernel, dim3(c->coop_blocks), dim3(256), args, 0, st));
+    }
+    epilogue_kernel<<<1, 128, 0, st>>>(c->counters, w->d_ctl, w->d_ring);
+    TR_CUDA(cudaGetLastError());
+    return TR_OK;
+}
+
+static int launch_step(tr_world* w, cudaStream_t st) {
+    Collide* c = state(w);
+    TR_TRY(launch_broad(w, st));
+    TR_TRY(launch_narrow<false>(w, st, c->ckeys, c->cap_contacts));
+    TR_TRY(launch_response(w, st));
+    return TR_OK;
+}
+
+static uint64_t mix64(uint64_t h, uint64_t v) {
+    h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    return h;
+}
+
+// everything the captured launches depend on
+static uint64_t step_signature(tr_world* w) {
+    Collide* c = state(w);
+    uint64_t h = 0x5452ull;
+    const void* ptrs[] = {w->center_r, w->half_ext, w->flags, w->pos_m[w->cur], w->vel_rest, c->keys, c->recs, c->cell_count, c->cell_start,
+                          c->ckeys, c->he, c->brec, c->counters, w->d_ctl, w->d_ring, c->frontier[1]};
+    for (const void* p : ptrs) h = mix64(h, (uint64_t)(uintptr_t)p);
+    h = mix64(h, w->n);
+    h = mix64(h, c->cap_contacts);
+    h = mix64(h, (uint64_t)(c->bx | (c->by << 5) | (c->bz << 10)) | ((uint64_t)(c->mixed ? 1 : 0) << 20) |
+                     ((uint64_t)w->params.response_mode << 24) | ((uint64_t)(executor_wide(w, c) ? 1 : 0) << 28));
+    uint32_t f[5];
+    memcpy(&f[0], &c->inv_cell, 4);
+    memcpy(&f[1], &c->rmax_grid, 4);
+    memcpy(&f[2], c->origin, 12);
+    for (uint32_t v : f) h = mix64(h, v);
+    return h | 1ull;
+}
+
+void collide_poll_stats(tr_world*) {}
+
+// Whole steps of a small world in one kernel (tiny.cuh).  integrate: the step's O(N) part runs here too.
+static bool tiny_eligible(const tr_world* w) {
+    static const bool off = getenv("TR_NO_TINY") != nullptr;
+    return !off && !(w->params.debug_flags & TR_DEBUG_NO_TINY) && w->n <= (uint64_t)TINY_MAX && w->nranks == 1 &&
+           (w->params.flags & TR_PAIR_GRAVITY) == 0;
+}
+
+int tiny_steps(tr_world* w, const StepConsts& sc, int nsteps, bool* taken) {
+    *taken = false;
+    if (!tiny_eligible(w) || nsteps <= 0) return TR_OK;
+    const bool coll = (w->params.flags & TR_COLLISIONS) != 0;
+    if (coll) {
+        if (!w->classified) TR_TRY(collide_classify(w));   // keeps tr_debug_grid usable; the tiny step itself has no grid
+        TR_TRY(ensure_buffers(w));
+    }
+    Collide* c = coll ? state(w) : nullptr;
+    TinyArgs a{};
+    a.pos_m = w->pos_m[w->cur];
+    a.vel_rest = w->vel_rest;
+    a.force = w->force;
+    a.drag = w->drag;
+    a.center_r = w->center_r;
+    a.half_ext = w->half_ext;
+    a.flags = w->flags;
+    a.n = (uint32_t)w->n;
+    a.c = sc;
+    a.collide = coll ? 1 : 0;
+    a.ckeys = c ? c->ckeys : nullptr;
+    a.counters = c ? c->counters : nullptr;
+    a.ctl = w->d_ctl;
+    a.ring = w->d_ring;
+    a.traj = w->traj;
+    a.traj_cnt = w->traj_cnt;
+    a.traj_max = w->traj ? w->traj_max : 0;
+    a.traj_stride = w->traj_stride;
+    tiny_step_kernel<<<1, TINY_MAX, 0, w->stream>>>(a, nsteps);
+    TR_CUDA(cudaGetLastError());
+    w->stats.kernel_launches += 1;
+    if (coll) {
+        w->coll_seq += 1;
+        c->host_contacts_valid = false;
+    }
+    *taken = true;
+    return TR_OK;
+}
+
+// One collision step, enqueued: detection + ordered response + the step's record.  Nothing here waits for the GPU.
 int collide_step(tr_world* w) {
     if (w->n == 0) return TR_OK;
     if (!w->classified) TR_TRY(collide_classify(w));
     TR_TRY(ensure_buffers(w));
     Collide* c = state(w);
-    uint64_t count = 0;
-    TR_TRY(detect<false>(w, c->ckeys, c->cap_contacts, &count));
-    // detect() synchronised with the host: the previous response's iteration count has arrived
-    if (c->rounds_pending && c->flow_pending) {
-        c->prev_rounds = c->h_rounds[0];
-        c->prev_contacts = c->last_contacts;
-    }
-    collide_poll_stats(w);
-    w->stats.side_list_size = c->last_side + c->last_far;   // everything outside the grid: oversize list + far list
-    w->stats.last_contacts = count;
-    c->last_contacts = 0;
-    if (count > c->cap_contacts) {
-        set_error("contact buffer overflow: %llu contacts, capacity %llu (raise tr_world_params.max_contacts)",
-                  (unsigned long long)count, (unsigned long long)c->cap_contacts);
-        return TR_ERR_CAPACITY;
-    }
-    c->rounds_pending = false;
-    w->stats.last_response_rounds = 0;
-    if (count == 0) return TR_OK;
-    const uint32_t cn = (uint32_t)count;
-    const uint32_t cblocks = (cn + 255) / 256;
-    PendingTimer t;
-    timer_begin(w, T_RESPONSE, &t);
-    const uint32_t nb = (uint32_t)w->n;
-    const uint32_t btiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
-    // lexicographic (i,j) order == the reference's visiting order: counting sort by i, rank by j
-    chist_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, cn, 32, c->body_cnt);
-    tile_sums_kernel<<<btiles, SCAN_THREADS, 0, w->stream>>>(c->body_cnt, nb, c->tile_sum);
-    scan_kernel<<<btiles, SCAN_THREADS, 0, w->stream>>>(c->body_cnt, c->tile_sum, c->row_start, nb, c->counters, -1);
-    cscatter_row_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, cn, c->row_start, c->body_cnt, c->ckeys_alt);
-    crank_row_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys_alt, c->row_start, cn, c->ckeys);
-    // column order (j, then i): the same, keyed by j
-    chist_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, cn, 0, c->body_cnt);
-    tile_sums_kernel<<<btiles, SCAN_THREADS, 0, w->stream>>>(c->body_cnt, nb, c->tile_sum);
-    scan_kernel<<<btiles, SCAN_THREADS, 0, w->stream>>>(c->body_cnt, c->tile_sum, c->col_start, nb, c->counters, -1);
-    cscatter_col_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, cn, c->col_start, c->body_cnt, c->colkeys);
-    crank_col_kernel<<<cblocks, 256, 0, w->stream>>>(c->colkeys, c->ckeys, c->col_start, cn, c->colc, c->col_pos);
-    const bool flow = w->params.response_mode != 1;   // 1 selects the level-synchronous kernel
-    if (flow) TR_CUDA(cudaMemsetAsync(c->frontier[0], 0xFF, (size_t)cn * sizeof(uint32_t), w->stream));   // queue = all EMPTY
-    deps_kernel<<<cblocks, 256, 0, w->stream>>>(c->ckeys, c->colc, c->col_pos, c->row_start, c->col_start, cn, c->dep, c->succ_i,
-                                                c->succ_j, c->crec, c->frontier[0], c->counters, flow ? C_QTAIL : C_FRONT, w->pos_m[w->cur],
-                                                w->vel_rest, w->center_r, w->half_ext, w->flags, flow ? (BodyRec*)c->brec : nullptr, c->cver,
-                                                (ContactGeo*)c->cgeo);
-    if (flow) {
-        FlowArgs ra{w->pos_m[w->cur], w->vel_rest, w->pos_m[w->cur], w->vel_rest, (BodyRec*)c->brec, c->cver, (const ContactGeo*)c->cgeo};
-        int fblocks = w->num_sms;                     // resident by construction: 128 threads per SM
-        int fwant = (int)((cn + 127) / 128);
-        if (fwant < fblocks) fblocks = fwant < 1 ? 1 : fwant;
-        // Executor width.  Deep graphs (a packed lattice: ~800 dependent hand-offs) are latency bound:
-        // single-lane workers, 5 CTAs of 4 warps per SM (3, 4, 6, 7, 8, 9 per SM: 1.59, 1.39, 1.36, 1.38, 1.40, 1.42 ms
-        // against 1.34: beyond ~3K workers the extra pollers cost more than the extra hands bring).
-        // Wide shallow graphs are throughput bound: whole warps.  The previous step tells which:
-        // contacts per lock-step iteration of its longest worker.
-        bool wide = w->params.response_mode == 2;
-        if (w->params.response_mode == 0 && c->prev_rounds > 0) wide = c->prev_contacts / c->prev_rounds > 16384;
-        if (wide) {
-            response_flow_kernel<32><<<fblocks, 128, 0, w->stream>>>(ra, c->crec, c->dep, c->frontier[0], cn, c->counters, 0u);
-        } else {
-            int sblocks = w->num_sms * 5;
-            const int swant = (int)((cn + 3) / 4);
-            if (swant < sblocks) sblocks = swant < 1 ? 1 : swant;
-            // idle back-off: 200 / 500 / 1000 / 1500 ns -> 1.34 / 1.33 / 1.38 / 1.52 ms
-            response_flow_kernel<1><<<sblocks, 128, 0, w->stream>>>(ra, c->crec, c->dep, c->frontier[0], cn, c->counters, 500u);
+    static const bool no_graph = getenv("TR_NO_GRAPH") != nullptr;
+    // the level-synchronous executor is a cooperative launch, and the legacy default stream cannot be captured: plain launches
+    if (no_graph || w->stream == nullptr || w->params.response_mode == 1) {
+        TR_TRY(launch_step(w, w->stream));
+    } else {
+        const int slot = w->cur;
+        const uint64_t sig = step_signature(w);
+        if (!c->graph[slot] || c->graph_sig[slot] != sig) {
+            if (c->graph[slot]) cudaGraphExecDestroy(c->graph[slot]);
+            c->graph[slot] = nullptr;
+            cudaGraph_t graph = nullptr;
+            TR_CUDA(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = launch_step(w, w->stream);
+            cudaError_t e = cudaStreamEndCapture(w->stream, &graph);
+            if (rc != TR_OK) return rc;
+            if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+            e = cudaGraphInstantiate(&c->graph[slot], graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+            c->graph_sig[slot] = sig;
         }
-        TR_CUDA(cudaGetLastError());
-        timer_end(w, &t);
-        w->stats.kernel_launches += 12;   // 2 x (hist, tile sums, scan, scatter, rank) + deps + response
-        c->last_contacts = count;
-        // watchdog flag + (unused) round counter come back with the next sync
-        TR_CUDA(cudaMemcpyAsync(c->h_rounds, c->counters + C_ROUNDS, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
-        c->rounds_pending = true;
-        c->flow_pending = true;
-        return TR_OK;
+        TR_CUDA(cudaGraphLaunch(c->graph[slot], w->stream));
     }
-    if (c->coop_blocks == 0) {
-        int per_sm = 0;
-        TR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, response_kernel, 256, 0));
-        if (per_sm < 1) per_sm = 1;
-        c->coop_blocks = w->num_sms;   // one CTA per SM: the grid barrier cost grows with the CTA count
+    w->stats.kernel_launches += 8;   // keys, tile sums, scan, scatter, narrow (+ side / far workers), prep, executor, epilogue
+    w->coll_seq += 1;
+    c->host_contacts_valid = false;
+    return TR_OK;
+}
+
+// Fold the step records the device has written since the last call into the host-side statistics
+// (after a stream synchronisation).  *overflow_seq = sequence number of a step whose contact list
+// did not fit (its response and every later step were skipped on the device), *found = its count.
+int collide_consume_records(tr_world* w, bool* overflow, uint32_t* overflow_seq, uint64_t* found) {
+    *overflow = false;
+    Collide* c = w->col;
+    if (!c || !w->h_ring) return TR_OK;
+    const uint32_t upto = w->coll_seq;
+    if (upto - w->ring_consumed > STEP_RING) w->ring_consumed = upto - STEP_RING;   // older records were overwritten
+    for (uint32_t s = w->ring_consumed; s < upto; ++s) {
+        const StepRecord r = w->h_ring[s % STEP_RING];
+        if (r.seq != s + 1u) continue;            // not written (cannot happen after a sync) or overwritten
+        if (r.flags & 4u) continue;               // no-op step behind an overflow: re-run by the recovery
+        const uint64_t cnt = ((uint64_t)r.contacts_hi << 32) | r.contacts_lo;
+        if (r.flags & 1u) {
+            if (!*overflow) {
+                *overflow = true;
+                *overflow_seq = s;
+                *found = cnt;
+            }
+            continue;
+        }
+        if (r.flags & 2u) {
+            if (w->deferred_error == TR_OK) {
+                w->deferred_error = TR_ERR_CUDA;
+                w->deferred_msg = "ordered response: dataflow watchdog fired (dependency graph did not drain)";
+            }
+        }
+        w->stats.last_contacts = cnt;
+        w->stats.side_list_size = r.side + r.far;   // everything outside the grid: oversize list + far list
+        w->stats.last_response_rounds = r.rounds;
+        c->last_contacts = cnt;
+        c->last_side = r.side;
+        c->last_far = r.far;
+        if (cnt) {
+            c->prev_contacts = cnt;
+            c->prev_rounds = r.rounds;
+        }
+        if (w->timing && r.t[3] >= r.t[0]) {
+            w->stats.broadphase_ms += (double)(r.t[1] - r.t[0]) * 1e-6;
+            w->stats.narrowphase_ms += (double)(r.t[2] - r.t[1]) * 1e-6;
+            w->stats.response_ms += (double)(r.t[3] - r.t[2]) * 1e-6;
+            w->stats.broadphase_launches += 1;
+        }
     }
-    RespArgs ra{w->pos_m[w->cur], w->vel_rest, w->center_r, w->half_ext, w->flags};
-    const unsigned long long* ck = c->ckeys;
-    uint32_t* dep = c->dep;
-    const uint32_t* si = c->succ_i;
-    const uint32_t* sj = c->succ_j;
-    uint32_t* f0 = c->frontier[0];
-    uint32_t* f1 = c->frontier[1];
-    uint32_t* cnt = c->counters;
-    void* args[] = {&ra, &ck, &dep, &si, &sj, &f0, &f1, &cnt};
-    int blocks = c->coop_blocks;
-    int want = (int)((cn + 255) / 256);
-    if (want < blocks) blocks = want < 1 ? 1 : want;
-    TR_CUDA(cudaLaunchCooperativeKernel((void*)response_kernel, dim3(blocks), dim3(256), args, 0, w->stream));
-    timer_end(w, &t);
-    w->stats.kernel_launches += 12;   // 2 x (hist, tile sums, scan, scatter, rank) + deps + response
-    c->last_contacts = count;
-    // wavefront count: copied to pinned memory asynchronously, picked up at the next sync (no extra stall)
-    TR_CUDA(cudaMemcpyAsync(c->h_rounds, c->counters + C_ROUNDS, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
-    c->rounds_pending = true;
+    w->ring_consumed = upto;
+    return TR_OK;
+}
+
+// Head-room policy, applied by the host after a synchronisation: grow ahead of a slowly filling list so that the
+// recovery path stays the exception.
+static int cache_host_contacts(tr_world* w);
+
+int collide_headroom(tr_world* w) {
+    Collide* c = w->col;
+    if (!c || c->cap_fixed || c->cap_contacts == 0) return TR_OK;
+    if (c->last_contacts * 10 > c->cap_contacts * 7) {
+        TR_TRY(cache_host_contacts(w));   // the last step's list lives in the buffers about to be replaced
+        return collide_grow_contacts(w, c->last_contacts * 2);
+    }
+    return TR_OK;
+}
+
+// the device keeps the list in arrival order; the reference's visiting order is lexicographic (i,j)
+static int cache_host_contacts(tr_world* w) {
+    Collide* c = w->col;
+    if (c->host_contacts_valid || c->last_contacts == 0) return TR_OK;
+    c->host_contacts.resize(c->last_contacts);
+    TR_CUDA(cudaMemcpyAsync(c->host_contacts.data(), c->ckeys, c->last_contacts * sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream));
+    TR_CUDA(cudaStreamSynchronize(w->stream));
+    std::sort(c->host_contacts.begin(), c->host_contacts.end());
+    c->host_contacts_valid = true;
     return TR_OK;
 }
 
@@ -492,14 +508,30 @@ int collide_read_contacts(tr_world* w, int32_t* pairs, uint64_t cap, uint64_t* n
     uint64_t cnt = c ? c->last_contacts : 0;
     if (n) *n = cnt;
     if (!pairs || cnt == 0) return TR_OK;
-    uint64_t take = cnt < cap ? cnt : cap;
-    std::vector<unsigned long long> h(take);
-    TR_CUDA(cudaMemcpyAsync(h.data(), c->ckeys, take * sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream));
-    TR_CUDA(cudaStreamSynchronize(w->stream));
+    TR_TRY(cache_host_contacts(w));
+    const uint64_t take = cnt < cap ? cnt : cap;
     for (uint64_t k = 0; k < take; ++k) {
-        pairs[2 * k] = (int32_t)(h[k] >> 32);
-        pairs[2 * k + 1] = (int32_t)(h[k] & 0xFFFFFFFFu);
+        pairs[2 * k] = (int32_t)(c->host_contacts[k] >> 32);
+        pairs[2 * k + 1] = (int32_t)(c->host_contacts[k] & 0xFFFFFFFFu);
     }
+    return TR_OK;
+}
+
+// debug entry points: a stand-alone broad phase (the step's counters are zero between steps; left zero again)
+static int debug_begin(tr_world* w) {
+    if (!w->classified) TR_TRY(collide_classify(w));
+    TR_TRY(ensure_buffers(w));
+    Collide* c = state(w);
+    TR_CUDA(cudaMemsetAsync(c->counters, 0, C_NCOUNTERS * sizeof(uint32_t), w->stream));
+    TR_TRY(launch_broad(w, w->stream));
+    return TR_OK;
+}
+
+static int debug_end(tr_world* w, uint32_t* host_counters) {
+    Collide* c = state(w);
+    TR_CUDA(cudaMemcpyAsync(host_counters, c->counters, C_NHOST * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+    TR_CUDA(cudaMemsetAsync(c->counters, 0, C_NCOUNTERS * sizeof(uint32_t), w->stream));
+    TR_CUDA(cudaStreamSynchronize(w->stream));
     return TR_OK;
 }
 
@@ -509,16 +541,15 @@ int collide_debug_grid(tr_world* w, uint32_t* keys, uint32_t* sorted_ids, uint64
         if (m) *m = 0;
         return TR_OK;
     }
-    if (!w->classified) TR_TRY(collide_classify(w));
-    TR_TRY(ensure_buffers(w));
+    TR_TRY(debug_begin(w));
     Collide* c = state(w);
-    TR_TRY(broad_phase(w));
     // K4, only here: the stable (key,id) order of the grid bodies
     canon_kernel<<<(uint32_t)((w->n + 255) / 256), 256, 0, w->stream>>>((const SlotRec*)c->recs, c->cell_start, grid_params(c),
                                                                           c->counters, c->sorted_ids);
     TR_CUDA(cudaGetLastError());
-    TR_TRY(read_counters(w));
-    const uint32_t gm = c->h_counters[C_GRID];
+    uint32_t hc[C_NHOST];
+    TR_TRY(debug_end(w, hc));
+    const uint32_t gm = hc[C_GRID];
     if (m) *m = gm;
     if (cell) *cell = c->cell;
     if (inv_cell) *inv_cell = c->inv_cell;
@@ -543,13 +574,14 @@ int collide_debug_candidates(tr_world* w, int32_t* pairs, uint64_t cap, uint64_t
         if (n) *n = 0;
         return TR_OK;
     }
-    if (!w->classified) TR_TRY(collide_classify(w));
-    TR_TRY(ensure_buffers(w));
     unsigned long long* d = nullptr;
     uint64_t dcap = pairs ? cap : 0;
     if (dcap) TR_CUDA(cudaMalloc(&d, dcap * sizeof(unsigned long long)));
-    uint64_t count = 0;
-    int rc = detect<true>(w, d, dcap, &count);
+    int rc = debug_begin(w);
+    if (rc == TR_OK) rc = launch_narrow<true>(w, w->stream, d, dcap);
+    uint32_t hc[C_NHOST];
+    if (rc == TR_OK) rc = debug_end(w, hc);
+    const uint64_t count = rc == TR_OK ? (((uint64_t)hc[C_CAND + 1] << 32) | hc[C_CAND]) : 0;
     if (rc == TR_OK && n) *n = count;
     w->stats.last_candidates = count;
     if (rc == TR_OK && pairs && count) {
@@ -573,17 +605,13 @@ int collide_free(tr_world* w) {
     cudaFree(c->keys); cudaFree(c->recs); cudaFree(c->sorted_ids);
     cudaFree(c->cell_start); cudaFree(c->cell_count); cudaFree(c->tile_sum);
     cudaFree(c->side_list); cudaFree(c->far_list); cudaFree(c->bnd_list); cudaFree(c->far_c); cudaFree(c->bnd_c); cudaFree(c->klass);
-    cudaFree(c->row_start); cudaFree(c->col_start); cudaFree(c->body_cnt); cudaFree(c->counters);
-    if (c->h_counters) cudaFreeHost(c->h_counters);
-    if (c->h_rounds) cudaFreeHost(c->h_rounds);
-    cudaFree(c->ckeys); cudaFree(c->ckeys_alt); cudaFree(c->colkeys);
-    cudaFree(c->colc); cudaFree(c->col_pos); cudaFree(c->dep);
-    cudaFree(c->succ_i); cudaFree(c->succ_j); cudaFree(c->crec); cudaFree(c->cver); cudaFree(c->cgeo); cudaFree(c->brec); cudaFree(c->frontier[0]); cudaFree(c->frontier[1]);
-    if (c->bp_graph) cudaGraphExecDestroy(c->bp_graph);
+    cudaFree(c->seg); cudaFree(c->long_list); cudaFree(c->body_cnt); cudaFree(c->counters); cudaFree(c->brec);
+    free_contact_buffers(c);
+    for (int k = 0; k < 2; ++k)
+        if (c->graph[k]) cudaGraphExecDestroy(c->graph[k]);
     delete c;
     w->col = nullptr;
     return TR_OK;
 }
 
 }  // namespace tr
-

@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ ce
                                                    uint32_t* __restrict__ bnd_list, float4* __restrict__ bnd_c,
                                                    uint32_t* __restrict__ cell_count, uint32_t* counters) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *reinterpret_cast<unsigned long long*>(counters + C_T0) = globaltimer_ns();   // start of the broad phase
     {
         // stream the (zeroed) histogram into L2 ahead of the scattered REDs: one 128-byte line per
         // thread of the leading CTAs, so random cloud ids do not pay a DRAM round trip per atomic
@@ -149,54 +150,75 @@ __global__ void __launch_bounds__(256) canon_kernel(const SlotRec* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------
-// K5: narrow phase over the 27-cell stencil (9 runs of up to 3 key-contiguous cells)
+// K5: narrow phase over the half stencil, (body, candidate) PAIRS balanced over the lanes of a warp
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void emit_pair(unsigned long long* out, unsigned long long cap, unsigned long long* counter,
                                           uint32_t i, uint32_t j) {
-    unsigned long long slot = atomicAdd(counter, 1ull);
+    const unsigned long long slot = warp_reserve(counter);   // one atomic for the lanes that hit together
     if (slot < cap) out[slot] = ((unsigned long long)i << 32) | j;
 }
 
-// Hits are staged per thread (NARROW_HITS partner ids in shared memory) and a warp reserves its
-// output slots with ONE atomic at the end.  Emitting from inside the loops - even warp-aggregated, as
-// ptxas does by itself - sends ~450K atomics to one address on the packed 1M scene, and same-address
-// atomics retire at ~0.85 clk each at L2: that queue, not the loads, was the packed narrow phase
-// (ncu: issue slots 15 % busy, L2 4 %, every warp waiting on the atomic's return).
+// The candidate relation "cell(b) is in the 27-cell stencil of cell(a)" is symmetric, so every
+// unordered pair is reached from exactly one side by a HALF stencil: the later slots of a's own
+// cell, and the 13 cells at "forward" offsets (dz,dy,dx) > (0,0,0) lexicographically (an offset o
+// and its opposite -o are distinct modulo the per-axis table size >= 4, and exactly one of them is forward).
+// With x as the fastest key digit those are 5 contiguous slot ranges ("windows") for an interior cell:
+//   [t+1, end of cell cx+1]  in the own row, and cells cx-1..cx+1 of the rows (dz,dy) =
+//   (0,+1), (+1,-1), (+1,0), (+1,+1).
+// "Later slots of the own cell" is any fixed order: the arrival order K3b left is as good as the id order.
+// MIXED: boxes live in the grid; a pair with at least one box uses the AABB predicate on the
+// collider sizes of both bodies, exactly as the reference dispatches (main.cpp:701-706).
+//
+// Work distribution.  Round 1 gave every lane one body and let it walk its five windows: a window
+// holds a Poisson(1.5) number of records on the sparse cloud, a warp runs the maximum over its lanes
+// window by window, and ncu counted 10.4 of 32 lanes active per instruction.  Now a warp owns 32
+// consecutive slots and works in two phases:
+//   expand   every lane writes its (candidate slot, owner lane) pairs into a per-warp list in shared
+//            memory at the offset a warp scan of the window lengths gives it (3 instructions per pair);
+//   test     the lanes walk the flattened list 32 pairs at a time: own record from shared memory, the
+//            candidate's record by one 256-bit load, exact predicate; every lane busy.
+// Hits are staged in a per-warp buffer and written out with ONE atomic per flush (same-address atomics
+// retire at ~0.85 clk each at L2: emitting from inside the loop was the packed narrow phase in round 1).
+// The 2 of 2^bx cells per row at the x edges, whose windows wrap, keep the lane-serial path (narrow_edge).
 constexpr int NARROW_THREADS = 128;
-constexpr int NARROW_HITS = 8;
+constexpr int NARROW_WARPS = NARROW_THREADS / 32;
+constexpr int NARROW_LIST = 640;     // (candidate, owner) pairs per warp and round: 20 per lane (mean 7 sparse, 14.5 packed)
+constexpr int NARROW_STAGE = 128;    // staged hits per warp
 
-__device__ __noinline__ void emit_pair_overflow(unsigned long long* out, unsigned long long cap, unsigned long long* counter,
-                                                uint32_t i, uint32_t j) {
-    emit_pair(out, cap, counter, i, j);
+struct NarrowWarp {
+    uint32_t u[NARROW_LIST];                   // candidate slot
+    uint8_t o[NARROW_LIST];                    // owner lane
+    unsigned long long hit[NARROW_STAGE];      // (min id << 32) | max id
+    SlotRec own[32];
+};
+
+__device__ __forceinline__ void narrow_flush(NarrowWarp& sw, uint32_t& nh, uint32_t lane, unsigned long long* out,
+                                             unsigned long long cap, unsigned long long* counter) {
+    if (nh == 0) return;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(counter, (unsigned long long)nh);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    for (uint32_t k = lane; k < nh; k += 32)
+        if (base + k < cap) out[base + k] = sw.hit[k];
+    nh = 0;
+    __syncwarp();
 }
 
 template <bool CANDIDATES, bool MIXED>
-__device__ __forceinline__ void test_one(uint32_t u, uint32_t va, uint32_t ida, const float4 ca, const float4 ha,
-                                         const SlotRec* __restrict__ recs, uint32_t (*s_hit)[NARROW_THREADS], uint32_t& nh,
-                                         unsigned long long* out, unsigned long long cap, unsigned long long* counter) {
-    float4 cb, hb;
-    uint32_t vb;
-    ld_rec(recs + u, cb, vb, hb);
-    const uint32_t idb = vb & ID_MASK;
-    bool hit = true;
-    if (!CANDIDATES) {
-        if (MIXED && ((va | vb) & BOX_BIT)) hit = aabb_hit(ca, ha, cb, hb);   // main.cpp:704
-        else hit = sphere_hit(ca, cb);                                       // main.cpp:702
-        hit = hit && !(va & vb & STATIC_BIT);                                // main.cpp:695
-    }
-    if (hit) {
-        if (nh < (uint32_t)NARROW_HITS) s_hit[nh][threadIdx.x] = idb;
-        else emit_pair_overflow(out, cap, counter, min(ida, idb), max(ida, idb));   // staging full: straight out
-        ++nh;
-    }
+__device__ __forceinline__ bool pair_hit(const float4 ca, uint32_t va, const float4 ha, const float4 cb, uint32_t vb, const float4 hb) {
+    if (CANDIDATES) return true;
+    bool hit;
+    if (MIXED && ((va | vb) & BOX_BIT)) hit = aabb_hit(ca, ha, cb, hb);   // main.cpp:704
+    else hit = sphere_hit(ca, cb);                                       // main.cpp:702
+    return hit && !(va & vb & STATIC_BIT);                               // main.cpp:695
 }
 
-// x-edge cell: the windows wrap around the row, so they are walked cell by cell (2 of 2^bx cells per row)
+// x-edge cell: the windows wrap around the row, so they are walked cell by cell by the owning lane
+// (2 of 2^bx cells per row); hits go straight out through the warp-aggregated append
 template <bool CANDIDATES, bool MIXED>
 __device__ __noinline__ void narrow_edge(uint32_t t, uint32_t key, int bx, int by, int bz, uint32_t va, const float4 ca, const float4 ha,
                                          const SlotRec* __restrict__ recs, const uint32_t* __restrict__ cell_start,
-                                         uint32_t (*s_hit)[NARROW_THREADS], uint32_t& nh, unsigned long long* out,
-                                         unsigned long long cap, unsigned long long* counter) {
+                                         unsigned long long* out, unsigned long long cap, unsigned long long* counter) {
     const uint32_t ida = va & ID_MASK;
     const uint32_t mx = (1u << bx) - 1u, my = (1u << by) - 1u, mz = (1u << bz) - 1u;
     const uint32_t cx = key & mx, cy = (key >> bx) & my, cz = (key >> (bx + by)) & mz;
@@ -221,45 +243,75 @@ __device__ __noinline__ void narrow_edge(uint32_t t, uint32_t key, int bx, int b
             e = cell_start[nk + 1];
         }
 #pragma unroll 1
-        for (uint32_t u = s; u < e; ++u) test_one<CANDIDATES, MIXED>(u, va, ida, ca, ha, recs, s_hit, nh, out, cap, counter);
+        for (uint32_t u = s; u < e; ++u) {
+            float4 cb, hb;
+            uint32_t vb;
+            ld_rec(recs + u, cb, vb, hb);
+            if (pair_hit<CANDIDATES, MIXED>(ca, va, ha, cb, vb, hb)) {
+                const uint32_t idb = vb & ID_MASK;
+                emit_pair(out, cap, counter, min(ida, idb), max(ida, idb));
+            }
+        }
     }
 }
 
-// The candidate relation "cell(b) is in the 27-cell stencil of cell(a)" is symmetric, so every
-// unordered pair is reached from exactly one side by a HALF stencil: the later slots of a's own
-// cell, and the 13 cells at "forward" offsets (dz,dy,dx) > (0,0,0) lexicographically (an offset o
-// and its opposite -o are distinct modulo the per-axis table size >= 4, and exactly one of them is forward).
-// With x as the fastest key digit those are 5 contiguous slot ranges for an interior cell:
-//   [t+1, end of cell cx+1]  in the own row, and cells cx-1..cx+1 of the rows (dz,dy) =
-//   (0,+1), (+1,-1), (+1,0), (+1,+1).
-// "Later slots of the own cell" is any fixed order: the arrival order K3b left is as good as the id order.
-// MIXED: boxes live in the grid; a pair with at least one box uses the AABB predicate on the
-// collider sizes of both bodies, exactly as the reference dispatches (main.cpp:701-706).
-// One thread per slot.  (A warp-cooperative version - the union of a warp's windows per stencil
-// row staged in shared memory by coalesced loads, each record read once per warp - was measured at
-// 98.9 us sparse / 286.7 us packed against 54.6 / 321.8 for this one: the staging phases serialise
-// a warp that otherwise hides its latency with 64 independent threads per scheduler.)
+// Blocks [0, slot_blocks) run the grid narrow phase; the blocks behind them are the "outside" workers
+// (side list and far list, K5b / K5c below) so that the whole detection is one launch.
+struct OutsideArgs {
+    const uint32_t* side_list;
+    const uint32_t* far_list;
+    const float4* far_c;
+    const uint32_t* bnd_list;
+    const float4* bnd_c;
+    const float4* center_r;
+    const float4* half_ext;
+    const uint8_t* flags;
+    const uint8_t* klass;
+    uint32_t n;
+};
+__device__ void outside_worker(uint32_t worker, uint32_t nworkers, const OutsideArgs& oa, const uint32_t* counters,
+                               unsigned long long* out, unsigned long long cap, unsigned long long* counter);
+
 template <bool CANDIDATES, bool MIXED>
 __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* __restrict__ recs,
                                                                 const uint32_t* __restrict__ cell_start,
-                                                                const uint32_t* __restrict__ counters, GridParams g,
-                                                                unsigned long long* out, unsigned long long cap,
+                                                                uint32_t* counters, GridParams g, uint32_t slot_blocks,
+                                                                OutsideArgs oa, unsigned long long* out, unsigned long long cap,
                                                                 unsigned long long* counter) {
-    __shared__ uint32_t s_hit[NARROW_HITS][NARROW_THREADS];
+    __shared__ NarrowWarp s_warp[NARROW_WARPS];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<unsigned long long*>(counters + C_T0 + 2) = globaltimer_ns();
+    if (blockIdx.x >= slot_blocks) {
+        if (!CANDIDATES) outside_worker(blockIdx.x - slot_blocks, gridDim.x - slot_blocks, oa, counters, out, cap, counter);
+        return;
+    }
+    const uint32_t ngrid = counters[C_GRID];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t t = blockIdx.x * NARROW_THREADS + threadIdx.x;
-    const uint32_t lane = threadIdx.x & 31;
-    uint32_t nh = 0, ida = 0;
-    if (t < counters[C_GRID]) {
-        float4 ca, ha;
-        uint32_t va;
+    if (t - lane >= ngrid) return;                 // the whole warp is past the last grid body
+    NarrowWarp& sw = s_warp[wid];
+    const bool valid = t < ngrid;
+    float4 ca = make_float4(0.f, 0.f, 0.f, 0.f), ha = ca;
+    uint32_t va = 0, key = 0;
+    uint32_t rs[5], len[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) rs[r] = len[r] = 0;
+    bool edge = false;
+    if (valid) {
         ld_rec(recs + t, ca, va, ha);
-        const uint32_t key = cell_key(ca, g);
-        ida = va & ID_MASK;
+        sw.own[lane].c = ca;
+        sw.own[lane].val = va;
+        if (MIXED) {
+            sw.own[lane].hx = ha.x;
+            sw.own[lane].hy = ha.y;
+            sw.own[lane].hz = ha.z;
+        }
+        key = cell_key(ca, g);
         const uint32_t mx = (1u << g.bx) - 1u, my = (1u << g.by) - 1u, mz = (1u << g.bz) - 1u;
         const uint32_t cx = key & mx, cy = (key >> g.bx) & my, cz = (key >> (g.bx + g.by)) & mz;
-        if (cx > 0 && cx < mx) {
+        edge = cx == 0 || cx == mx;
+        if (!edge) {
             // interior cell: five contiguous slot ranges, all nine look-ups issued before the first use
-            uint32_t rs[5], re[5];
+            uint32_t re[5];
             rs[0] = t + 1;
             re[0] = cell_start[key + 2];
 #pragma unroll
@@ -270,92 +322,129 @@ __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* _
                 rs[r + 1] = cell_start[row + cx - 1];
                 re[r + 1] = cell_start[row + cx + 2];
             }
-            // (one flattened loop over the five windows - a lane moving on as soon as its own window is
-            // exhausted - was slower: 77 / 90 us against 62 / 73; the compiler pipelines these loops better)
 #pragma unroll
-            for (int r = 0; r < 5; ++r)
-                for (uint32_t u = rs[r]; u < re[r]; ++u)
-                    test_one<CANDIDATES, MIXED>(u, va, ida, ca, ha, recs, s_hit, nh, out, cap, counter);
-        } else {
-            narrow_edge<CANDIDATES, MIXED>(t, key, g.bx, g.by, g.bz, va, ca, ha, recs, cell_start, s_hit, nh, out, cap, counter);
+            for (int r = 0; r < 5; ++r) len[r] = re[r] - rs[r];
         }
     }
-    // one reservation per warp for everything it staged
-    if (!__any_sync(0xFFFFFFFFu, nh != 0)) return;
-    const uint32_t cnt = min(nh, (uint32_t)NARROW_HITS);
-    uint32_t incl = cnt;
+    // offsets of every lane's pairs in the warp's flattened list
+    const uint32_t mine = len[0] + len[1] + len[2] + len[3] + len[4];
+    uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
         if (lane >= (uint32_t)o) incl += y;
     }
     const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    if (total == 0) return;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(counter, (unsigned long long)total);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0) + (incl - cnt);
-    for (uint32_t k = 0; k < cnt; ++k) {
-        const uint32_t idb = s_hit[k][threadIdx.x];
-        if (base + k < cap) out[base + k] = ((unsigned long long)min(ida, idb) << 32) | max(ida, idb);
+    const uint32_t off = incl - mine;
+    uint32_t nh = 0;                               // staged hits (warp-uniform)
+    __syncwarp();
+    for (uint32_t base = 0; base < total; base += NARROW_LIST) {
+        // ---- expand: this round covers list positions [base, base + NARROW_LIST)
+        uint32_t wo = off;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            const uint32_t lo = max(wo, base), hi = min(wo + len[r], base + (uint32_t)NARROW_LIST);
+            for (uint32_t k = lo; k < hi; ++k) {
+                sw.u[k - base] = rs[r] + (k - wo);
+                sw.o[k - base] = (uint8_t)lane;
+            }
+            wo += len[r];
+        }
+        __syncwarp();
+        // ---- test: 32 pairs per iteration
+        const uint32_t cnt = min((uint32_t)NARROW_LIST, total - base);
+        for (uint32_t p0 = 0; p0 < cnt; p0 += 32) {
+            const uint32_t p = p0 + lane;
+            bool hit = false;
+            unsigned long long pr = 0;
+            if (p < cnt) {
+                const uint32_t u = sw.u[p], o = sw.o[p];
+                float4 cb, hb;
+                uint32_t vb;
+                ld_rec(recs + u, cb, vb, hb);
+                const float4 oc = sw.own[o].c;
+                const uint32_t ov = sw.own[o].val;
+                float4 oh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (MIXED) oh = make_float4(sw.own[o].hx, sw.own[o].hy, sw.own[o].hz, 0.f);
+                hit = pair_hit<CANDIDATES, MIXED>(oc, ov, oh, cb, vb, hb);
+                const uint32_t ida = ov & ID_MASK, idb = vb & ID_MASK;
+                pr = ((unsigned long long)min(ida, idb) << 32) | max(ida, idb);
+            }
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+            if (m) {
+                if (hit) sw.hit[nh + __popc(m & ((1u << lane) - 1u))] = pr;
+                nh += __popc(m);
+                __syncwarp();
+                if (nh > (uint32_t)(NARROW_STAGE - 32)) narrow_flush(sw, nh, lane, out, cap, counter);
+            }
+        }
+        __syncwarp();
     }
+    narrow_flush(sw, nh, lane, out, cap, counter);
+    if (edge) narrow_edge<CANDIDATES, MIXED>(t, key, g.bx, g.by, g.bz, va, ca, ha, recs, cell_start, out, cap, counter);
 }
 
-// K5b: side-list bodies against every live body.  grid = (ceil(n/256), up to 64).
-__global__ void __launch_bounds__(256) side_kernel(const uint32_t* __restrict__ side_list, const uint32_t* __restrict__ counters,
-                                                   const float4* __restrict__ center_r,
-                                                   const float4* __restrict__ half_ext,
-                                                   const uint8_t* __restrict__ flags, const uint8_t* __restrict__ klass,
-                                                   uint32_t n, unsigned long long* out, unsigned long long cap,
-                                                   unsigned long long* counter) {
-    const uint32_t side_count = counters[C_SIDE];
-    uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= n) return;
-    const uint8_t kx = klass[x];
-    if (kx == 0) return;
-    const float4 cx = center_r[x], hx = half_ext[x];
-    const uint8_t fx = flags[x];
-    for (uint32_t si = blockIdx.y; si < side_count; si += gridDim.y) {
-        const uint32_t s = side_list[si];
-        if (s == x) continue;
-        if (kx == 2 && x < s) continue;   // side-side pairs are emitted once, from the lower id's row
-        const uint8_t fs = flags[s];
-        if ((fx & F_STATIC) && (fs & F_STATIC)) continue;
-        const float4 cs = center_r[s];
-        bool hit;
-        if ((fx & F_SPHERE) && (fs & F_SPHERE)) hit = sphere_hit(cx, cs);
-        else hit = aabb_hit(cx, hx, cs, half_ext[s]);
-        if (hit) emit_pair(out, cap, counter, min(x, s), max(x, s));
-    }
-}
-
+// K5b: side-list bodies (oversize / non-finite extent) against every live body.  Persistent workers:
+// a worker takes tiles of 128 bodies (grid-stride) and walks the side list for each of its bodies.
 // K5c: "far" bodies (normal extent, finite centre, outside the grid domain |u| < 32768) against each
-// other and against the grid bodies within two cells of the domain boundary; side_kernel covers
+// other and against the grid bodies within two cells of the domain boundary; K5b covers
 // far-vs-oversize.  A contact implies |delta u| < 1 per axis (cell = 2*rmax*(1+2^-7)) and computed
 // u carries < 0.01 of error at that magnitude, so a grid body that touches a far body has
-// |u| > 32766 on that axis: nobody else needs testing.  Thread = far body (grid-stride), rows
-// (gridDim.y) stride over the partner list, so any launch geometry is correct.
-// Both lists carry id|flags (pack_val) and a compact copy of the centres, so the partner loop
-// streams consecutive 16-byte entries instead of gathering by id.
-__global__ void __launch_bounds__(256) far_kernel(const uint32_t* __restrict__ far_list, const float4* __restrict__ far_c,
-                                                  const uint32_t* __restrict__ bnd_list, const float4* __restrict__ bnd_c,
-                                                  const uint32_t* __restrict__ counters, const float4* __restrict__ half_ext,
-                                                  unsigned long long* out, unsigned long long cap, unsigned long long* counter) {
-    const uint32_t nfar = counters[C_FAR], nbnd = counters[C_BND];
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nfar; t += gridDim.x * blockDim.x) {
-        const uint32_t va = far_list[t];
-        const uint32_t a = va & ID_MASK;
-        const float4 ca = far_c[t];
-        // partners: far bodies later in the list, then every boundary grid body
-        for (uint32_t k = t + 1 + blockIdx.y; k < nfar + nbnd; k += gridDim.y) {
-            const bool kf = k < nfar;
-            const uint32_t vb = kf ? far_list[k] : bnd_list[k - nfar];
-            if (va & vb & STATIC_BIT) continue;                      // main.cpp:695
-            const float4 cb = kf ? far_c[k] : bnd_c[k - nfar];
-            const uint32_t b = vb & ID_MASK;
-            bool hit;
-            if ((va | vb) & BOX_BIT) hit = aabb_hit(ca, half_ext[a], cb, half_ext[b]);   // main.cpp:704
-            else hit = sphere_hit(ca, cb);                                               // main.cpp:702
-            if (hit) emit_pair(out, cap, counter, min(a, b), max(a, b));
+// |u| > 32766 on that axis: nobody else needs testing.  Both lists carry id|flags (pack_val) and a
+// compact copy of the centres, so the partner loop streams consecutive 16-byte entries instead of
+// gathering by id.  Work items are (far body, slice of the partner list) so that a few far bodies
+// next to a long boundary list still spread over the workers.
+__device__ void outside_worker(uint32_t worker, uint32_t nworkers, const OutsideArgs& oa, const uint32_t* counters,
+                               unsigned long long* out, unsigned long long cap, unsigned long long* counter) {
+    const uint32_t side_count = counters[C_SIDE], nfar = counters[C_FAR], nbnd = counters[C_BND];   // written by K2
+    if (side_count == 0 && nfar == 0) return;
+    if (side_count) {
+        const uint32_t ntiles = (oa.n + NARROW_THREADS - 1) / NARROW_THREADS;
+        for (uint32_t tile = worker; tile < ntiles; tile += nworkers) {
+            const uint32_t x = tile * NARROW_THREADS + threadIdx.x;
+            if (x >= oa.n) continue;
+            const uint8_t kx = oa.klass[x];
+            if (kx == 0) continue;                 // mass <= 0: dropped from every pair (main.cpp:696)
+            const float4 cx = oa.center_r[x], hx = oa.half_ext[x];
+            const uint8_t fx = oa.flags[x];
+            for (uint32_t si = 0; si < side_count; ++si) {
+                const uint32_t s = oa.side_list[si];
+                if (s == x) continue;
+                if (kx == 2 && x < s) continue;    // side-side pairs are emitted once, from the higher id's row
+                const uint8_t fs = oa.flags[s];
+                if ((fx & F_STATIC) && (fs & F_STATIC)) continue;             // main.cpp:695
+                const float4 cs = oa.center_r[s];
+                bool hit;
+                if ((fx & F_SPHERE) && (fs & F_SPHERE)) hit = sphere_hit(cx, cs);      // main.cpp:702
+                else hit = aabb_hit(cx, hx, cs, oa.half_ext[s]);                       // main.cpp:704
+                if (hit) emit_pair(out, cap, counter, min(x, s), max(x, s));
+            }
+        }
+    }
+    if (nfar) {
+        // items = (far body t, slice of 1024 partners); partners of t: far bodies later in the list, then every boundary grid body
+        const uint32_t total = nfar + nbnd;
+        const uint32_t slices = (total + 1023) / 1024;
+        const unsigned long long items = (unsigned long long)nfar * slices;
+        for (unsigned long long it = (unsigned long long)worker * NARROW_THREADS + threadIdx.x; it < items;
+             it += (unsigned long long)nworkers * NARROW_THREADS) {
+            const uint32_t t = (uint32_t)(it / slices), sl = (uint32_t)(it % slices);
+            const uint32_t k0 = max(t + 1, sl * 1024u), k1 = min(total, (sl + 1) * 1024u);
+            if (k0 >= k1) continue;
+            const uint32_t va = oa.far_list[t];
+            const uint32_t a = va & ID_MASK;
+            const float4 ca = oa.far_c[t];
+            for (uint32_t k = k0; k < k1; ++k) {
+                const bool kf = k < nfar;
+                const uint32_t vb = kf ? oa.far_list[k] : oa.bnd_list[k - nfar];
+                if (va & vb & STATIC_BIT) continue;                      // main.cpp:695
+                const float4 cb = kf ? oa.far_c[k] : oa.bnd_c[k - nfar];
+                const uint32_t b = vb & ID_MASK;
+                bool hit;
+                if ((va | vb) & BOX_BIT) hit = aabb_hit(ca, oa.half_ext[a], cb, oa.half_ext[b]);   // main.cpp:704
+                else hit = sphere_hit(ca, cb);                                               // main.cpp:702
+                if (hit) emit_pair(out, cap, counter, min(a, b), max(a, b));
+            }
         }
     }
 }

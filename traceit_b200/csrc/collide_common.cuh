@@ -24,13 +24,42 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
-// counters[] slots
+// counters[] slots (device memory, zeroed by the last kernel of every collision step)
 // The three counters every dataflow worker hammers (queue head, queue tail, finished work) sit on
 // 128-byte lines of their own: on one line their atomics and the idle workers' polls all queue at
 // one L2 slice (having idle workers merely READ the tail next to the pushes doubled the step time).
-enum { C_SIDE = 0, C_GRID = 1, C_CONTACTS = 2 /*u64*/, C_CAND = 4 /*u64*/, C_FRONT = 8 /*3*/, C_ROUNDS = 11, C_ABORT = 12, C_FIN = 13,
-       C_FAR = 16, C_BND = 17, C_NHOST = 24 /* read back by the host */,
+enum { C_SIDE = 0, C_GRID = 1, C_CONTACTS = 2 /*u64*/, C_CAND = 4 /*u64*/, C_HE = 6 /* half-edge slots handed out */,
+       C_LONG = 7 /* bodies with a long contact list */, C_FRONT = 8 /*3*/, C_ROUNDS = 11, C_ABORT = 12, C_FIN = 13, C_BAR = 14 /* grid barrier of prep_kernel */,
+       C_FAR = 16, C_BND = 17, C_T0 = 18 /* 3 x u64 globaltimer stamps: broad, narrow, prep */,
+       C_NHOST = 24,
        C_QHEAD = 32, C_QTAIL = 64, C_DONE = 96, C_NCOUNTERS = 128 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Opportunistic warp-aggregated append: the lanes that reach this call together reserve their output slots with ONE
+// atomic (same-address atomics retire at ~0.85 clk each at L2).  Returns the slot of the calling lane.
+__device__ __forceinline__ unsigned long long warp_reserve(unsigned long long* counter) {
+    const uint32_t mask = __activemask();
+    const uint32_t lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+__device__ __forceinline__ uint32_t warp_reserve32(uint32_t* counter) {
+    const uint32_t mask = __activemask();
+    const uint32_t lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
 
 }  // namespace tr
 
@@ -39,11 +68,11 @@ struct Collide {
     float cell = 1.f, inv_cell = 1.f, rmax_grid = 0.f;
     float origin[3] = {0, 0, 0};
     int bx = 2, by = 2, bz = 2;   // bits per axis of the wrapped cell key (x is the fastest digit)
-    bool may_have_side = true;    // some body is statically outside the grid (oversize / NaN extent)
     bool mixed = false;           // live boxes exist: they share the grid, extents include collider::size
     uint64_t cap_bodies = 0;      // arrays below sized for this many bodies
     uint64_t ncell_alloc = 0;
     uint64_t cap_contacts = 0;
+    bool cap_fixed = false;       // the caller set tr_world_params.max_contacts: never grown
 
     // per body
     uint32_t* keys = nullptr;        // K2 out: key, or sentinel 1<<(bx+by+bz) for non-grid bodies
@@ -59,44 +88,37 @@ struct Collide {
     float4* far_c = nullptr;         // their collider centres, same slots
     float4* bnd_c = nullptr;
     uint8_t* klass = nullptr;        // 0 dropped (mass<=0), 1 grid, 2 side list, 3 lost (non-finite centre), 4 far
-    uint32_t* row_start = nullptr;   // [N+1] dense: contacts with i == body are [row_start[b], row_start[b+1])
-    uint32_t* col_start = nullptr;   // [N+1] dense: column-order slots with j == body
-    uint32_t* body_cnt = nullptr;    // [N] per-body histogram scratch (self-cleaning)
+    uint32_t* body_cnt = nullptr;    // [N] contacts per body; self-cleaning (prep_kernel zeroes what it touched)
+    uint2* seg = nullptr;            // [N] {first half-edge slot, contacts} of every body in contact this step
+    uint32_t* long_list = nullptr;   // bodies whose contact list is long enough to be sorted by a CTA
 
     uint32_t* counters = nullptr;
-    uint32_t* h_counters = nullptr;  // pinned mirror (detection read-back)
-    uint32_t* h_rounds = nullptr;    // pinned: response wavefront count, fetched lazily
-    bool rounds_pending = false;
-    bool flow_pending = false;       // h_rounds holds the dataflow kernel's watchdog flag, not a round count
 
     // per contact
-    unsigned long long* ckeys = nullptr;      // (i<<32)|j, unsorted then sorted
-    unsigned long long* ckeys_alt = nullptr;
-    unsigned long long* colkeys = nullptr;    // column scatter scratch: (i<<32)|c in arrival order
-    uint32_t* colc = nullptr;                 // contact index per column slot
-    uint32_t* col_pos = nullptr;              // inverse of colc
+    unsigned long long* ckeys = nullptr;      // (i<<32)|j in arrival order (sorted on the host when tr_read_contacts asks)
+    uint2* arank = nullptr;                   // arrival rank of the contact among its bodies' contacts {in i's list, in j's list}
+    uint2* he = nullptr;                      // [2 * cap] half edges {partner id, contact}, one segment per body
     uint32_t* dep = nullptr;
-    uint32_t* succ_i = nullptr;
-    uint32_t* succ_j = nullptr;
-    uint4* crec = nullptr;                    // packed {i, j, succ_i, succ_j} per contact (dataflow executor)
+    uint4* crec = nullptr;                    // packed {i, j, succ_i, succ_j} per contact
     uint2* cver = nullptr;                    // versions of bodies i and j that contact c must see (dataflow executor)
     struct tr_contact_geo* cgeo = nullptr;    // per contact: normal, inverse masses, restitution, static bits (tr::ContactGeo)
     struct tr_body_rec* brec = nullptr;       // per body: version-checked velocity + position record (tr::BodyRec)
-    uint32_t* frontier[2] = {nullptr, nullptr};
+    uint32_t* frontier[2] = {nullptr, nullptr};   // [0]: ready queue of the dataflow executor / first frontier; [1]: level-synchronous only
 
-    // K2-K3b as one CUDA graph (memset + 4 kernels): launch parameters only change when the
-    // buffers, the grid or the body count change, so the graph is re-captured only then
-    cudaGraphExec_t bp_graph = nullptr;
-    uint64_t bp_sig[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // the whole collision step as ONE CUDA graph per live pos_m buffer: launch parameters only change when the
+    // buffers, the grid, the body count or the executor choice change, so it is re-captured only then
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    uint64_t graph_sig[2] = {0, 0};
 
+    // what the host knows from the step records it has consumed so far
     uint64_t last_contacts = 0;
-    uint64_t last_grid = 0;
-    uint32_t last_side = 0;
-    uint32_t last_far = 0;        // far / boundary list sizes of the previous step (launch sizing)
-    uint32_t last_bnd = 0;
+    uint32_t last_side = 0, last_far = 0;
     int coop_blocks = 0;
+    int prep_blocks = 0;
     uint64_t prev_contacts = 0;   // last dataflow response: contacts and iterations of the longest worker
     uint32_t prev_rounds = 0;
+    std::vector<unsigned long long> host_contacts;   // tr_read_contacts: the last step's list, sorted on demand
+    bool host_contacts_valid = false;
 };
 
 namespace tr {

@@ -8,67 +8,31 @@ namespace tr {
 // ---------------------------------------------------------------------------------------
 // K6 preparation: dependency structure of the lexicographic Gauss-Seidel order
 // ---------------------------------------------------------------------------------------
-// The contact list is put into the reference's visiting order - lexicographic (i,j) - and into
-// "column" order (j, then i) with the same counting-sort machinery as the broad phase, keyed by
-// body id: histogram (RED) -> two-kernel scan -> scatter into the body's segment (atomicSub counts
-// the histogram back to zero) -> rank inside the segment.  The scans leave DENSE tables
-// row_start[N+1] / col_start[N+1], so "first / last contact of body b" is a lookup.
-__global__ void __launch_bounds__(256) chist_kernel(const unsigned long long* __restrict__ ckeys, uint32_t c_n, int shift,
-                                                    uint32_t* __restrict__ cnt) {
-    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < c_n) atomicAdd(&cnt[(uint32_t)(ckeys[c] >> shift)], 1u);
-}
-
-__global__ void __launch_bounds__(256) cscatter_row_kernel(const unsigned long long* __restrict__ ckeys, uint32_t c_n,
-                                                           const uint32_t* __restrict__ row_start, uint32_t* __restrict__ cnt,
-                                                           unsigned long long* __restrict__ tmp) {
-    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= c_n) return;
-    const unsigned long long k = ckeys[c];
-    const uint32_t i = (uint32_t)(k >> 32);
-    tmp[row_start[i] + atomicSub(&cnt[i], 1u) - 1u] = k;
-}
-
-// rows: ascending j inside body i's segment (j is unique inside a row)
-__global__ void __launch_bounds__(256) crank_row_kernel(const unsigned long long* __restrict__ tmp,
-                                                        const uint32_t* __restrict__ row_start, uint32_t c_n,
-                                                        unsigned long long* __restrict__ sorted) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= c_n) return;
-    const unsigned long long k = tmp[t];
-    const uint32_t i = (uint32_t)(k >> 32);
-    const uint32_t s = row_start[i], e = row_start[i + 1];
-    uint32_t rank = 0;
-    for (uint32_t u = s; u < e; ++u) rank += (tmp[u] < k) ? 1u : 0u;
-    sorted[s + rank] = k;
-}
-
-// columns: entry = (i << 32 | c) of the contact c = (i,j) in row order, scattered to body j's segment
-__global__ void __launch_bounds__(256) cscatter_col_kernel(const unsigned long long* __restrict__ ckeys, uint32_t c_n,
-                                                           const uint32_t* __restrict__ col_start, uint32_t* __restrict__ cnt,
-                                                           unsigned long long* __restrict__ tmp) {
-    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= c_n) return;
-    const unsigned long long k = ckeys[c];
-    const uint32_t j = (uint32_t)k;
-    tmp[col_start[j] + atomicSub(&cnt[j], 1u) - 1u] = (k & 0xFFFFFFFF00000000ull) | c;
-}
-
-__global__ void __launch_bounds__(256) crank_col_kernel(const unsigned long long* __restrict__ tmp,
-                                                        const unsigned long long* __restrict__ ckeys,
-                                                        const uint32_t* __restrict__ col_start, uint32_t c_n,
-                                                        uint32_t* __restrict__ colc, uint32_t* __restrict__ col_pos) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= c_n) return;
-    const unsigned long long e = tmp[t];
-    const uint32_t c = (uint32_t)e;
-    const uint32_t j = (uint32_t)ckeys[c];
-    const uint32_t s = col_start[j], en = col_start[j + 1];
-    uint32_t rank = 0;
-    for (uint32_t u = s; u < en; ++u) rank += (tmp[u] < e) ? 1u : 0u;   // ascending i (unique inside a column)
-    colc[s + rank] = c;
-    col_pos[c] = s + rank;
-}
+// The reference visits the contacts in lexicographic (i,j) order, i < j (main.cpp:674-675).  The
+// contacts of ONE body b in that order are its column entries (k,b), k < b, by ascending k, followed
+// by its row entries (b,j), j > b, by ascending j - i.e. simply ALL its contacts by ascending PARTNER
+// id.  So the dependency structure is one sort of the 2C half edges (body, partner, contact) by
+// (body, partner): contact c may run when the predecessor half edge of both its bodies has run.
+// Nothing needs the contact list itself in sorted order (tr_read_contacts sorts on the host).
+//
+// prep_kernel does that sort as ONE persistent kernel with a grid barrier between its phases, sized by
+// the contact count on the device (no host round trip between detection and response):
+//   A  count    r = atomicAdd(body_cnt[b], 1) for both bodies of every contact: degree + arrival rank
+//   B  alloc    the half edge that arrived first at a body reserves the body's segment (warp-aggregated
+//               bump allocation); bodies with more than PREP_SHORT contacts go on the long list
+//   C  scatter  half edge {partner, contact} -> segment[arrival rank]; body_cnt counted back to zero
+//   D  sort     long segments only: one CTA per segment, bitonic by partner id (shared memory up to
+//               2048 entries, in place in global memory beyond) - a hub body with L contacts costs
+//               O(L log^2 L), not the O(L^2) of ranking every entry against every other
+//   E  deps     per contact: rank among / successor in the lists of both bodies (linear scan of a short
+//               unsorted segment, binary search in a sorted long one) -> dep[c], {i, j, succ_i, succ_j},
+//               expected record versions, contact constants, version-0 body records, ready queue.
+// An isStatic body is never changed by a contact (main.cpp:725-741), so its contacts do not order each
+// other: no dependency edge, no version bump, no write-back through a static body - everything resting
+// on one static slab runs concurrently instead of one after the other.
+constexpr uint32_t PREP_SHORT = 24;        // segments up to this length are ranked by linear scans
+constexpr int PREP_THREADS = 256;
+constexpr uint32_t PREP_SMEM_SORT = 2048;  // long segments up to this many entries are sorted in shared memory
 
 // Body b's contacts in sweep order are: its column entries (k,b) by ascending k, then its
 // row entries (b,j) by ascending j.  pred/succ below are the neighbours of contact c in the
@@ -145,50 +109,218 @@ __device__ __forceinline__ bool ld_body(const BodyRec* p, uint32_t want, float4&
     return r3 == want && r7 == want;
 }
 
-__global__ void __launch_bounds__(256) deps_kernel(const unsigned long long* __restrict__ ckeys,
-                                                   const uint32_t* __restrict__ colc, const uint32_t* __restrict__ col_pos,
-                                                   const uint32_t* __restrict__ row_start,
-                                                   const uint32_t* __restrict__ col_start, uint32_t c_n,
-                                                   uint32_t* __restrict__ dep, uint32_t* __restrict__ succ_i,
-                                                   uint32_t* __restrict__ succ_j, uint4* __restrict__ crec,
-                                                   uint32_t* __restrict__ frontier0, uint32_t* counters, int ready_counter,
-                                                   const float4* __restrict__ pos_m, const float4* __restrict__ vel_rest,
-                                                   const float4* __restrict__ center_r, const float4* __restrict__ half_ext,
-                                                   const uint8_t* __restrict__ flags, BodyRec* __restrict__ brec,
-                                                   uint2* __restrict__ cver, ContactGeo* __restrict__ cgeo) {
-    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= c_n) return;
-    unsigned long long k = ckeys[c];
-    uint32_t i = (uint32_t)(k >> 32), j = (uint32_t)k;
-    uint32_t t = col_pos[c];
-    // contacts applied to each body before this one: column entries of i + earlier row entries; earlier column entries of j
-    const uint32_t ei = (col_start[i + 1] - col_start[i]) + (c - row_start[i]);
-    const uint32_t ej = t - col_start[j];
-    uint32_t d = (ei ? 1u : 0u) + (ej ? 1u : 0u);
-    dep[c] = d;
-    const uint32_t si = (c + 1 < row_start[i + 1]) ? c + 1 : EMPTY;
-    uint32_t sj;
-    if (t + 1 < col_start[j + 1]) sj = colc[t + 1];
-    else sj = (row_start[j + 1] > row_start[j]) ? row_start[j] : EMPTY;  // j's first row entry follows its last column entry
-    succ_i[c] = si;
-    succ_j[c] = sj;
-    crec[c] = make_uint4(i, j, si, sj);
-    if (brec) {                                   // dataflow executors: expected versions, version-0 records, constants
-        cver[c] = make_uint2(ei, ej);
-        const float4 vi = vel_rest[i], vj = vel_rest[j], pi = pos_m[i], pj = pos_m[j];
-        if (ei == 0) st_body(brec + i, vi, pi, 0u);
-        if (ej == 0) st_body(brec + j, vj, pj, 0u);
-        const uint8_t fi = flags[i], fj = flags[j];
+struct PrepArgs {
+    const unsigned long long* ckeys;
+    unsigned long long cap;
+    uint32_t* counters;
+    uint32_t* ctl;
+    uint32_t* body_cnt;
+    uint2* seg;
+    uint2* arank;
+    uint2* he;
+    uint32_t* long_list;
+    uint32_t* dep;
+    uint4* crec;
+    uint2* cver;
+    ContactGeo* cgeo;
+    BodyRec* brec;          // NULL for the level-synchronous executor
+    uint32_t* queue;
+    int ready_counter;      // C_QTAIL (dataflow) or C_FRONT (level-synchronous)
+    const float4* pos_m;
+    const float4* vel_rest;
+    const float4* center_r;
+    const float4* half_ext;
+    const uint8_t* flags;
+};
+
+// all CTAs of prep_kernel are resident (the host sizes the grid from the occupancy API): a counter barrier
+__device__ __forceinline__ void prep_barrier(uint32_t* bar, uint32_t& phase) {
+    __syncthreads();
+    ++phase;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        const uint32_t want = phase * gridDim.x;
+        while (*((volatile uint32_t*)bar) < want) __nanosleep(40);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// ascending bitonic network (flip + shear steps: virtual +inf padding beyond len never moves down)
+template <typename Get, typename Swap>
+__device__ __forceinline__ void bitonic_steps(uint32_t len, Get key_at, Swap swap_at) {
+    uint32_t pow2 = 1;
+    while (pow2 < len) pow2 <<= 1;
+    for (uint32_t k = 2; k <= pow2; k <<= 1) {
+        for (uint32_t t = threadIdx.x; t < pow2 / 2; t += blockDim.x) {       // flip: i <-> block_end - offset
+            const uint32_t g = t / (k / 2), r = t % (k / 2);
+            const uint32_t i = g * k + r, l = g * k + (k - 1 - r);
+            if (l < len && key_at(i) > key_at(l)) swap_at(i, l);
+        }
+        __syncthreads();
+        for (uint32_t j = k / 4; j >= 1; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < pow2 / 2; t += blockDim.x) {
+                const uint32_t g = t / j, r = t % j;
+                const uint32_t i = g * 2 * j + r, l = i + j;
+                if (l < len && key_at(i) > key_at(l)) swap_at(i, l);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// position of `partner` among the half edges of one body: rank (number of smaller partners) and the
+// contact of the next larger partner (EMPTY if none)
+__device__ __forceinline__ void segment_lookup(const uint2* __restrict__ he, const uint2 sg, uint32_t partner, uint32_t& rank,
+                                               uint32_t& succ) {
+    const uint2* p = he + sg.x;
+    if (sg.y <= PREP_SHORT) {
+        uint32_t r = 0, best = EMPTY, bestc = EMPTY;
+        for (uint32_t k = 0; k < sg.y; ++k) {
+            const uint2 e = __ldcg(p + k);   // written by other SMs earlier in this kernel: L2, not L1
+            r += e.x < partner ? 1u : 0u;
+            if (e.x > partner && e.x < best) {   // partner ids are < 2^30, so EMPTY works as +inf
+                best = e.x;
+                bestc = e.y;
+            }
+        }
+        rank = r;
+        succ = bestc;
+    } else {
+        uint32_t lo = 0, hi = sg.y;              // sorted by phase D: first entry with partner id >= partner
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldcg(p + mid).x < partner) lo = mid + 1;
+            else hi = mid;
+        }
+        rank = lo;
+        succ = lo + 1 < sg.y ? __ldcg(p + lo + 1).y : EMPTY;
+    }
+}
+
+__global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
+    __shared__ uint2 s_sort[PREP_SMEM_SORT];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<unsigned long long*>(a.counters + C_T0 + 4) = globaltimer_ns();
+    if (a.ctl[CTL_ABORT] != 0) return;                     // an earlier step overflowed: the host has to re-run from there
+    const unsigned long long found = *reinterpret_cast<const unsigned long long*>(a.counters + C_CONTACTS);
+    if (found > a.cap) {
+        // more contacts than the buffers hold: no response at all, and no later step may touch the state
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.ctl[CTL_ABORT] = a.ctl[CTL_SEQ] + 1u;
+        return;
+    }
+    const uint32_t cn = (uint32_t)found;
+    if (cn == 0) return;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    uint32_t phase = 0;
+    uint32_t* bar = a.counters + C_BAR;
+
+    // ---- A: degrees + arrival ranks (and an EMPTY ready queue)
+    for (uint32_t c = gtid; c < cn; c += gsize) {
+        const unsigned long long k = a.ckeys[c];
+        const uint32_t i = (uint32_t)(k >> 32), j = (uint32_t)k;
+        a.arank[c] = make_uint2(atomicAdd(&a.body_cnt[i], 1u), atomicAdd(&a.body_cnt[j], 1u));
+        a.queue[c] = EMPTY;
+    }
+    prep_barrier(bar, phase);
+
+    // ---- B: segment allocation by the first arrival at each body
+    for (uint32_t c0 = blockIdx.x * blockDim.x; c0 < cn; c0 += gsize) {   // whole warps stay in the loop (shuffles below)
+        const uint32_t c = c0 + threadIdx.x;
+        uint32_t i = 0, j = 0, li = 0, lj = 0;
+        if (c < cn) {
+            const unsigned long long k = a.ckeys[c];
+            const uint2 r = a.arank[c];
+            i = (uint32_t)(k >> 32);
+            j = (uint32_t)k;
+            if (r.x == 0) li = __ldcg(&a.body_cnt[i]);
+            if (r.y == 0) lj = __ldcg(&a.body_cnt[j]);
+        }
+        const uint32_t need = li + lj, lane = threadIdx.x & 31;
+        uint32_t incl = need;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += y;
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        uint32_t base = 0;
+        if (lane == 31 && total) base = atomicAdd(&a.counters[C_HE], total);
+        base = __shfl_sync(0xFFFFFFFFu, base, 31) + (incl - need);
+        if (li) {
+            a.seg[i] = make_uint2(base, li);
+            if (li > PREP_SHORT) a.long_list[atomicAdd(&a.counters[C_LONG], 1u)] = i;
+            base += li;
+        }
+        if (lj) {
+            a.seg[j] = make_uint2(base, lj);
+            if (lj > PREP_SHORT) a.long_list[atomicAdd(&a.counters[C_LONG], 1u)] = j;
+        }
+    }
+    prep_barrier(bar, phase);
+
+    // ---- C: half edges into their segments; the histogram counts itself back to zero
+    for (uint32_t c = gtid; c < cn; c += gsize) {
+        const unsigned long long k = a.ckeys[c];
+        const uint32_t i = (uint32_t)(k >> 32), j = (uint32_t)k;
+        const uint2 r = a.arank[c];
+        a.he[__ldcg(&a.seg[i]).x + r.x] = make_uint2(j, c);
+        a.he[__ldcg(&a.seg[j]).x + r.y] = make_uint2(i, c);
+        if (r.x == 0) a.body_cnt[i] = 0;
+        if (r.y == 0) a.body_cnt[j] = 0;
+    }
+    prep_barrier(bar, phase);
+
+    // ---- D: long segments sorted by partner id, one CTA each
+    const uint32_t nlong = *((volatile uint32_t*)&a.counters[C_LONG]);
+    for (uint32_t l = blockIdx.x; l < nlong; l += gridDim.x) {
+        const uint2 sg = __ldcg(&a.seg[__ldcg(&a.long_list[l])]);
+        uint2* p = a.he + sg.x;
+        if (sg.y <= PREP_SMEM_SORT) {
+            for (uint32_t k = threadIdx.x; k < sg.y; k += blockDim.x) s_sort[k] = __ldcg(p + k);
+            __syncthreads();
+            bitonic_steps(sg.y, [&](uint32_t x) { return s_sort[x].x; },
+                          [&](uint32_t x, uint32_t y) { const uint2 t = s_sort[x]; s_sort[x] = s_sort[y]; s_sort[y] = t; });
+            for (uint32_t k = threadIdx.x; k < sg.y; k += blockDim.x) p[k] = s_sort[k];
+            __syncthreads();
+        } else {
+            bitonic_steps(sg.y, [&](uint32_t x) { return __ldcg(&p[x]).x; },
+                          [&](uint32_t x, uint32_t y) { const uint2 t = __ldcg(&p[x]); const uint2 u = __ldcg(&p[y]); __stcg(&p[x], u); __stcg(&p[y], t); });
+        }
+    }
+    if (nlong) prep_barrier(bar, phase);           // nlong is the same for every CTA
+
+    // ---- E: dependencies, versions, constants, ready queue
+    for (uint32_t c = gtid; c < cn; c += gsize) {
+        const unsigned long long k = a.ckeys[c];
+        const uint32_t i = (uint32_t)(k >> 32), j = (uint32_t)k;
+        uint32_t ri, rj, si, sj;
+        segment_lookup(a.he, __ldcg(&a.seg[i]), j, ri, si);
+        segment_lookup(a.he, __ldcg(&a.seg[j]), i, rj, sj);
+        const uint8_t fi = a.flags[i], fj = a.flags[j];
+        const float4 vi = a.vel_rest[i], vj = a.vel_rest[j], pi = a.pos_m[i], pj = a.pos_m[j];
+        if (a.brec) {                                  // version-0 records, written once per body
+            if (ri == 0) st_body(a.brec + i, vi, pi, 0u);
+            if (rj == 0) st_body(a.brec + j, vj, pj, 0u);
+        }
+        // contacts applied to each body before this one; a static body is never changed, so nothing orders its contacts
+        const uint32_t ei = (fi & F_STATIC) ? 0u : ri, ej = (fj & F_STATIC) ? 0u : rj;
+        if (fi & F_STATIC) si = EMPTY;
+        if (fj & F_STATIC) sj = EMPTY;
+        const uint32_t d = (ei ? 1u : 0u) + (ej ? 1u : 0u);
+        a.dep[c] = d;
+        a.crec[c] = make_uint4(i, j, si, sj);
+        a.cver[c] = make_uint2(ei, ej);
         ContactGeo g;
-        contact_normal(fi, fj, center_r[i], center_r[j], half_ext, i, j, g.nx, g.ny, g.nz);
+        contact_normal(fi, fj, a.center_r[i], a.center_r[j], a.half_ext, i, j, g.nx, g.ny, g.nz);
         g.ima = __fdiv_rn(1.0f, pi.w);
         g.imb = __fdiv_rn(1.0f, pj.w);
         g.den = __fadd_rn(g.ima, g.imb);
         g.e = (vj.w < vi.w) ? vj.w : vi.w;               // std::min(a.rest, b.rest)
         g.bits = ((fi & F_STATIC) ? 1u : 0u) | ((fj & F_STATIC) ? 2u : 0u);
-        cgeo[c] = g;
+        a.cgeo[c] = g;
+        if (d == 0) a.queue[warp_reserve32(&a.counters[a.ready_counter])] = c;
     }
-    if (d == 0) frontier0[atomicAdd(&counters[ready_counter], 1u)] = c;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -202,9 +334,10 @@ struct RespArgs {
     const uint8_t* flags;
 };
 
-__device__ __forceinline__ void respond(const RespArgs& a, uint32_t i, uint32_t j) {
-    const uint8_t fi = a.flags[i], fj = a.flags[j];
-    const float4 ci = a.center_r[i], cj = a.center_r[j];
+// One contact on VALUES: normal from the collider centres (main.cpp:701-706), approach test exactly as written
+// (main.cpp:714), impulse and positional nudge (main.cpp:716-741).  v*.w = restitution, p*.w = mass.
+__device__ __forceinline__ void respond_values(uint8_t fi, uint8_t fj, const float4 ci, const float4 cj, const float4 hi, const float4 hj,
+                                               float4& vi, float4& vj, float4& pi, float4& pj) {
     float nx, ny, nz;
     if ((fi & F_SPHERE) && (fj & F_SPHERE)) {
         // normalize(b.center - a.center), main.cpp:703 + 211-223
@@ -219,7 +352,6 @@ __device__ __forceinline__ void respond(const RespArgs& a, uint32_t i, uint32_t 
         }
     } else {
         // calculateAABBNormal, main.cpp:622-638
-        const float4 hi = a.half_ext[i], hj = a.half_ext[j];
         float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
         float ox = __fsub_rn(__fadd_rn(hi.x, hj.x), fabsf(dx));
         float oy = __fsub_rn(__fadd_rn(hi.y, hj.y), fabsf(dy));
@@ -229,11 +361,6 @@ __device__ __forceinline__ void respond(const RespArgs& a, uint32_t i, uint32_t 
         else if (oy < oz) ny = dy > 0 ? 1.0f : -1.0f;
         else nz = dz > 0 ? 1.0f : -1.0f;
     }
-    // L2 loads: these were written by other SMs in earlier wavefronts.  Positions are fetched in
-    // the same round trip (needed only when the pair is not skipped, but a second dependent trip
-    // would sit on the critical path of the ordered replay).
-    float4 vi = __ldcg(a.vel_rest + i), vj = __ldcg(a.vel_rest + j);
-    float4 pi = __ldcg(a.pos_m + i), pj = __ldcg(a.pos_m + j);
     float rvx = __fsub_rn(vi.x, vj.x), rvy = __fsub_rn(vi.y, vj.y), rvz = __fsub_rn(vi.z, vj.z);
     float vn = dot3_rn(rvx, rvy, rvz, nx, ny, nz);
     if (vn > 0) return;                                  // main.cpp:714 (as written)
@@ -251,8 +378,6 @@ __device__ __forceinline__ void respond(const RespArgs& a, uint32_t i, uint32_t 
         pi.x = __fsub_rn(pi.x, __fmul_rn(cx, ima));
         pi.y = __fsub_rn(pi.y, __fmul_rn(cy, ima));
         pi.z = __fsub_rn(pi.z, __fmul_rn(cz, ima));
-        a.vel_rest[i] = vi;
-        a.pos_m[i] = pi;
     }
     if (!(fj & F_STATIC)) {
         vj.x = __fadd_rn(vj.x, __fmul_rn(ix, imb));
@@ -261,6 +386,28 @@ __device__ __forceinline__ void respond(const RespArgs& a, uint32_t i, uint32_t 
         pj.x = __fadd_rn(pj.x, __fmul_rn(cx, imb));
         pj.y = __fadd_rn(pj.y, __fmul_rn(cy, imb));
         pj.z = __fadd_rn(pj.z, __fmul_rn(cz, imb));
+    }
+}
+
+// the same contact on the SoA state (level-synchronous executor)
+__device__ __forceinline__ void respond(const RespArgs& a, uint32_t i, uint32_t j) {
+    const uint8_t fi = a.flags[i], fj = a.flags[j];
+    // L2 loads: these were written by other SMs in earlier wavefronts.  Positions are fetched in
+    // the same round trip (needed only when the pair is not skipped, but a second dependent trip
+    // would sit on the critical path of the ordered replay).
+    float4 vi = __ldcg(a.vel_rest + i), vj = __ldcg(a.vel_rest + j);
+    float4 pi = __ldcg(a.pos_m + i), pj = __ldcg(a.pos_m + j);
+    float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), hj = hi;
+    if (!((fi & F_SPHERE) && (fj & F_SPHERE))) {
+        hi = a.half_ext[i];
+        hj = a.half_ext[j];
+    }
+    respond_values(fi, fj, a.center_r[i], a.center_r[j], hi, hj, vi, vj, pi, pj);
+    if (!(fi & F_STATIC)) {
+        a.vel_rest[i] = vi;
+        a.pos_m[i] = pi;
+    }
+    if (!(fj & F_STATIC)) {
         a.vel_rest[j] = vj;
         a.pos_m[j] = pj;
     }
@@ -329,13 +476,16 @@ __device__ __forceinline__ bool respond_rec(const FlowArgs& a, uint32_t c, uint3
     // nobody reads the record of a body again after its last contact: back to the SoA state.  Only
     // x, y, z are written (8 + 4 bytes): the w components (restitution, mass) are already there, and
     // loading them to rebuild a float4 would park the store - and the atomics behind it - on an L2 round trip.
-    if (last_i) {
+    // (a static body is never changed: its record stays at version 0 for all its contacts, nothing to store)
+    if (g.bits & 1u) {
+    } else if (last_i) {
         store_xyz(a.vel_out + i, vi);
         store_xyz(a.pos_out + i, pi);
     } else {
         st_body(a.brec + i, vi, pi, want.x + 1u);
     }
-    if (last_j) {
+    if (g.bits & 2u) {
+    } else if (last_j) {
         store_xyz(a.vel_out + j, vj);
         store_xyz(a.pos_out + j, pj);
     } else {
@@ -346,11 +496,10 @@ __device__ __forceinline__ bool respond_rec(const FlowArgs& a, uint32_t c, uint3
 
 // Persistent cooperative kernel: one wavefront per round, grid-wide barrier between rounds.
 // counters[8 + r%3] is the size of round r's frontier.
-__global__ void __launch_bounds__(256) response_kernel(RespArgs a, const unsigned long long* __restrict__ ckeys,
-                                                       uint32_t* dep, const uint32_t* __restrict__ succ_i,
-                                                       const uint32_t* __restrict__ succ_j, uint32_t* f0, uint32_t* f1,
-                                                       uint32_t* counters) {
+__global__ void __launch_bounds__(256) response_kernel(RespArgs a, const uint4* __restrict__ crec, uint32_t* dep, uint32_t* f0,
+                                                       uint32_t* f1, uint32_t* counters, const uint32_t* ctl) {
     cg::grid_group grid = cg::this_grid();
+    if (ctl[CTL_ABORT] != 0) return;   // uniform: set by an earlier kernel
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t gsize = gridDim.x * blockDim.x;
     uint32_t round = 0;
@@ -363,13 +512,11 @@ __global__ void __launch_bounds__(256) response_kernel(RespArgs a, const unsigne
         if (gtid == 0) counters[8 + (round + 2) % 3] = 0;
         for (uint32_t idx = gtid; idx < n; idx += gsize) {
             const uint32_t c = __ldcg(fin + idx);
-            const unsigned long long k = ckeys[c];
-            respond(a, (uint32_t)(k >> 32), (uint32_t)k);
+            const uint4 k = crec[c];
+            respond(a, k.x, k.y);
             __threadfence();
-            uint32_t s = succ_i[c];
-            if (s != EMPTY && atomicSub(&dep[s], 1u) == 1u) fout[atomicAdd(cnt_out, 1u)] = s;
-            s = succ_j[c];
-            if (s != EMPTY && atomicSub(&dep[s], 1u) == 1u) fout[atomicAdd(cnt_out, 1u)] = s;
+            if (k.z != EMPTY && atomicSub(&dep[k.z], 1u) == 1u) fout[atomicAdd(cnt_out, 1u)] = k.z;
+            if (k.w != EMPTY && atomicSub(&dep[k.w], 1u) == 1u) fout[atomicAdd(cnt_out, 1u)] = k.w;
         }
         grid.sync();
         ++round;
@@ -387,7 +534,8 @@ __global__ void __launch_bounds__(256) response_kernel(RespArgs a, const unsigne
 // (BodyRec above); the releasing side stores the records and decrements the successors' dependency
 // counters WITHOUT a fence in between, the side that sees a counter reach zero (or its queue slot
 // fill) loads the records from L2 and polls until both carry the versions the contact expects.
-// A spin budget (C_ABORT) guarantees termination even if the graph were broken.
+// A spin budget (C_ABORT) guarantees termination even if the graph were broken: an idle worker gives up after
+// FLOW_SPIN_LIMIT polls (~1 s) during which the finished count did not move (busy workers publish it every 256 contacts).
 constexpr uint32_t FLOW_SPIN_LIMIT = 1u << 21;
 
 // LANES = active lanes per warp.  1: a worker is a single lane (the other 31 exit at once), its hop
@@ -398,12 +546,15 @@ constexpr uint32_t FLOW_SPIN_LIMIT = 1u << 21;
 // shallow graphs.
 template <int LANES>
 __global__ void __launch_bounds__(128) response_flow_kernel(FlowArgs a, const uint4* __restrict__ crec, uint32_t* dep,
-                                                            uint32_t* q, uint32_t c_n, uint32_t* counters, uint32_t idle_ns) {
+                                                            uint32_t* q, const uint32_t* ctl, uint32_t* counters, uint32_t idle_ns) {
     if ((threadIdx.x & 31) >= LANES) return;
+    if (ctl[CTL_ABORT] != 0) return;               // contact buffer overflow in this or an earlier step: no response
+    const uint32_t c_n = counters[C_CONTACTS];     // <= capacity < 2^32 here (prep_kernel checked)
+    if (c_n == 0) return;
     constexpr uint32_t LMASK = LANES == 32 ? 0xFFFFFFFFu : ((1u << LANES) - 1u);
     volatile uint32_t* vq = q;
     volatile uint32_t* vc = counters;
-    uint32_t cur = EMPTY, slot = EMPTY, spins = 0, mine = 0;
+    uint32_t cur = EMPTY, slot = EMPTY, spins = 0, mine = 0, seen_done = 0;
     uint4 rec = make_uint4(0, 0, EMPTY, EMPTY);    // {i, j, succ_i, succ_j} of `cur`, loaded one iteration early
     bool alive = true;
     uint32_t iters = 0;
@@ -474,7 +625,10 @@ __global__ void __launch_bounds__(128) response_flow_kernel(FlowArgs a, const ui
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(a.brec + n2.x));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(a.brec + n2.y));
             }
-            ++mine;
+            if (++mine >= 256u) {                 // progress for the watchdog of the idle workers (and the finished count)
+                if (atomicAdd(&counters[C_DONE], mine) + mine >= c_n) vc[C_FIN] = 1u;
+                mine = 0;
+            }
             uint32_t next = EMPTY;
             // both ready: keep the successor along body j (the column side), queue the one along body i -
             // 5 % faster on the packed scene than the other way round (1.27 against 1.33 ms)
@@ -517,6 +671,9 @@ __global__ void __launch_bounds__(128) response_flow_kernel(FlowArgs a, const ui
                     spins = 0;
                 } else if ((++spins & 15u) == 0 && (vc[C_FIN] || vc[C_ABORT])) {
                     alive = false;                // termination is polled every 16th idle iteration
+                } else if ((spins & 4095u) == 0 && vc[C_DONE] != seen_done) {
+                    seen_done = vc[C_DONE];       // the watchdog measures time WITHOUT progress, not time: a deep but
+                    spins = 0;                    // healthy chain (a line of a million touching spheres) must not trip it
                 } else if (spins > FLOW_SPIN_LIMIT) {
                     atomicExch(&counters[C_ABORT], 1u);
                     alive = false;
@@ -539,6 +696,38 @@ __global__ void __launch_bounds__(128) response_flow_kernel(FlowArgs a, const ui
     }
 #endif
     if ((threadIdx.x & 31) == 0) atomicMax(&counters[C_ROUNDS], iters);   // observability: longest warp
+}
+
+// Last kernel of a collision step: the step's record for the host (mapped pinned memory - the host reads it
+// after its next synchronisation, nothing waits for it), then the counters are zeroed for the next step.
+__global__ void __launch_bounds__(128) epilogue_kernel(uint32_t* counters, uint32_t* ctl, StepRecord* ring) {
+    if (threadIdx.x == 0) {
+        const uint32_t seq = ctl[CTL_SEQ];
+        StepRecord r;
+        r.flags = 0;
+        const unsigned long long found = *reinterpret_cast<const unsigned long long*>(counters + C_CONTACTS);
+        if (ctl[CTL_ABORT] == seq + 1u) r.flags |= 1u;            // this step overflowed the contact buffers
+        else if (ctl[CTL_ABORT] != 0) r.flags |= 4u;              // a step before it did: this one did nothing
+        if (counters[C_ABORT]) r.flags |= 2u;                     // dataflow watchdog
+        r.contacts_lo = (uint32_t)found;
+        r.contacts_hi = (uint32_t)(found >> 32);
+        r.side = counters[C_SIDE];
+        r.far = counters[C_FAR];
+        r.bnd = counters[C_BND];
+        r.grid = counters[C_GRID];
+        r.rounds = counters[C_ROUNDS];
+        r.long_segments = counters[C_LONG];
+        r.pad[0] = r.pad[1] = 0;
+        r.t[0] = *reinterpret_cast<const unsigned long long*>(counters + C_T0);
+        r.t[1] = *reinterpret_cast<const unsigned long long*>(counters + C_T0 + 2);
+        r.t[2] = *reinterpret_cast<const unsigned long long*>(counters + C_T0 + 4);
+        r.t[3] = globaltimer_ns();
+        r.seq = seq + 1u;
+        ring[seq % STEP_RING] = r;
+        ctl[CTL_SEQ] = seq + 1u;
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < (uint32_t)C_NCOUNTERS; k += blockDim.x) counters[k] = 0;
 }
 
 }  // namespace tr

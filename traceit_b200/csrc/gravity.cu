@@ -5,7 +5,7 @@
 // src/main.cpp:763-791,811.
 //
 // Shape of the kernel (sm_100a):
-//  * persistent CTAs (4 x 256 threads per SM) pull (target tile, source chunk) work items
+//  * persistent CTAs (2 x 256 threads per SM: 123 registers, no spills) pull (target tile, source chunk) work items
 //    from an atomic counter, so the 148 SMs stay evenly loaded for any N;
 //  * every thread owns GRAV_PAIRS pairs of targets held as packed f32x2 registers and
 //    runs the inner loop on FADD2/FMUL2/FFMA2 (two fp32 lanes per instruction: half the
@@ -109,6 +109,7 @@ struct GravArgs {
     float4* center_r;
     const uint8_t* flags;
     float4* force_out;      // optional: pair-gravity force per owned body (debug / parity)
+    const uint32_t* ctl;    // [CTL_ABORT] != 0: an earlier collision step overflowed its buffers, do nothing (world.cuh)
     StepConsts c;
     int fused;
 };
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(GRAV_THREADS, TR_GRAV_MINBLOCKS) gravity_kerne
 
     const uint32_t tid = threadIdx.x;
     const uint32_t total_items = a.n_tiles * a.n_chunks;
+    if (a.ctl[CTL_ABORT] != 0) return;   // every CTA sees the same value: it was set by an earlier kernel
 
     if (tid == 0) {
 #pragma unroll
@@ -311,9 +313,9 @@ __global__ void __launch_bounds__(GRAV_THREADS, TR_GRAV_MINBLOCKS) gravity_kerne
 // Standalone O(N) integrator, used when pair gravity is off (the live reference step).
 __global__ void __launch_bounds__(256) integrate_kernel(float4* pos_m, float4* vel_rest, float4* force,
                                                         const float2* drag, float4* center_r, const uint8_t* flags,
-                                                        uint32_t first, uint32_t count, StepConsts c) {
+                                                        uint32_t first, uint32_t count, StepConsts c, const uint32_t* ctl) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
+    if (t >= count || ctl[CTL_ABORT] != 0) return;
     uint32_t i = first + t;
     if (flags[i] & F_STATIONARY) return;
     float4 pm = pos_m[i];
@@ -372,6 +374,7 @@ int gravity_step(tr_world* w, const StepConsts& c, bool integrate_fused, float4*
     a.center_r = w->center_r;
     a.flags = w->flags;
     a.force_out = force_out;
+    a.ctl = w->d_ctl;
     a.c = c;
     a.fused = integrate_fused ? 1 : 0;
 
@@ -402,7 +405,7 @@ int integrate_only(tr_world* w, const StepConsts& c) {
     timer_begin(w, T_INTEGRATE, &t);
     unsigned blocks = (unsigned)((w->own_count + 255) / 256);
     integrate_kernel<<<blocks, 256, 0, w->stream>>>(w->pos_m[w->cur], w->vel_rest, w->force, w->drag, w->center_r,
-                                                    w->flags, (uint32_t)w->own_first, (uint32_t)w->own_count, c);
+                                                    w->flags, (uint32_t)w->own_first, (uint32_t)w->own_count, c, w->d_ctl);
     timer_end(w, &t);
     TR_CUDA(cudaGetLastError());
     w->stats.kernel_launches += 1;

@@ -5,7 +5,7 @@
 // Every operation is an explicitly rounded intrinsic (__fmul_rn / __fadd_rn / __fdiv_rn /
 // __fsqrt_rn): nvcc never contracts those into FMAs, so given the same inputs the result
 // is BIT-IDENTICAL to the reference compiled without FMA contraction (its CMakeLists.txt
-// sets no -march) - the property tests/test_gpu_step.py checks.
+// sets no -march) - the property tests/test_gpu_parity.py::test_integrator_bit_exact checks.
 #pragma once
 
 #include "world.cuh"

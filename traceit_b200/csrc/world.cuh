@@ -66,6 +66,31 @@ inline uint32_t grav_chunk_len(uint64_t n) {
     return (uint32_t)c;
 }
 
+// ---- device-side step bookkeeping --------------------------------------------------------
+// Nothing in a step waits for the host any more, so what the host used to read back between
+// kernels travels through two small blocks instead:
+//  * tr_world::d_ctl (device memory): [CTL_ABORT] = 0, or 1 + the sequence number of the step whose
+//    contact list overflowed its buffers.  EVERY kernel of every later step tests it first and
+//    returns at once, so the state stays exactly as that step's integration left it (detection reads
+//    only collider centres, which the response never writes) until the host, at the next
+//    synchronisation, grows the buffers and re-runs the response of that step and the steps after it.
+//    [CTL_SEQ] = number of collision steps completed on the device.
+//  * tr_world::h_ring (mapped pinned host memory, written by the last kernel of a collision step):
+//    one StepRecord per step - counts, the executor's statistics, globaltimer stamps of the phases.
+enum { CTL_ABORT = 0, CTL_SEQ = 1, CTL_WORDS = 8 };
+constexpr uint32_t STEP_RING = 256;
+struct StepRecord {
+    uint32_t seq;            // 1 + sequence number (0 = never written)
+    uint32_t flags;          // 1: contact buffer overflow (response skipped), 2: dataflow watchdog fired
+    uint32_t contacts_lo, contacts_hi;
+    uint32_t side, far, bnd, grid;
+    uint32_t rounds;         // iterations of the longest dataflow worker / wavefronts
+    uint32_t long_segments;  // bodies whose contact list was sorted by a CTA (more than PREP_SHORT contacts)
+    uint32_t pad[2];
+    unsigned long long t[4]; // %globaltimer (ns) at the start of: broad phase, narrow phase, K6 prep; end of the step
+};
+static_assert(sizeof(StepRecord) == 80, "layout shared with the host");
+
 struct StepConsts {
     float gx, gy, gz;
     float dt;
@@ -145,6 +170,19 @@ struct tr_world {
     // collision scratch (collide.cu)
     struct Collide* col = nullptr;
 
+    // device-side step bookkeeping (see StepRecord above)
+    uint32_t* d_ctl = nullptr;              // device: CTL_WORDS words
+    tr::StepRecord* h_ring = nullptr;       // mapped pinned host memory, STEP_RING records
+    tr::StepRecord* d_ring = nullptr;       // device alias of h_ring
+    uint32_t ring_consumed = 0;             // records folded into stats so far (== sequence number of the next one)
+    uint32_t coll_seq = 0;                  // collision steps enqueued so far
+    struct PendingStep {                    // one per step enqueued since the last synchronisation (overflow recovery)
+        uint32_t coll_seq;                  // sequence number of its collision pass (or ~0u)
+        int cur_after;                      // pos_m buffer index that is live after the step
+    };
+    std::vector<PendingStep> pending_steps;
+    bool in_recovery = false;
+
     // stats / timing
     tr_stats stats{};
     bool timing = false;
@@ -163,11 +201,17 @@ void timers_collect(tr_world* w);
 
 // gravity.cu
 int gravity_step(tr_world* w, const StepConsts& c, bool integrate_fused, float4* force_out);
+// api.cu: wait for the stream, fold the step records in, recover from a contact-buffer overflow
+int settle(tr_world* w);
 int integrate_only(tr_world* w, const StepConsts& c);
 int measure_fma_peak(int device, double* lane_ops_per_s, double* sm_clock_mhz);
 
 // collide.cu
 int collide_step(tr_world* w);
+int tiny_steps(tr_world* w, const StepConsts& c, int nsteps, bool* taken);
+int collide_consume_records(tr_world* w, bool* overflow, uint32_t* overflow_seq, uint64_t* found);
+int collide_grow_contacts(tr_world* w, uint64_t found);
+int collide_headroom(tr_world* w);
 int collide_free(tr_world* w);
 int collide_read_contacts(tr_world* w, int32_t* pairs, uint64_t cap, uint64_t* n);
 int collide_debug_grid(tr_world* w, uint32_t* keys, uint32_t* sorted_ids, uint64_t* m, float* cell, float* inv_cell,
