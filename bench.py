@@ -7,8 +7,10 @@
 One "step" = one pass of the hot path over the synthetic cloud the workload names.
 Rank 0 prints ONE JSON line.  `value` is ordered body-pair interactions per second over the
 whole job (N^2 per step; the self pair is included and contributes zero) with
-inputs resident in HBM; `e2e` is the same metric through the C-ABI host-buffer call
-(tr_step_host: host AoS -> device, step, device -> host AoS every step).
+inputs resident in HBM; `e2e` is the same metric through the C ABI with HOST buffers and the copies
+inside the timed region: tr_step_frame (the step's per-frame input, the external forces, host -> device;
+step; what the step changes - pos, vel, collider centre - device -> host), and `e2e_full_aos` through
+tr_step_host (the whole 92-byte descriptor of every body both ways every step).
 
 Workloads (BASELINE.json configs):
   cfg2  64K-body cloud: all-pairs gravity + drag + integration, collisions off
@@ -455,24 +457,37 @@ def measure(ctx: Ctx, name: str, n: int | None, steps: int, warmup: int, *, shar
     if nranks > 1:
         res["allgather_ms"] = st.allgather_ms / max(steps, 1)
 
-    # ---- e2e: the C-ABI host-buffer call, host<->device copies inside the timed region
+    # ---- e2e: through the C ABI with HOST buffers, host<->device copies inside the timed region, wall clock.
+    #   e2e           tr_step_frame: the per-frame call of a device-resident world - the step's per-frame INPUT (external
+    #                 forces, 12 B/body) goes up, what the step CHANGES (pos, vel, collider centre, 36 B/body) comes down
+    #   e2e_full_aos  tr_step_host: the whole 92-byte descriptor of every body up AND down every step (round 1's e2e)
     if want_e2e:
-        host = world.read_bodies(own_first, own_count)
-        world.step_host(host, 1)          # warm the staging buffers
-        world.step_host(host, 1)          # (second call page-locks the caller's buffer in place)
-        if sharded:
-            ctx.barrier()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            world.step_host(host, 1)
-        if sharded:
-            ctx.barrier()
-        dt = time.perf_counter() - t0
-        dt = ctx.max_over_ranks(dt) if sharded else dt
+        def timed(call):
+            call()
+            call()                        # (the second call page-locks the caller's buffers in place)
+            if sharded:
+                ctx.barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                call()
+            if sharded:
+                ctx.barrier()
+            dt = time.perf_counter() - t0
+            return ctx.max_over_ranks(dt) if sharded else dt
+
+        frame = np.zeros(own_count, dtype=tr.FRAME_DTYPE)
+        forces = np.zeros((own_count, 3), dtype=np.float32)
+        dt = timed(lambda: world.step_frame(frame, forces, 1))
         res["e2e"] = {"value": pair_visits * steps / dt, "unit": res["unit"],
-                      "h2d_bytes_per_step": int(own_count) * 92, "d2h_bytes_per_step": int(own_count) * 92,
+                      "h2d_bytes_per_step": int(own_count) * 12, "d2h_bytes_per_step": int(own_count) * 36,
                       "ms_per_step": dt / steps * 1e3, "steps_per_s": steps / dt,
-                      "api": "tr_step_host (AoS tr_body_desc in/out per step)"}
+                      "api": "tr_step_frame (per-body external force in, pos/vel/centre out, every step)"}
+        host = world.read_bodies(own_first, own_count)
+        dt = timed(lambda: world.step_host(host, 1))
+        res["e2e_full_aos"] = {"value": pair_visits * steps / dt, "unit": res["unit"],
+                               "h2d_bytes_per_step": int(own_count) * 92, "d2h_bytes_per_step": int(own_count) * 92,
+                               "ms_per_step": dt / steps * 1e3, "steps_per_s": steps / dt,
+                               "api": "tr_step_host (AoS tr_body_desc in/out per step)"}
     world.close()
     return res
 
@@ -609,7 +624,8 @@ def main():
                    "l2": "flushed between timed steps (256 MB memset, outside the per-step events)" if ctx.flush_buf is not None else "not flushed",
                    "timing": "sum of per-step CUDA-event intervals on the launching stream, max over ranks",
                    "interaction": main_res["interaction"]},
-        "clocks": main_res.get("clocks"), "e2e": main_res.get("e2e"), "gpu_launches": main_res["gpu_launches"],
+        "clocks": main_res.get("clocks"), "e2e": main_res.get("e2e"), "e2e_full_aos": main_res.get("e2e_full_aos"),
+        "gpu_launches": main_res["gpu_launches"],
         "roofline": main_res.get("roofline"), "cpu_baseline": cpu,
         "wall_ms_per_step_incl_flush": main_res["wall_ms_per_step_incl_flush"], "secondary": secondary,
     }

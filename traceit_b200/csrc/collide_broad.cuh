@@ -83,9 +83,17 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ ce
 }
 
 // K3b: one record per grid body into its cell's segment; counting the histogram back down leaves it
-// zeroed for the next step.  The record carries everything the narrow phase reads about a body -
-// centre + radius, id|flags, AABB half extents - in ONE 32-byte sector written by one 256-bit store
-// (SASS STG.E.ENL2.256) and read back by one 256-bit load, so nothing is gathered by id afterwards.
+// zeroed for the next step.  The record carries everything the narrow phase reads about a body, so nothing
+// is gathered by id afterwards.  Two layouts:
+//   mixed worlds (boxes in the grid)  ONE 32-byte sector: centre + radius, id|flags, AABB half extents, written
+//                                     by one 256-bit store (SASS STG.E.ENL2.256) and read back by one 256-bit load;
+//   compact (all-sphere worlds,       20 bytes in two arrays carved out of the same buffer: float4 centre + radius
+//   TR_COMPACT_RECS=1 only)           (all the sphere predicate reads: a candidate costs a 128-bit load, half the LSU
+//                                     wavefronts of the 256-bit one) and the 32-bit id|flags word.  Measured at 1M:
+//                                     narrow phase 45.7 -> 40.4 us (random cloud) / 77.6 -> 74.6 us (pack), but the two
+//                                     partial-sector stores of K3b cost the random cloud's broad phase 34.3 -> 46.2 us
+//                                     (pack: 23.7 -> 22.6 us): a net loss wherever body ids are not spatially coherent,
+//                                     hence off by default.
 struct __align__(32) SlotRec {
     float4 c;              // collider centre, radius
     uint32_t val;          // id | BOX_BIT | STATIC_BIT
@@ -121,31 +129,46 @@ __global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict
                                                       const uint8_t* __restrict__ flags, const float4* __restrict__ center_r,
                                                       const float4* __restrict__ half_ext,   // NULL unless boxes are in the grid
                                                       uint32_t n, const uint32_t* __restrict__ cell_start,
-                                                      uint32_t* __restrict__ cell_count, SlotRec* __restrict__ recs) {
+                                                      uint32_t* __restrict__ cell_count, SlotRec* __restrict__ recs,
+                                                      uint32_t* __restrict__ rec_val /* all-sphere layout: id|flags array; NULL = 32-byte records */) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t key = keys[i];
     if (key >= sentinel) return;          // side-list, far, lost or dropped body
     const float4 c = center_r[i];
-    float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (half_ext) h = half_ext[i];
     const uint32_t val = pack_val(i, flags[i]);
     const uint32_t old = atomicSub(&cell_count[key], 1u);
-    st_rec(recs + (cell_start[key] + old - 1u), c, val, h);
+    const uint32_t slot = cell_start[key] + old - 1u;
+    if (rec_val) {
+        reinterpret_cast<float4*>(recs)[slot] = c;
+        rec_val[slot] = val;
+    } else {
+        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (half_ext) h = half_ext[i];
+        st_rec(recs + slot, c, val, h);
+    }
+}
+
+// centre + radius / id|flags of the body in slot u, either layout
+__device__ __forceinline__ float4 rec_center(const SlotRec* recs, const uint32_t* rec_val, uint32_t u) {
+    return rec_val ? reinterpret_cast<const float4*>(recs)[u] : recs[u].c;
+}
+__device__ __forceinline__ uint32_t rec_idflags(const SlotRec* recs, const uint32_t* rec_val, uint32_t u) {
+    return rec_val ? rec_val[u] : recs[u].val;
 }
 
 // K4 (on demand): the stable (key,id) order.  The rank of a body inside its cell is the number of
 // co-occupants with a smaller id.
-__global__ void __launch_bounds__(256) canon_kernel(const SlotRec* __restrict__ recs, const uint32_t* __restrict__ cell_start,
-                                                    GridParams g, const uint32_t* __restrict__ counters,
-                                                    uint32_t* __restrict__ sorted_ids) {
+__global__ void __launch_bounds__(256) canon_kernel(const SlotRec* __restrict__ recs, const uint32_t* __restrict__ rec_val,
+                                                    const uint32_t* __restrict__ cell_start, GridParams g,
+                                                    const uint32_t* __restrict__ counters, uint32_t* __restrict__ sorted_ids) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= counters[C_GRID]) return;
-    const uint32_t key = cell_key(recs[t].c, g);
-    const uint32_t id = recs[t].val & ID_MASK;
+    const uint32_t key = cell_key(rec_center(recs, rec_val, t), g);
+    const uint32_t id = rec_idflags(recs, rec_val, t) & ID_MASK;
     const uint32_t s = cell_start[key], e = cell_start[key + 1];
     uint32_t rank = 0;
-    for (uint32_t u = s; u < e; ++u) rank += ((recs[u].val & ID_MASK) < id) ? 1u : 0u;
+    for (uint32_t u = s; u < e; ++u) rank += ((rec_idflags(recs, rec_val, u) & ID_MASK) < id) ? 1u : 0u;
     sorted_ids[s + rank] = id;
 }
 
@@ -179,17 +202,25 @@ __device__ __forceinline__ void emit_pair(unsigned long long* out, unsigned long
 //            candidate's record by one 256-bit load, exact predicate; every lane busy.
 // Hits are staged in a per-warp buffer and written out with ONE atomic per flush (same-address atomics
 // retire at ~0.85 clk each at L2: emitting from inside the loop was the packed narrow phase in round 1).
-// The 2 of 2^bx cells per row at the x edges, whose windows wrap, keep the lane-serial path (narrow_edge).
+// The 2 of 2^bx cells per row at the x edges, whose three-cell runs wrap around the row end, simply have two
+// windows per row instead of one (a lane-serial special path for them - 1.6 % of the bodies, one active lane
+// per warp - was measured at 27 % of the kernel's executed instructions).
 constexpr int NARROW_THREADS = 128;
 constexpr int NARROW_WARPS = NARROW_THREADS / 32;
-constexpr int NARROW_LIST = 640;     // (candidate, owner) pairs per warp and round: 20 per lane (mean 7 sparse, 14.5 packed)
-constexpr int NARROW_STAGE = 128;    // staged hits per warp
+constexpr int NARROW_LIST = 512;     // (candidate, owner) pairs per warp and round: 16 per lane (mean 7 sparse, 14.5 packed)
+constexpr int NARROW_STAGE = 96;     // staged hits per warp
+#ifndef TR_NARROW_UNROLL
+#define TR_NARROW_UNROLL 2
+#endif
+constexpr int NARROW_UNROLL = TR_NARROW_UNROLL;   // candidate records in flight per lane
 
 struct NarrowWarp {
-    uint32_t u[NARROW_LIST];                   // candidate slot
-    uint8_t o[NARROW_LIST];                    // owner lane
+    uint32_t u[NARROW_LIST];                   // candidate slot << 5 | owner lane (worlds of more than 2^27 grid bodies: slot only)
+    uint8_t o[NARROW_LIST];                    // owner lane, only used by those worlds
     unsigned long long hit[NARROW_STAGE];      // (min id << 32) | max id
-    SlotRec own[32];
+    float4 own_c[32];                          // the warp's own bodies: centre + radius,
+    uint32_t own_v[32];                        //   id|flags,
+    float4 own_h[32];                          //   half extents (mixed worlds)
 };
 
 __device__ __forceinline__ void narrow_flush(NarrowWarp& sw, uint32_t& nh, uint32_t lane, unsigned long long* out,
@@ -213,48 +244,6 @@ __device__ __forceinline__ bool pair_hit(const float4 ca, uint32_t va, const flo
     return hit && !(va & vb & STATIC_BIT);                               // main.cpp:695
 }
 
-// x-edge cell: the windows wrap around the row, so they are walked cell by cell by the owning lane
-// (2 of 2^bx cells per row); hits go straight out through the warp-aggregated append
-template <bool CANDIDATES, bool MIXED>
-__device__ __noinline__ void narrow_edge(uint32_t t, uint32_t key, int bx, int by, int bz, uint32_t va, const float4 ca, const float4 ha,
-                                         const SlotRec* __restrict__ recs, const uint32_t* __restrict__ cell_start,
-                                         unsigned long long* out, unsigned long long cap, unsigned long long* counter) {
-    const uint32_t ida = va & ID_MASK;
-    const uint32_t mx = (1u << bx) - 1u, my = (1u << by) - 1u, mz = (1u << bz) - 1u;
-    const uint32_t cx = key & mx, cy = (key >> bx) & my, cz = (key >> (bx + by)) & mz;
-    // window w: 0 = rest of the own cell, 1 = cell cx+1 of the own row, 2.. = 3 cells of each forward row
-#pragma unroll 1
-    for (int w = 0; w < 14; ++w) {
-        uint32_t s, e;
-        if (w == 0) {
-            s = t + 1;
-            e = cell_start[key + 1];
-        } else {
-            uint32_t nk;
-            if (w == 1) {
-                nk = (key & ~mx) | ((cx + 1) & mx);
-            } else {
-                const int r = (w - 2) / 3, dx = (w - 2) % 3 - 1;
-                const int dz = r == 0 ? 0 : 1;
-                const int dy = r == 0 ? 1 : r - 2;
-                nk = (((cy + dy) & my) << bx) | (((cz + dz) & mz) << (bx + by)) | ((cx + dx) & mx);
-            }
-            s = cell_start[nk];
-            e = cell_start[nk + 1];
-        }
-#pragma unroll 1
-        for (uint32_t u = s; u < e; ++u) {
-            float4 cb, hb;
-            uint32_t vb;
-            ld_rec(recs + u, cb, vb, hb);
-            if (pair_hit<CANDIDATES, MIXED>(ca, va, ha, cb, vb, hb)) {
-                const uint32_t idb = vb & ID_MASK;
-                emit_pair(out, cap, counter, min(ida, idb), max(ida, idb));
-            }
-        }
-    }
-}
-
 // Blocks [0, slot_blocks) run the grid narrow phase; the blocks behind them are the "outside" workers
 // (side list and far list, K5b / K5c below) so that the whole detection is one launch.
 struct OutsideArgs {
@@ -274,6 +263,7 @@ __device__ void outside_worker(uint32_t worker, uint32_t nworkers, const Outside
 
 template <bool CANDIDATES, bool MIXED>
 __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* __restrict__ recs,
+                                                                const uint32_t* __restrict__ rec_val,   // all-sphere layout (MIXED = false)
                                                                 const uint32_t* __restrict__ cell_start,
                                                                 uint32_t* counters, GridParams g, uint32_t slot_blocks,
                                                                 OutsideArgs oa, unsigned long long* out, unsigned long long cap,
@@ -290,44 +280,54 @@ __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* _
     if (t - lane >= ngrid) return;                 // the whole warp is past the last grid body
     NarrowWarp& sw = s_warp[wid];
     const bool valid = t < ngrid;
-    float4 ca = make_float4(0.f, 0.f, 0.f, 0.f), ha = ca;
-    uint32_t va = 0, key = 0;
-    uint32_t rs[5], len[5];
+    // Windows of this lane's body: per stencil row (own row, then the four forward rows) one slot range, plus a
+    // second one in the 2 of 2^bx cells per row whose three-cell run wraps around the row end (cx = 0: cells
+    // {0,1} + {mx}; cx = mx: cells {mx-1,mx} + {0}).  Ten (start, length) pairs, the second five almost always empty.
+    uint32_t rs[10], len[10];
 #pragma unroll
-    for (int r = 0; r < 5; ++r) rs[r] = len[r] = 0;
-    bool edge = false;
+    for (int r = 0; r < 10; ++r) rs[r] = len[r] = 0;
+    const bool big = ngrid > (1u << 27);           // slot << 5 | lane does not fit one word
     if (valid) {
-        ld_rec(recs + t, ca, va, ha);
-        sw.own[lane].c = ca;
-        sw.own[lane].val = va;
-        if (MIXED) {
-            sw.own[lane].hx = ha.x;
-            sw.own[lane].hy = ha.y;
-            sw.own[lane].hz = ha.z;
+        float4 ca, ha = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t va;
+        if (MIXED || !rec_val) {
+            ld_rec(recs + t, ca, va, ha);
+            if (MIXED) sw.own_h[lane] = ha;
+        } else {
+            ca = reinterpret_cast<const float4*>(recs)[t];
+            va = rec_val[t];
         }
-        key = cell_key(ca, g);
+        sw.own_c[lane] = ca;
+        sw.own_v[lane] = va;
+        const uint32_t key = cell_key(ca, g);
         const uint32_t mx = (1u << g.bx) - 1u, my = (1u << g.by) - 1u, mz = (1u << g.bz) - 1u;
         const uint32_t cx = key & mx, cy = (key >> g.bx) & my, cz = (key >> (g.bx + g.by)) & mz;
-        edge = cx == 0 || cx == mx;
-        if (!edge) {
-            // interior cell: five contiguous slot ranges, all nine look-ups issued before the first use
-            uint32_t re[5];
-            rs[0] = t + 1;
-            re[0] = cell_start[key + 2];
+        // the run of cells cx-1..cx+1 of a row, as cell offsets inside the row: [a0, a1) and, when it wraps, [b0, b1)
+        const uint32_t a0 = cx == 0 ? 0u : cx - 1u, a1 = cx == mx ? mx + 1u : cx + 2u;
+        const bool wrap = cx == 0 || cx == mx;
+        const uint32_t b0 = cx == 0 ? mx : 0u;
+        // own row: the later slots of the own cell and cell cx+1 (cell 0 of the row when cx = mx)
+        rs[0] = t + 1;
+        len[0] = cell_start[key + (cx == mx ? 1u : 2u)] - rs[0];
+        if (cx == mx) {
+            rs[5] = cell_start[key - cx];
+            len[5] = cell_start[key - cx + 1u] - rs[5];
+        }
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int dz = r == 0 ? 0 : 1;
-                const int dy = r == 0 ? 1 : r - 2;
-                const uint32_t row = (((cy + dy) & my) << g.bx) | (((cz + dz) & mz) << (g.bx + g.by));
-                rs[r + 1] = cell_start[row + cx - 1];
-                re[r + 1] = cell_start[row + cx + 2];
+        for (int r = 0; r < 4; ++r) {
+            const int dz = r == 0 ? 0 : 1;
+            const int dy = r == 0 ? 1 : r - 2;
+            const uint32_t row = (((cy + dy) & my) << g.bx) | (((cz + dz) & mz) << (g.bx + g.by));
+            rs[r + 1] = cell_start[row + a0];
+            len[r + 1] = cell_start[row + a1] - rs[r + 1];
+            if (wrap) {
+                rs[r + 6] = cell_start[row + b0];
+                len[r + 6] = cell_start[row + b0 + 1u] - rs[r + 6];
             }
-#pragma unroll
-            for (int r = 0; r < 5; ++r) len[r] = re[r] - rs[r];
         }
     }
     // offsets of every lane's pairs in the warp's flattened list
-    const uint32_t mine = len[0] + len[1] + len[2] + len[3] + len[4];
+    const uint32_t mine = (len[0] + len[1] + len[2] + len[3] + len[4]) + (len[5] + len[6] + len[7] + len[8] + len[9]);
     uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -342,46 +342,72 @@ __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* _
         // ---- expand: this round covers list positions [base, base + NARROW_LIST)
         uint32_t wo = off;
 #pragma unroll
-        for (int r = 0; r < 5; ++r) {
+        for (int r = 0; r < 10; ++r) {
             const uint32_t lo = max(wo, base), hi = min(wo + len[r], base + (uint32_t)NARROW_LIST);
-            for (uint32_t k = lo; k < hi; ++k) {
-                sw.u[k - base] = rs[r] + (k - wo);
-                sw.o[k - base] = (uint8_t)lane;
+            if (!big) {
+                for (uint32_t k = lo; k < hi; ++k) sw.u[k - base] = ((rs[r] + (k - wo)) << 5) | lane;
+            } else {
+                for (uint32_t k = lo; k < hi; ++k) {
+                    sw.u[k - base] = rs[r] + (k - wo);
+                    sw.o[k - base] = (uint8_t)lane;
+                }
             }
             wo += len[r];
         }
         __syncwarp();
-        // ---- test: 32 pairs per iteration
+        // ---- test: NARROW_UNROLL x 32 pairs per iteration, the candidates' records of one iteration all in flight together
         const uint32_t cnt = min((uint32_t)NARROW_LIST, total - base);
-        for (uint32_t p0 = 0; p0 < cnt; p0 += 32) {
-            const uint32_t p = p0 + lane;
-            bool hit = false;
-            unsigned long long pr = 0;
-            if (p < cnt) {
-                const uint32_t u = sw.u[p], o = sw.o[p];
-                float4 cb, hb;
-                uint32_t vb;
-                ld_rec(recs + u, cb, vb, hb);
-                const float4 oc = sw.own[o].c;
-                const uint32_t ov = sw.own[o].val;
-                float4 oh = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (MIXED) oh = make_float4(sw.own[o].hx, sw.own[o].hy, sw.own[o].hz, 0.f);
-                hit = pair_hit<CANDIDATES, MIXED>(oc, ov, oh, cb, vb, hb);
-                const uint32_t ida = ov & ID_MASK, idb = vb & ID_MASK;
-                pr = ((unsigned long long)min(ida, idb) << 32) | max(ida, idb);
+        for (uint32_t p0 = 0; p0 < cnt; p0 += 32 * NARROW_UNROLL) {
+            float4 cb[NARROW_UNROLL], hb[NARROW_UNROLL];
+            uint32_t vb[NARROW_UNROLL], ow[NARROW_UNROLL];
+#pragma unroll
+            for (int k = 0; k < NARROW_UNROLL; ++k) {
+                const uint32_t p = p0 + 32 * k + lane;
+                ow[k] = 0xFFu;
+                if (p < cnt) {
+                    uint32_t u = sw.u[p];
+                    if (!big) {
+                        ow[k] = u & 31u;
+                        u >>= 5;
+                    } else {
+                        ow[k] = sw.o[p];
+                    }
+                    if (MIXED || !rec_val) {
+                        ld_rec(recs + u, cb[k], vb[k], hb[k]);
+                    } else {
+                        cb[k] = reinterpret_cast<const float4*>(recs)[u];
+                        vb[k] = rec_val[u];
+                    }
+                }
             }
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
-            if (m) {
-                if (hit) sw.hit[nh + __popc(m & ((1u << lane) - 1u))] = pr;
-                nh += __popc(m);
-                __syncwarp();
-                if (nh > (uint32_t)(NARROW_STAGE - 32)) narrow_flush(sw, nh, lane, out, cap, counter);
+#pragma unroll
+            for (int k = 0; k < NARROW_UNROLL; ++k) {
+                if (p0 + 32 * k >= cnt) break;                 // warp-uniform
+                bool hit = false;
+                unsigned long long pr = 0;
+                if (ow[k] != 0xFFu) {
+                    const uint32_t o = ow[k];
+                    const float4 oc = sw.own_c[o];
+                    const uint32_t ov = sw.own_v[o];
+                    float4 oh = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (MIXED) oh = sw.own_h[o];
+                    else hb[k] = oh;
+                    hit = pair_hit<CANDIDATES, MIXED>(oc, ov, oh, cb[k], vb[k], hb[k]);
+                    const uint32_t ida = ov & ID_MASK, idb = vb[k] & ID_MASK;
+                    pr = ((unsigned long long)min(ida, idb) << 32) | max(ida, idb);
+                }
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+                if (m) {
+                    if (hit) sw.hit[nh + __popc(m & ((1u << lane) - 1u))] = pr;
+                    nh += __popc(m);
+                    __syncwarp();
+                    if (nh > (uint32_t)(NARROW_STAGE - 32)) narrow_flush(sw, nh, lane, out, cap, counter);
+                }
             }
         }
         __syncwarp();
     }
     narrow_flush(sw, nh, lane, out, cap, counter);
-    if (edge) narrow_edge<CANDIDATES, MIXED>(t, key, g.bx, g.by, g.bz, va, ca, ha, recs, cell_start, out, cap, counter);
 }
 
 // K5b: side-list bodies (oversize / non-finite extent) against every live body.  Persistent workers:
@@ -422,20 +448,26 @@ __device__ void outside_worker(uint32_t worker, uint32_t nworkers, const Outside
         }
     }
     if (nfar) {
-        // items = (far body t, slice of 1024 partners); partners of t: far bodies later in the list, then every boundary grid body
+        // items = (tile of 128 consecutive far bodies, slice of 1024 partners): one far body per thread, and every thread
+        // of the CTA reads the SAME partner entry in each iteration (a broadcast, one transaction per warp).
+        // Partners of far body t: the far bodies later in the list, then every boundary grid body.
         const uint32_t total = nfar + nbnd;
         const uint32_t slices = (total + 1023) / 1024;
-        const unsigned long long items = (unsigned long long)nfar * slices;
-        for (unsigned long long it = (unsigned long long)worker * NARROW_THREADS + threadIdx.x; it < items;
-             it += (unsigned long long)nworkers * NARROW_THREADS) {
-            const uint32_t t = (uint32_t)(it / slices), sl = (uint32_t)(it % slices);
-            const uint32_t k0 = max(t + 1, sl * 1024u), k1 = min(total, (sl + 1) * 1024u);
-            if (k0 >= k1) continue;
+        const uint32_t tiles = (nfar + NARROW_THREADS - 1) / NARROW_THREADS;
+        const unsigned long long items = (unsigned long long)tiles * slices;
+        for (unsigned long long it = worker; it < items; it += nworkers) {
+            const uint32_t tile = (uint32_t)(it / slices), sl = (uint32_t)(it % slices);
+            const uint32_t t = tile * NARROW_THREADS + threadIdx.x;
+            const uint32_t k1 = min(total, (sl + 1) * 1024u);
+            uint32_t k0 = sl * 1024u;
+            if (k1 <= tile * NARROW_THREADS + 1u) continue;   // the whole slice lies before the tile's first body: nothing later
+            if (t >= nfar) continue;
             const uint32_t va = oa.far_list[t];
             const uint32_t a = va & ID_MASK;
             const float4 ca = oa.far_c[t];
             for (uint32_t k = k0; k < k1; ++k) {
                 const bool kf = k < nfar;
+                if (kf && k <= t) continue;                              // far-far pairs once, from the earlier body
                 const uint32_t vb = kf ? oa.far_list[k] : oa.bnd_list[k - nfar];
                 if (va & vb & STATIC_BIT) continue;                      // main.cpp:695
                 const float4 cb = kf ? oa.far_c[k] : oa.bnd_c[k - nfar];

@@ -91,19 +91,47 @@ struct __align__(32) BodyRec {
 };
 static_assert(sizeof(BodyRec) == 32, "one sector");
 
+// Every access to a record that can race with another SM's access is a RELAXED, GPU-SCOPE, 128-BIT access
+// (PTX .b128: one scalar access in the memory model, single-copy atomic - a 256-bit vector access would be
+// "a set of 32-bit accesses in unspecified order" there).  Each 16-byte half carries its own version, so the two
+// halves are validated independently and a reader can never act on a torn record; SASS: LDG/STG.E.128.STRONG.GPU.
+// (-DTR_BODY_REC_WEAK restores round 1's single weak 256-bit access for A/B timing.)
+__device__ __forceinline__ void st128_relaxed(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("{\n\t.reg .b128 t;\n\t.reg .b64 lo, hi;\n\tmov.b64 lo, {%1,%2};\n\tmov.b64 hi, {%3,%4};\n\tmov.b128 t, {lo, hi};\n\t"
+                 "st.relaxed.gpu.global.b128 [%0], t;\n\t}" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
+__device__ __forceinline__ void ld128_relaxed(const void* p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    asm volatile("{\n\t.reg .b128 t;\n\t.reg .b64 lo, hi;\n\tld.relaxed.gpu.global.b128 t, [%4];\n\tmov.b128 {lo, hi}, t;\n\t"
+                 "mov.b64 {%0,%1}, lo;\n\tmov.b64 {%2,%3}, hi;\n\t}"
+                 : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
+                 : "l"(p)
+                 : "memory");
+}
+
 __device__ __forceinline__ void st_body(BodyRec* p, const float4 v, const float4 x, uint32_t ver) {
+#ifdef TR_BODY_REC_WEAK
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)),
                  "r"(__float_as_uint(v.z)), "r"(ver), "r"(__float_as_uint(x.x)), "r"(__float_as_uint(x.y)),
                  "r"(__float_as_uint(x.z)), "r"(ver)
                  : "memory");
+#else
+    st128_relaxed(&p->vx, __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), ver);
+    st128_relaxed(&p->px, __float_as_uint(x.x), __float_as_uint(x.y), __float_as_uint(x.z), ver);
+#endif
 }
 // L2 load (the record is written by other SMs); true when both halves carry the expected version
 __device__ __forceinline__ bool ld_body(const BodyRec* p, uint32_t want, float4& v, float4& x) {
     uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+#ifdef TR_BODY_REC_WEAK
     asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
                  : "l"(p)
                  : "memory");
+#else
+    ld128_relaxed(&p->vx, r0, r1, r2, r3);
+    ld128_relaxed(&p->px, r4, r5, r6, r7);
+#endif
     v.x = __uint_as_float(r0); v.y = __uint_as_float(r1); v.z = __uint_as_float(r2);
     x.x = __uint_as_float(r4); x.y = __uint_as_float(r5); x.z = __uint_as_float(r6);
     return r3 == want && r7 == want;
@@ -134,13 +162,13 @@ struct PrepArgs {
 };
 
 // all CTAs of prep_kernel are resident (the host sizes the grid from the occupancy API): a counter barrier
-__device__ __forceinline__ void prep_barrier(uint32_t* bar, uint32_t& phase) {
+__device__ __forceinline__ void prep_barrier(uint32_t* bar, uint32_t& phase, uint32_t nblocks) {
     __syncthreads();
     ++phase;
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(bar, 1u);
-        const uint32_t want = phase * gridDim.x;
+        const uint32_t want = phase * nblocks;
         while (*((volatile uint32_t*)bar) < want) __nanosleep(40);
         __threadfence();
     }
@@ -211,7 +239,10 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
     }
     const uint32_t cn = (uint32_t)found;
     if (cn == 0) return;
-    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    // a sparse world keeps only as many CTAs as it has work for: the grid barrier costs what its participants cost
+    const uint32_t nblocks = min(gridDim.x, (cn + PREP_THREADS - 1) / PREP_THREADS);
+    if (blockIdx.x >= nblocks) return;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = nblocks * blockDim.x;
     uint32_t phase = 0;
     uint32_t* bar = a.counters + C_BAR;
 
@@ -222,7 +253,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
         a.arank[c] = make_uint2(atomicAdd(&a.body_cnt[i], 1u), atomicAdd(&a.body_cnt[j], 1u));
         a.queue[c] = EMPTY;
     }
-    prep_barrier(bar, phase);
+    prep_barrier(bar, phase, nblocks);
 
     // ---- B: segment allocation by the first arrival at each body
     for (uint32_t c0 = blockIdx.x * blockDim.x; c0 < cn; c0 += gsize) {   // whole warps stay in the loop (shuffles below)
@@ -257,7 +288,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
             if (lj > PREP_SHORT) a.long_list[atomicAdd(&a.counters[C_LONG], 1u)] = j;
         }
     }
-    prep_barrier(bar, phase);
+    prep_barrier(bar, phase, nblocks);
 
     // ---- C: half edges into their segments; the histogram counts itself back to zero
     for (uint32_t c = gtid; c < cn; c += gsize) {
@@ -269,11 +300,11 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
         if (r.x == 0) a.body_cnt[i] = 0;
         if (r.y == 0) a.body_cnt[j] = 0;
     }
-    prep_barrier(bar, phase);
+    prep_barrier(bar, phase, nblocks);
 
     // ---- D: long segments sorted by partner id, one CTA each
     const uint32_t nlong = *((volatile uint32_t*)&a.counters[C_LONG]);
-    for (uint32_t l = blockIdx.x; l < nlong; l += gridDim.x) {
+    for (uint32_t l = blockIdx.x; l < nlong; l += nblocks) {
         const uint2 sg = __ldcg(&a.seg[__ldcg(&a.long_list[l])]);
         uint2* p = a.he + sg.x;
         if (sg.y <= PREP_SMEM_SORT) {
@@ -288,7 +319,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
                           [&](uint32_t x, uint32_t y) { const uint2 t = __ldcg(&p[x]); const uint2 u = __ldcg(&p[y]); __stcg(&p[x], u); __stcg(&p[y], t); });
         }
     }
-    if (nlong) prep_barrier(bar, phase);           // nlong is the same for every CTA
+    if (nlong) prep_barrier(bar, phase, nblocks);  // nlong is the same for every CTA
 
     // ---- E: dependencies, versions, constants, ready queue
     for (uint32_t c = gtid; c < cn; c += gsize) {
@@ -550,7 +581,7 @@ __global__ void __launch_bounds__(128) response_flow_kernel(FlowArgs a, const ui
     if ((threadIdx.x & 31) >= LANES) return;
     if (ctl[CTL_ABORT] != 0) return;               // contact buffer overflow in this or an earlier step: no response
     const uint32_t c_n = counters[C_CONTACTS];     // <= capacity < 2^32 here (prep_kernel checked)
-    if (c_n == 0) return;
+    if ((unsigned long long)blockIdx.x * (blockDim.x / 32) * LANES >= c_n) return;   // no more workers than contacts (also: none for none)
     constexpr uint32_t LMASK = LANES == 32 ? 0xFFFFFFFFu : ((1u << LANES) - 1u);
     volatile uint32_t* vq = q;
     volatile uint32_t* vc = counters;

@@ -55,7 +55,11 @@ constexpr int GRAV_TILE = GRAV_THREADS * GRAV_T;       // 2048 targets per tile
 #endif
 constexpr int GRAV_SUB = TR_GRAV_SUB;                  // sources per TMA stage (16 B each)
 constexpr int GRAV_STAGES = TR_GRAV_STAGES;
-constexpr int GRAV_MAX_CHUNKS = 64;                    // partial sums per target
+// Partial sums per target = source chunks per tile.  74 = half the B200's 148 SMs: with 2 persistent CTAs per SM
+// (296) a target block of T tiles is T * 74 work items = T / 4 items per CTA, a whole number whenever T is a
+// multiple of 4 - 4M bodies over 8 GPUs: 256 tiles x 74 = 64 rounds exactly, where 64 chunks gave 55.35 rounds
+// executed as 56 (round 1: the 8-GPU limiter).  A function of N only, like the chunk length below.
+constexpr int GRAV_MAX_CHUNKS = 74;
 
 // chunk length is a function of N only, so a sharded run adds the same partial sums in
 // the same order as an unsharded one (bit-identical for any rank count).
