@@ -463,6 +463,9 @@ def measure(ctx: Ctx, name: str, n: int | None, steps: int, warmup: int, *, shar
     #   e2e_full_aos  tr_step_host: the whole 92-byte descriptor of every body up AND down every step (round 1's e2e)
     if want_e2e:
         def timed(call):
+            # every e2e figure starts from the workload's initial state, like the device-timed loop did (the packed
+            # lattice of cfg5 is not stationary: the reference's inverted approach test blows it apart after ~30 steps)
+            world.write_bodies(bodies)
             call()
             call()                        # (the second call page-locks the caller's buffers in place)
             if sharded:
@@ -482,7 +485,7 @@ def measure(ctx: Ctx, name: str, n: int | None, steps: int, warmup: int, *, shar
                       "h2d_bytes_per_step": int(own_count) * 12, "d2h_bytes_per_step": int(own_count) * 36,
                       "ms_per_step": dt / steps * 1e3, "steps_per_s": steps / dt,
                       "api": "tr_step_frame (per-body external force in, pos/vel/centre out, every step)"}
-        host = world.read_bodies(own_first, own_count)
+        host = bodies[own_first:own_first + own_count].copy()
         dt = timed(lambda: world.step_host(host, 1))
         res["e2e_full_aos"] = {"value": pair_visits * steps / dt, "unit": res["unit"],
                                "h2d_bytes_per_step": int(own_count) * 92, "d2h_bytes_per_step": int(own_count) * 92,
