@@ -172,6 +172,7 @@ static int ensure_buffers(tr_world* w) {
         TR_TRY(realloc_dev(&c->klass, cap));
         TR_TRY(realloc_dev(&c->seg, cap));
         TR_TRY(realloc_dev(&c->long_list, cap));
+        TR_TRY(realloc_dev(&c->huge_list, cap));
         TR_TRY(realloc_dev(&c->body_cnt, cap));
         TR_CUDA(cudaMemsetAsync(c->body_cnt, 0, cap * sizeof(uint32_t), w->stream));
         c->cap_bodies = cap;
@@ -287,7 +288,7 @@ static int launch_response(tr_world* w, cudaStream_t st) {
         if (per_sm > 4) per_sm = 4;               // every CTA must be resident: prep_kernel synchronises the grid itself
         c->prep_blocks = w->num_sms * per_sm;
     }
-    PrepArgs pa{c->ckeys, c->cap_contacts, c->counters, w->d_ctl, c->body_cnt, c->seg, c->arank, c->he, c->long_list, c->dep, c->crec,
+    PrepArgs pa{c->ckeys, c->cap_contacts, c->counters, w->d_ctl, c->body_cnt, c->seg, c->arank, c->he, c->long_list, c->huge_list, c->dep, c->crec,
                 c->cver, (ContactGeo*)c->cgeo, flow ? (BodyRec*)c->brec : nullptr, c->frontier[0], flow ? C_QTAIL : C_FRONT,
                 w->pos_m[w->cur], w->vel_rest, w->center_r, w->half_ext, w->flags};
     prep_kernel<<<c->prep_blocks, PREP_THREADS, 0, st>>>(pa);
@@ -613,7 +614,7 @@ int collide_free(tr_world* w) {
     cudaFree(c->keys); cudaFree(c->recs); cudaFree(c->sorted_ids);
     cudaFree(c->cell_start); cudaFree(c->cell_count); cudaFree(c->tile_sum);
     cudaFree(c->side_list); cudaFree(c->far_list); cudaFree(c->bnd_list); cudaFree(c->far_c); cudaFree(c->bnd_c); cudaFree(c->klass);
-    cudaFree(c->seg); cudaFree(c->long_list); cudaFree(c->body_cnt); cudaFree(c->counters); cudaFree(c->brec);
+    cudaFree(c->seg); cudaFree(c->long_list); cudaFree(c->huge_list); cudaFree(c->body_cnt); cudaFree(c->counters); cudaFree(c->brec);
     free_contact_buffers(c);
     for (int k = 0; k < 2; ++k)
         if (c->graph[k]) cudaGraphExecDestroy(c->graph[k]);

@@ -29,7 +29,7 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 // 128-byte lines of their own: on one line their atomics and the idle workers' polls all queue at
 // one L2 slice (having idle workers merely READ the tail next to the pushes doubled the step time).
 enum { C_SIDE = 0, C_GRID = 1, C_CONTACTS = 2 /*u64*/, C_CAND = 4 /*u64*/, C_HE = 6 /* half-edge slots handed out */,
-       C_LONG = 7 /* bodies with a long contact list */, C_FRONT = 8 /*3*/, C_ROUNDS = 11, C_ABORT = 12, C_FIN = 13, C_BAR = 14 /* grid barrier of prep_kernel */,
+       C_LONG = 7 /* bodies with a long contact list */, C_FRONT = 8 /*3*/, C_ROUNDS = 11, C_ABORT = 12, C_FIN = 13, C_BAR = 14 /* grid barrier of prep_kernel */, C_HUGE = 15 /* bodies whose contact list the whole grid sorts */,
        C_FAR = 16, C_BND = 17, C_T0 = 18 /* 3 x u64 globaltimer stamps: broad, narrow, prep */,
        C_NHOST = 24,
        C_QHEAD = 32, C_QTAIL = 64, C_DONE = 96, C_NCOUNTERS = 128 };
@@ -91,6 +91,7 @@ struct Collide {
     uint32_t* body_cnt = nullptr;    // [N] contacts per body; self-cleaning (prep_kernel zeroes what it touched)
     uint2* seg = nullptr;            // [N] {first half-edge slot, contacts} of every body in contact this step
     uint32_t* long_list = nullptr;   // bodies whose contact list is long enough to be sorted by a CTA
+    uint32_t* huge_list = nullptr;   // ... by all CTAs together (more than PREP_SMEM_SORT contacts)
 
     uint32_t* counters = nullptr;
 

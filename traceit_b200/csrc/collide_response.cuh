@@ -21,9 +21,11 @@ namespace tr {
 //   B  alloc    the half edge that arrived first at a body reserves the body's segment (warp-aggregated
 //               bump allocation); bodies with more than PREP_SHORT contacts go on the long list
 //   C  scatter  half edge {partner, contact} -> segment[arrival rank]; body_cnt counted back to zero
-//   D  sort     long segments only: one CTA per segment, bitonic by partner id (shared memory up to
-//               2048 entries, in place in global memory beyond) - a hub body with L contacts costs
-//               O(L log^2 L), not the O(L^2) of ranking every entry against every other
+//   D  sort     long segments only, bitonic by partner id: one CTA per segment in shared memory up to 2048
+//               entries; beyond that (a hub: the slab 10^5 bodies rest on) all CTAs sort the segment together,
+//               chunks in shared memory and the long-distance steps in global memory with a grid barrier per
+//               step - a body with L contacts costs O(L log^2 L) spread over the grid, not the O(L^2) on one
+//               thread of ranking every entry against every other
 //   E  deps     per contact: rank among / successor in the lists of both bodies (linear scan of a short
 //               unsorted segment, binary search in a sorted long one) -> dep[c], {i, j, succ_i, succ_j},
 //               expected record versions, contact constants, version-0 body records, ready queue.
@@ -147,6 +149,7 @@ struct PrepArgs {
     uint2* arank;
     uint2* he;
     uint32_t* long_list;
+    uint32_t* huge_list;
     uint32_t* dep;
     uint4* crec;
     uint2* cver;
@@ -175,25 +178,65 @@ __device__ __forceinline__ void prep_barrier(uint32_t* bar, uint32_t& phase, uin
     __syncthreads();
 }
 
-// ascending bitonic network (flip + shear steps: virtual +inf padding beyond len never moves down)
-template <typename Get, typename Swap>
-__device__ __forceinline__ void bitonic_steps(uint32_t len, Get key_at, Swap swap_at) {
+// Ascending bitonic network in its flip + shear form: stage k = one "flip" step (i <-> the mirror position inside
+// its block of k) followed by shear steps at distances k/4 ... 1 (i <-> i + j inside blocks of 2j).  Every
+// compare-exchange puts the smaller key at the lower index, so virtual +inf padding beyond len never moves down
+// and any length works: a pair whose upper index is >= len is simply skipped.
+// pair t of a flip step of stage k / of a shear step at distance j:
+__device__ __forceinline__ void flip_pair(uint32_t t, uint32_t k, uint32_t& i, uint32_t& l) {
+    const uint32_t g = t / (k / 2), r = t % (k / 2);
+    i = g * k + r;
+    l = g * k + (k - 1 - r);
+}
+__device__ __forceinline__ void shear_pair(uint32_t t, uint32_t j, uint32_t& i, uint32_t& l) {
+    const uint32_t g = t / j, r = t % j;
+    i = g * 2 * j + r;
+    l = i + j;
+}
+__device__ __forceinline__ void smem_cmpx(uint2* s, uint32_t i, uint32_t l, uint32_t len) {
+    if (l < len && s[i].x > s[l].x) {
+        const uint2 t = s[i];
+        s[i] = s[l];
+        s[l] = t;
+    }
+}
+// one CTA, a chunk of len <= PREP_SMEM_SORT entries in shared memory: the whole network (from_k = 2) or only the
+// shear steps below the chunk size that finish a stage whose upper steps were done in global memory (shears_only)
+__device__ __forceinline__ void smem_sort(uint2* s, uint32_t len, bool shears_only) {
     uint32_t pow2 = 1;
     while (pow2 < len) pow2 <<= 1;
-    for (uint32_t k = 2; k <= pow2; k <<= 1) {
-        for (uint32_t t = threadIdx.x; t < pow2 / 2; t += blockDim.x) {       // flip: i <-> block_end - offset
-            const uint32_t g = t / (k / 2), r = t % (k / 2);
-            const uint32_t i = g * k + r, l = g * k + (k - 1 - r);
-            if (l < len && key_at(i) > key_at(l)) swap_at(i, l);
-        }
-        __syncthreads();
-        for (uint32_t j = k / 4; j >= 1; j >>= 1) {
+    uint32_t i, l;
+    if (!shears_only) {
+        for (uint32_t k = 2; k <= pow2; k <<= 1) {
             for (uint32_t t = threadIdx.x; t < pow2 / 2; t += blockDim.x) {
-                const uint32_t g = t / j, r = t % j;
-                const uint32_t i = g * 2 * j + r, l = i + j;
-                if (l < len && key_at(i) > key_at(l)) swap_at(i, l);
+                flip_pair(t, k, i, l);
+                smem_cmpx(s, i, l, len);
             }
             __syncthreads();
+            for (uint32_t j = k / 4; j >= 1; j >>= 1) {
+                for (uint32_t t = threadIdx.x; t < pow2 / 2; t += blockDim.x) {
+                    shear_pair(t, j, i, l);
+                    smem_cmpx(s, i, l, len);
+                }
+                __syncthreads();
+            }
+        }
+    } else {
+        for (uint32_t j = PREP_SMEM_SORT / 2; j >= 1; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < PREP_SMEM_SORT / 2; t += blockDim.x) {
+                shear_pair(t, j, i, l);
+                smem_cmpx(s, i, l, len);
+            }
+            __syncthreads();
+        }
+    }
+}
+__device__ __forceinline__ void global_cmpx(uint2* p, uint32_t i, uint32_t l, uint32_t len) {
+    if (l < len) {
+        const uint2 x = __ldcg(p + i), y = __ldcg(p + l);
+        if (x.x > y.x) {
+            __stcg(p + i, y);
+            __stcg(p + l, x);
         }
     }
 }
@@ -280,12 +323,14 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
         base = __shfl_sync(0xFFFFFFFFu, base, 31) + (incl - need);
         if (li) {
             a.seg[i] = make_uint2(base, li);
-            if (li > PREP_SHORT) a.long_list[atomicAdd(&a.counters[C_LONG], 1u)] = i;
+            if (li > PREP_SMEM_SORT) a.huge_list[atomicAdd(&a.counters[C_HUGE], 1u)] = i;
+            else if (li > PREP_SHORT) a.long_list[atomicAdd(&a.counters[C_LONG], 1u)] = i;
             base += li;
         }
         if (lj) {
             a.seg[j] = make_uint2(base, lj);
-            if (lj > PREP_SHORT) a.long_list[atomicAdd(&a.counters[C_LONG], 1u)] = j;
+            if (lj > PREP_SMEM_SORT) a.huge_list[atomicAdd(&a.counters[C_HUGE], 1u)] = j;
+            else if (lj > PREP_SHORT) a.long_list[atomicAdd(&a.counters[C_LONG], 1u)] = j;
         }
     }
     prep_barrier(bar, phase, nblocks);
@@ -302,21 +347,58 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
     }
     prep_barrier(bar, phase, nblocks);
 
-    // ---- D: long segments sorted by partner id, one CTA each
+    // ---- D: long segments sorted by partner id.  Up to PREP_SMEM_SORT entries: one CTA each, in shared memory.
     const uint32_t nlong = *((volatile uint32_t*)&a.counters[C_LONG]);
     for (uint32_t l = blockIdx.x; l < nlong; l += nblocks) {
         const uint2 sg = __ldcg(&a.seg[__ldcg(&a.long_list[l])]);
+        if (sg.y > PREP_SMEM_SORT) continue;
         uint2* p = a.he + sg.x;
-        if (sg.y <= PREP_SMEM_SORT) {
-            for (uint32_t k = threadIdx.x; k < sg.y; k += blockDim.x) s_sort[k] = __ldcg(p + k);
-            __syncthreads();
-            bitonic_steps(sg.y, [&](uint32_t x) { return s_sort[x].x; },
-                          [&](uint32_t x, uint32_t y) { const uint2 t = s_sort[x]; s_sort[x] = s_sort[y]; s_sort[y] = t; });
-            for (uint32_t k = threadIdx.x; k < sg.y; k += blockDim.x) p[k] = s_sort[k];
-            __syncthreads();
-        } else {
-            bitonic_steps(sg.y, [&](uint32_t x) { return __ldcg(&p[x]).x; },
-                          [&](uint32_t x, uint32_t y) { const uint2 t = __ldcg(&p[x]); const uint2 u = __ldcg(&p[y]); __stcg(&p[x], u); __stcg(&p[y], t); });
+        for (uint32_t k = threadIdx.x; k < sg.y; k += blockDim.x) s_sort[k] = __ldcg(p + k);
+        __syncthreads();
+        smem_sort(s_sort, sg.y, false);
+        for (uint32_t k = threadIdx.x; k < sg.y; k += blockDim.x) p[k] = s_sort[k];
+        __syncthreads();
+    }
+    // Hubs (a slab that 10^5 bodies rest on): ALL CTAs sort one such segment together.  Chunks of PREP_SMEM_SORT
+    // entries are sorted in shared memory; the stages above the chunk size do their long-distance steps in global
+    // memory - one compare-exchange per thread of the grid and a grid barrier per step - and finish inside the chunks
+    // again.  27 barriers for 10^5 entries; a single CTA walking the same network alone took 12 ms.
+    const uint32_t nhuge = *((volatile uint32_t*)&a.counters[C_HUGE]);
+    for (uint32_t hgi = 0; hgi < nhuge; ++hgi) {
+        const uint2 sg = __ldcg(&a.seg[__ldcg(&a.huge_list[hgi])]);
+        uint2* p = a.he + sg.x;
+        const uint32_t len = sg.y, nchunks = (len + PREP_SMEM_SORT - 1) / PREP_SMEM_SORT;
+        uint32_t pow2 = 1;
+        while (pow2 < len) pow2 <<= 1;
+        for (int pass = 0;; ++pass) {
+            // pass 0 sorts every chunk; pass m > 0 is stage k = PREP_SMEM_SORT << m
+            const uint32_t k = PREP_SMEM_SORT << pass;
+            if (pass > 0) {
+                if (k > pow2) break;
+                uint32_t i, l;
+                for (uint32_t t = gtid; t < pow2 / 2; t += gsize) {
+                    flip_pair(t, k, i, l);
+                    global_cmpx(p, i, l, len);
+                }
+                prep_barrier(bar, phase, nblocks);
+                for (uint32_t j = k / 4; j >= PREP_SMEM_SORT; j >>= 1) {
+                    for (uint32_t t = gtid; t < pow2 / 2; t += gsize) {
+                        shear_pair(t, j, i, l);
+                        global_cmpx(p, i, l, len);
+                    }
+                    prep_barrier(bar, phase, nblocks);
+                }
+            }
+            for (uint32_t ch = blockIdx.x; ch < nchunks; ch += nblocks) {
+                uint2* q = p + ch * PREP_SMEM_SORT;
+                const uint32_t clen = min(PREP_SMEM_SORT, len - ch * PREP_SMEM_SORT);
+                for (uint32_t x = threadIdx.x; x < clen; x += blockDim.x) s_sort[x] = __ldcg(q + x);
+                __syncthreads();
+                smem_sort(s_sort, clen, pass > 0);
+                for (uint32_t x = threadIdx.x; x < clen; x += blockDim.x) __stcg(q + x, s_sort[x]);
+                __syncthreads();
+            }
+            prep_barrier(bar, phase, nblocks);
         }
     }
     if (nlong) prep_barrier(bar, phase, nblocks);  // nlong is the same for every CTA
@@ -747,7 +829,7 @@ __global__ void __launch_bounds__(128) epilogue_kernel(uint32_t* counters, uint3
         r.bnd = counters[C_BND];
         r.grid = counters[C_GRID];
         r.rounds = counters[C_ROUNDS];
-        r.long_segments = counters[C_LONG];
+        r.long_segments = counters[C_LONG] + counters[C_HUGE];
         r.pad[0] = r.pad[1] = 0;
         r.t[0] = *reinterpret_cast<const unsigned long long*>(counters + C_T0);
         r.t[1] = *reinterpret_cast<const unsigned long long*>(counters + C_T0 + 2);
