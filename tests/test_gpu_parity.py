@@ -432,16 +432,19 @@ def test_full_size_1m_properties(tr, oracle):
         assert mine == {(min(i, j), max(i, j)) for j in hit.tolist()}
 
 
-def test_crowded_cell(tr, oracle):
-    """1500 bodies in ONE cell (over a million contacts): the counting sort, the on-demand stable
-    order and the narrow phase must still produce the exact keys, order, candidates and contact set."""
+@pytest.mark.parametrize("crowd", [1500, 2600])
+def test_crowded_cell(tr, oracle, crowd):
+    """1500 / 2600 bodies in ONE cell (1.1M / 3.4M contacts): the counting sort, the on-demand stable order (a crowded
+    cell is sorted by a CTA: in shared memory up to 2048 occupants, in global memory beyond) and the narrow phase
+    must still produce the exact keys, order, candidates and contact set; every crowded body has thousands of
+    contacts, so the K6 prep sorts its contact list too (2600: by the whole grid)."""
     n = 6000
     b = scenes.random_cloud(n, 5150, spheres=True, density_l=0.8)
     rs = np.random.RandomState(3)
-    # 1500 bodies packed into a ball much smaller than one cell (cell edge ~1.008)
-    b["pos"][:1500] = (rs.uniform(-0.05, 0.05, size=(1500, 3)) + np.array([0.5, 0.5, 0.5])).astype(np.float32)
+    # the crowd is packed into a ball much smaller than one cell (cell edge ~1.008)
+    b["pos"][:crowd] = (rs.uniform(-0.05, 0.05, size=(crowd, 3)) + np.array([0.5, 0.5, 0.5])).astype(np.float32)
     b["center"] = b["pos"]
-    b["vel"][:1500] = 0
+    b["vel"][:crowd] = 0
     p = tr.default_params(g=(0, 0, 0), max_contacts=4_000_000)
     with tr.World(p) as w:
         w.add(b)
@@ -452,7 +455,7 @@ def test_crowded_cell(tr, oracle):
         contacts = w.contacts()
     keys = oracle.grid_keys(b, (0, 0, 0), g["inv_cell"], g["bits"])
     assert np.array_equal(g["keys"], keys)
-    assert np.bincount(keys).max() >= 1500
+    assert np.bincount(keys).max() >= crowd
     order, _ = oracle.grid_sort(keys, np.arange(n, dtype=np.int32), g["bits"])
     assert np.array_equal(g["sorted_ids"].astype(np.int32), order)
     ocand, _, nc, _ = oracle.grid_pairs(b, np.ones(n, np.uint8), (0, 0, 0), g["inv_cell"], g["bits"], want_contacts=False)
@@ -881,3 +884,23 @@ def test_response_modes_soak(tr, n_side, steps):
     finally:
         for w in worlds:
             w.close()
+
+
+def test_overflow_recovery_survives_a_long_asynchronous_batch(tr):
+    """300 steps enqueued without a synchronisation, the FIRST of which overflows the initial contact buffers: the
+    ring of per-step records (256 entries) has long wrapped when the host finally looks, the overflow notice has not.
+    Same bits as a world that synchronised after every step (whose buffers grew at step 1, before anything else ran)."""
+    b = scenes.dense_lattice(32)
+    p = tr.default_params(g=(0, 0, 0))
+    with tr.World(p) as w1, tr.World(p) as w2:
+        w1.add(b)
+        w2.add(b)
+        for _ in range(300):
+            w1.step(1, sync=False)
+        for _ in range(300):
+            w2.step(1)
+        a, c = w1.read_bodies(), w2.read_bodies()
+        for f in FIELDS:
+            assert_bits_equal(a[f], c[f], f"long batch:{f}")
+        assert np.array_equal(w1.contacts(), w2.contacts())
+        assert w1.stats().steps == 300

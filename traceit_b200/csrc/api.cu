@@ -501,9 +501,9 @@ static int create_common(const tr_world_params* p, int device, int rank, int nra
     // device-side step bookkeeping: control words in device memory, the step records in mapped pinned host memory
     if (se == cudaSuccess) se = cudaMalloc(&w->d_ctl, CTL_WORDS * sizeof(uint32_t));
     if (se == cudaSuccess) se = cudaMemset(w->d_ctl, 0, CTL_WORDS * sizeof(uint32_t));
-    if (se == cudaSuccess) se = cudaHostAlloc(&w->h_ring, STEP_RING * sizeof(StepRecord), cudaHostAllocMapped);
+    if (se == cudaSuccess) se = cudaHostAlloc(&w->h_ring, (STEP_RING + 1) * sizeof(StepRecord), cudaHostAllocMapped);
     if (se == cudaSuccess) {
-        memset(w->h_ring, 0, STEP_RING * sizeof(StepRecord));
+        memset(w->h_ring, 0, (STEP_RING + 1) * sizeof(StepRecord));
         se = cudaHostGetDevicePointer((void**)&w->d_ring, w->h_ring, 0);
     }
     if (se != cudaSuccess) {

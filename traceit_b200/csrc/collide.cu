@@ -448,20 +448,23 @@ int collide_consume_records(tr_world* w, bool* overflow, uint32_t* overflow_seq,
     Collide* c = w->col;
     if (!c || !w->h_ring) return TR_OK;
     const uint32_t upto = w->coll_seq;
+    {
+        // a step that overflowed leaves its record in the slot behind the ring, where no later step overwrites it
+        StepRecord& note = w->h_ring[STEP_RING];
+        if (note.seq != 0) {
+            *overflow = true;
+            *overflow_seq = note.seq - 1u;
+            *found = ((uint64_t)note.contacts_hi << 32) | note.contacts_lo;
+            note.seq = 0;
+        }
+    }
     if (upto - w->ring_consumed > STEP_RING) w->ring_consumed = upto - STEP_RING;   // older records were overwritten
     for (uint32_t s = w->ring_consumed; s < upto; ++s) {
         const StepRecord r = w->h_ring[s % STEP_RING];
         if (r.seq != s + 1u) continue;            // not written (cannot happen after a sync) or overwritten
         if (r.flags & 4u) continue;               // no-op step behind an overflow: re-run by the recovery
         const uint64_t cnt = ((uint64_t)r.contacts_hi << 32) | r.contacts_lo;
-        if (r.flags & 1u) {
-            if (!*overflow) {
-                *overflow = true;
-                *overflow_seq = s;
-                *found = cnt;
-            }
-            continue;
-        }
+        if (r.flags & 1u) continue;               // reported through the notice slot above
         if (r.flags & 2u) {
             if (w->deferred_error == TR_OK) {
                 w->deferred_error = TR_ERR_CUDA;
@@ -555,9 +558,12 @@ int collide_debug_grid(tr_world* w, uint32_t* keys, uint32_t* sorted_ids, uint64
     }
     TR_TRY(debug_begin(w));
     Collide* c = state(w);
-    // K4, only here: the stable (key,id) order of the grid bodies
-    canon_kernel<<<(uint32_t)((w->n + 255) / 256), 256, 0, w->stream>>>((const SlotRec*)c->recs, rec_val_of(c), c->cell_start, grid_params(c),
-                                                                          c->counters, c->sorted_ids);
+    // K4, only here: the stable (key,id) order of the grid bodies (crowded cells: listed in long_list, sorted by CTAs with
+    // the half-edge array - idle between steps, at least as long as the record array - as scratch)
+    canon_kernel<<<(uint32_t)((w->n + 255) / 256), 256, 0, w->stream>>>((const SlotRec*)c->recs, c->cell_start, grid_params(c),
+                                                                          c->counters, c->sorted_ids, c->long_list);
+    canon_big_kernel<<<w->num_sms, 256, 0, w->stream>>>((const SlotRec*)c->recs, c->cell_start, c->counters, c->long_list, c->sorted_ids,
+                                                        c->he);
     TR_CUDA(cudaGetLastError());
     uint32_t hc[C_NHOST];
     TR_TRY(debug_end(w, hc));

@@ -157,19 +157,68 @@ __device__ __forceinline__ uint32_t rec_idflags(const SlotRec* recs, const uint3
     return rec_val ? rec_val[u] : recs[u].val;
 }
 
-// K4 (on demand): the stable (key,id) order.  The rank of a body inside its cell is the number of
-// co-occupants with a smaller id.
-__global__ void __launch_bounds__(256) canon_kernel(const SlotRec* __restrict__ recs, const uint32_t* __restrict__ rec_val,
-                                                    const uint32_t* __restrict__ cell_start, GridParams g,
-                                                    const uint32_t* __restrict__ counters, uint32_t* __restrict__ sorted_ids) {
+// K4 (on demand, tr_debug_grid): the stable (key,id) order.  The rank of a body inside its cell is the number of
+// co-occupants with a smaller id: counted directly in cells of up to CANON_SMALL bodies; a crowded cell is put on a
+// list by the thread of its first slot and sorted by a CTA (canon_big_kernel), so that a cell holding L bodies
+// costs O(L log^2 L), not L^2.
+constexpr uint32_t CANON_SMALL = 32;
+__global__ void __launch_bounds__(256) canon_kernel(const SlotRec* __restrict__ recs, const uint32_t* __restrict__ cell_start,
+                                                    GridParams g, uint32_t* counters, uint32_t* __restrict__ sorted_ids,
+                                                    uint32_t* __restrict__ big_cells) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= counters[C_GRID]) return;
-    const uint32_t key = cell_key(rec_center(recs, rec_val, t), g);
-    const uint32_t id = rec_idflags(recs, rec_val, t) & ID_MASK;
+    const uint32_t key = cell_key(recs[t].c, g);
+    const uint32_t id = recs[t].val & ID_MASK;
     const uint32_t s = cell_start[key], e = cell_start[key + 1];
+    if (e - s > CANON_SMALL) {
+        if (t == s) big_cells[atomicAdd(&counters[C_LONG], 1u)] = key;
+        return;
+    }
     uint32_t rank = 0;
-    for (uint32_t u = s; u < e; ++u) rank += ((rec_idflags(recs, rec_val, u) & ID_MASK) < id) ? 1u : 0u;
+    for (uint32_t u = s; u < e; ++u) rank += ((recs[u].val & ID_MASK) < id) ? 1u : 0u;
     sorted_ids[s + rank] = id;
+}
+
+__global__ void __launch_bounds__(256) canon_big_kernel(const SlotRec* __restrict__ recs, const uint32_t* __restrict__ cell_start,
+                                                        const uint32_t* __restrict__ counters, const uint32_t* __restrict__ big_cells,
+                                                        uint32_t* __restrict__ sorted_ids, uint2* __restrict__ scratch) {
+    __shared__ uint2 s_sort[PREP_SMEM_SORT];
+    const uint32_t nbig = counters[C_LONG];
+    for (uint32_t b = blockIdx.x; b < nbig; b += gridDim.x) {
+        const uint32_t key = big_cells[b];
+        const uint32_t s = cell_start[key], len = cell_start[key + 1] - s;
+        if (len <= PREP_SMEM_SORT) {
+            for (uint32_t k = threadIdx.x; k < len; k += blockDim.x) s_sort[k] = make_uint2(recs[s + k].val & ID_MASK, 0u);
+            __syncthreads();
+            smem_sort(s_sort, len, false);
+            for (uint32_t k = threadIdx.x; k < len; k += blockDim.x) sorted_ids[s + k] = s_sort[k].x;
+            __syncthreads();
+        } else {
+            // beyond the shared-memory size: the same network in global memory (scratch is at least as long as recs)
+            uint2* p = scratch + s;
+            for (uint32_t k = threadIdx.x; k < len; k += blockDim.x) p[k] = make_uint2(recs[s + k].val & ID_MASK, 0u);
+            __syncthreads();
+            uint32_t pow2 = 1;
+            while (pow2 < len) pow2 <<= 1;
+            uint32_t i, l;
+            for (uint32_t k = 2; k <= pow2; k <<= 1) {
+                for (uint32_t t = threadIdx.x; t < pow2 / 2; t += blockDim.x) {
+                    flip_pair(t, k, i, l);
+                    global_cmpx(p, i, l, len);
+                }
+                __syncthreads();
+                for (uint32_t j = k / 4; j >= 1; j >>= 1) {
+                    for (uint32_t t = threadIdx.x; t < pow2 / 2; t += blockDim.x) {
+                        shear_pair(t, j, i, l);
+                        global_cmpx(p, i, l, len);
+                    }
+                    __syncthreads();
+                }
+            }
+            for (uint32_t k = threadIdx.x; k < len; k += blockDim.x) sorted_ids[s + k] = __ldcg(p + k).x;
+            __syncthreads();
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -163,6 +163,75 @@ __device__ __forceinline__ uint32_t pack_val(uint32_t id, uint8_t f) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Bitonic sort of {key, payload} pairs by key: shared-memory chunks + global long-distance steps.
+// Used by the K6 prep (a body's contact list by partner id) and by K4 (a crowded cell by body id).
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t PREP_SMEM_SORT = 2048;  // entries a CTA sorts in shared memory (16 KB)
+
+// Ascending bitonic network in its flip + shear form: stage k = one "flip" step (i <-> the mirror position inside
+// its block of k) followed by shear steps at distances k/4 ... 1 (i <-> i + j inside blocks of 2j).  Every
+// compare-exchange puts the smaller key at the lower index, so virtual +inf padding beyond len never moves down
+// and any length works: a pair whose upper index is >= len is simply skipped.
+// pair t of a flip step of stage k / of a shear step at distance j:
+__device__ __forceinline__ void flip_pair(uint32_t t, uint32_t k, uint32_t& i, uint32_t& l) {
+    const uint32_t g = t / (k / 2), r = t % (k / 2);
+    i = g * k + r;
+    l = g * k + (k - 1 - r);
+}
+__device__ __forceinline__ void shear_pair(uint32_t t, uint32_t j, uint32_t& i, uint32_t& l) {
+    const uint32_t g = t / j, r = t % j;
+    i = g * 2 * j + r;
+    l = i + j;
+}
+__device__ __forceinline__ void smem_cmpx(uint2* s, uint32_t i, uint32_t l, uint32_t len) {
+    if (l < len && s[i].x > s[l].x) {
+        const uint2 t = s[i];
+        s[i] = s[l];
+        s[l] = t;
+    }
+}
+// one CTA, a chunk of len <= PREP_SMEM_SORT entries in shared memory: the whole network (from_k = 2) or only the
+// shear steps below the chunk size that finish a stage whose upper steps were done in global memory (shears_only)
+__device__ __forceinline__ void smem_sort(uint2* s, uint32_t len, bool shears_only) {
+    uint32_t pow2 = 1;
+    while (pow2 < len) pow2 <<= 1;
+    uint32_t i, l;
+    if (!shears_only) {
+        for (uint32_t k = 2; k <= pow2; k <<= 1) {
+            for (uint32_t t = threadIdx.x; t < pow2 / 2; t += blockDim.x) {
+                flip_pair(t, k, i, l);
+                smem_cmpx(s, i, l, len);
+            }
+            __syncthreads();
+            for (uint32_t j = k / 4; j >= 1; j >>= 1) {
+                for (uint32_t t = threadIdx.x; t < pow2 / 2; t += blockDim.x) {
+                    shear_pair(t, j, i, l);
+                    smem_cmpx(s, i, l, len);
+                }
+                __syncthreads();
+            }
+        }
+    } else {
+        for (uint32_t j = PREP_SMEM_SORT / 2; j >= 1; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < PREP_SMEM_SORT / 2; t += blockDim.x) {
+                shear_pair(t, j, i, l);
+                smem_cmpx(s, i, l, len);
+            }
+            __syncthreads();
+        }
+    }
+}
+__device__ __forceinline__ void global_cmpx(uint2* p, uint32_t i, uint32_t l, uint32_t len) {
+    if (l < len) {
+        const uint2 x = __ldcg(p + i), y = __ldcg(p + l);
+        if (x.x > y.x) {
+            __stcg(p + i, y);
+            __stcg(p + l, x);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Exclusive scan of a histogram in two unchained kernels (a look-back chain over
 // ~1000 tiles costs more in latency than the second launch):
 //   tile_sums_kernel   one CTA per tile of 2048 cells -> tile_sum[tile]

@@ -80,7 +80,9 @@ inline uint32_t grav_chunk_len(uint64_t n) {
 //    synchronisation, grows the buffers and re-runs the response of that step and the steps after it.
 //    [CTL_SEQ] = number of collision steps completed on the device.
 //  * tr_world::h_ring (mapped pinned host memory, written by the last kernel of a collision step):
-//    one StepRecord per step - counts, the executor's statistics, globaltimer stamps of the phases.
+//    one StepRecord per step - counts, the executor's statistics, globaltimer stamps of the phases - in a ring of
+//    STEP_RING records, plus one slot (index STEP_RING) that holds the record of a step that overflowed until the
+//    host has dealt with it.
 enum { CTL_ABORT = 0, CTL_SEQ = 1, CTL_WORDS = 8 };
 constexpr uint32_t STEP_RING = 256;
 struct StepRecord {
@@ -176,7 +178,7 @@ struct tr_world {
 
     // device-side step bookkeeping (see StepRecord above)
     uint32_t* d_ctl = nullptr;              // device: CTL_WORDS words
-    tr::StepRecord* h_ring = nullptr;       // mapped pinned host memory, STEP_RING records
+    tr::StepRecord* h_ring = nullptr;       // mapped pinned host memory, STEP_RING + 1 records
     tr::StepRecord* d_ring = nullptr;       // device alias of h_ring
     uint32_t ring_consumed = 0;             // records folded into stats so far (== sequence number of the next one)
     uint32_t coll_seq = 0;                  // collision steps enqueued so far
