@@ -74,9 +74,21 @@ def raw_rows(rep):
 # ---- the numbers bench.py reads back (traffic / ncu stopwatch), with their provenance
 if have("prof_broad_cfg3.ncu-rep"):
     k = raw_rows("prof_broad_cfg3")
-    json.dump({f"cfg3:{N}": {"kernel_us_sum": sum(x["us"] for x in k), "dram_bytes": int(sum(x["dram"] for x in k)),
-                             "kernels": [[x["name"], round(x["us"], 2)] for x in k],
-                             "source": f"profiles/{tag}_broadphase_kernels_cfg3_ncu.txt: ncu --set full, the four kernels of one step, cold caches and serialised"}},
+    # durations: the timing-only launch list (the profiling recipe's `--metrics gpu__time_duration.sum` pass, averaged over its
+    # launches); DRAM bytes: the --set full capture of one step
+    avg = {}
+    lst = os.path.join(P, f"{tag}_launches_collide_cfg3.csv")
+    if os.path.exists(lst):
+        for ln in open(lst):
+            f = ln.strip().split(",")
+            if len(f) == 5 and f[0].startswith("tr::"):
+                avg[f[0][4:]] = float(f[3])
+    names = ["keys_kernel", "tile_sums_kernel", "scan_kernel", "scatter_kernel"]
+    us = [avg.get(nm, next(x["us"] for x in k if x["name"].endswith(nm))) for nm in names]
+    json.dump({f"cfg3:{N}": {"kernel_us_sum": round(sum(us), 2), "dram_bytes": int(sum(x["dram"] for x in k)),
+                             "kernels": [[nm, round(u, 2)] for nm, u in zip(names, us)],
+                             "source": f"durations: profiles/{tag}_launches_collide_cfg3.csv (ncu --metrics gpu__time_duration.sum, average per launch, cold caches and "
+                                       f"serialised); DRAM bytes: profiles/{tag}_broadphase_kernels_cfg3_ncu.txt (ncu --set full, the four kernels of one step)"}},
               open(os.path.join(P, "broadphase_ncu.json"), "w"), indent=1)
 nar = {}
 for c in ("cfg3", "cfg5"):
