@@ -293,7 +293,7 @@ static int launch_response(tr_world* w, cudaStream_t st) {
     }
     PrepArgs pa{c->ckeys, c->cap_contacts, c->counters, w->d_ctl, c->body_cnt, c->seg, c->arank, c->he, c->long_list, c->huge_list, c->dep, c->crec,
                 c->cver, (ContactGeo*)c->cgeo, flow ? (BodyRec*)c->brec : nullptr, c->frontier[0], flow ? C_QTAIL : C_FRONT,
-                w->pos_m[w->cur], w->vel_rest, w->center_r, w->half_ext, w->flags};
+                w->pos_m[w->cur], w->vel_rest, w->center_r, w->half_ext, w->flags, (uint32_t)w->n};
     prep_kernel<<<c->prep_blocks, PREP_THREADS, 0, st>>>(pa);
     TR_CUDA(cudaGetLastError());
     if (flow) {

@@ -48,11 +48,13 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ ce
             }
             if (fits && in_domain) {
                 key = pack_key(__float2int_rd(ux), __float2int_rd(uy), __float2int_rd(uz), g);
+                TR_ASSERT(key < sentinel);
                 k = 1;
                 atomicAdd(&cell_count[key], 1u);   // result unused: a fire-and-forget RED
                 // grid bodies within two cells of the domain boundary are the only ones a "far" body can touch
                 if (fmaxf(fmaxf(fabsf(ux), fabsf(uy)), fabsf(uz)) >= 32766.0f) {
                     const uint32_t slot = atomicAdd(&counters[C_BND], 1u);
+                    TR_ASSERT(slot < n);
                     bnd_list[slot] = pack_val(i, f);
                     bnd_c[slot] = c;
                 }
@@ -62,6 +64,7 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ ce
                 // more than the largest admitted reach) and oversize side-list bodies.
                 k = 4;
                 const uint32_t slot = atomicAdd(&counters[C_FAR], 1u);
+                TR_ASSERT(slot < n);
                 far_list[slot] = pack_val(i, f);
                 far_c[slot] = c;
             } else if (fits && g.rmax_grid < 1.0e18f) {
@@ -74,6 +77,7 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ ce
             } else {
                 k = 2;
                 uint32_t slot = atomicAdd(&counters[C_SIDE], 1u);
+                TR_ASSERT(slot < n);
                 side_list[slot] = i;
             }
         }
@@ -139,6 +143,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict
     const uint32_t val = pack_val(i, flags[i]);
     const uint32_t old = atomicSub(&cell_count[key], 1u);
     const uint32_t slot = cell_start[key] + old - 1u;
+    TR_ASSERT(old >= 1u && old <= n && slot < n && slot < cell_start[key + 1]);
     if (rec_val) {
         reinterpret_cast<float4*>(recs)[slot] = c;
         rec_val[slot] = val;
@@ -385,6 +390,8 @@ __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* _
     }
     const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
     const uint32_t off = incl - mine;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) TR_ASSERT(len[r] <= ngrid && (len[r] == 0 || rs[r] + len[r] <= ngrid));
     uint32_t nh = 0;                               // staged hits (warp-uniform)
     __syncwarp();
     for (uint32_t base = 0; base < total; base += NARROW_LIST) {
@@ -394,7 +401,10 @@ __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* _
         for (int r = 0; r < 10; ++r) {
             const uint32_t lo = max(wo, base), hi = min(wo + len[r], base + (uint32_t)NARROW_LIST);
             if (!big) {
-                for (uint32_t k = lo; k < hi; ++k) sw.u[k - base] = ((rs[r] + (k - wo)) << 5) | lane;
+                for (uint32_t k = lo; k < hi; ++k) {
+                    TR_ASSERT(k - base < (uint32_t)NARROW_LIST);
+                    sw.u[k - base] = ((rs[r] + (k - wo)) << 5) | lane;
+                }
             } else {
                 for (uint32_t k = lo; k < hi; ++k) {
                     sw.u[k - base] = rs[r] + (k - wo);
@@ -421,6 +431,7 @@ __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* _
                     } else {
                         ow[k] = sw.o[p];
                     }
+                    TR_ASSERT(u < ngrid && ow[k] < 32u);
                     if (MIXED || !rec_val) {
                         ld_rec(recs + u, cb[k], vb[k], hb[k]);
                     } else {
@@ -447,6 +458,7 @@ __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* _
                 }
                 const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
                 if (m) {
+                    TR_ASSERT(nh + 32u <= (uint32_t)NARROW_STAGE);
                     if (hit) sw.hit[nh + __popc(m & ((1u << lane) - 1u))] = pr;
                     nh += __popc(m);
                     __syncwarp();

@@ -14,6 +14,17 @@
 
 namespace cg = cooperative_groups;
 
+// Index checks of a CHECKED build (make EXTRA=-DTR_CHECKED TAG=checked OUT=../libtraceit_b200_checked.so): every
+// computed index into a scratch array is asserted against the array's extent; a violation traps the kernel
+// (cudaErrorAssert at the next synchronisation).  compute-sanitizer is closed on the development pool, so the GPU
+// suite is run once against this build instead (profiles/r02_checked_build.txt).  The product build compiles them out.
+#ifdef TR_CHECKED
+#include <cassert>
+#define TR_ASSERT(cond) assert(cond)
+#else
+#define TR_ASSERT(cond) ((void)0)
+#endif
+
 namespace tr {
 
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;

@@ -161,6 +161,7 @@ struct PrepArgs {
     const float4* center_r;
     const float4* half_ext;
     const uint8_t* flags;
+    uint32_t n;             // bodies (index checks of the checked build)
 };
 
 // all CTAs of prep_kernel are resident (the host sizes the grid from the occupancy API): a counter barrier
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
     for (uint32_t c = gtid; c < cn; c += gsize) {
         const unsigned long long k = a.ckeys[c];
         const uint32_t i = (uint32_t)(k >> 32), j = (uint32_t)k;
+        TR_ASSERT(i < j && j < a.n);
         a.arank[c] = make_uint2(atomicAdd(&a.body_cnt[i], 1u), atomicAdd(&a.body_cnt[j], 1u));
         a.queue[c] = EMPTY;
     }
@@ -257,6 +259,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
         uint32_t base = 0;
         if (lane == 31 && total) base = atomicAdd(&a.counters[C_HE], total);
         base = __shfl_sync(0xFFFFFFFFu, base, 31) + (incl - need);
+        TR_ASSERT((unsigned long long)base + li + lj <= 2ull * a.cap);
         if (li) {
             a.seg[i] = make_uint2(base, li);
             if (li > PREP_SMEM_SORT) a.huge_list[atomicAdd(&a.counters[C_HUGE], 1u)] = i;
@@ -276,6 +279,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
         const unsigned long long k = a.ckeys[c];
         const uint32_t i = (uint32_t)(k >> 32), j = (uint32_t)k;
         const uint2 r = a.arank[c];
+        TR_ASSERT(r.x < __ldcg(&a.seg[i]).y && r.y < __ldcg(&a.seg[j]).y);
         a.he[__ldcg(&a.seg[i]).x + r.x] = make_uint2(j, c);
         a.he[__ldcg(&a.seg[j]).x + r.y] = make_uint2(i, c);
         if (r.x == 0) a.body_cnt[i] = 0;
@@ -346,6 +350,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
         uint32_t ri, rj, si, sj;
         segment_lookup(a.he, __ldcg(&a.seg[i]), j, ri, si);
         segment_lookup(a.he, __ldcg(&a.seg[j]), i, rj, sj);
+        TR_ASSERT(ri < __ldcg(&a.seg[i]).y && rj < __ldcg(&a.seg[j]).y && (si == EMPTY || si < cn) && (sj == EMPTY || sj < cn));
         const uint8_t fi = a.flags[i], fj = a.flags[j];
         const float4 vi = a.vel_rest[i], vj = a.vel_rest[j], pi = a.pos_m[i], pj = a.pos_m[j];
         if (a.brec) {                                  // version-0 records, written once per body
@@ -368,7 +373,11 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
         g.e = (vj.w < vi.w) ? vj.w : vi.w;               // std::min(a.rest, b.rest)
         g.bits = ((fi & F_STATIC) ? 1u : 0u) | ((fj & F_STATIC) ? 2u : 0u);
         a.cgeo[c] = g;
-        if (d == 0) a.queue[warp_reserve32(&a.counters[a.ready_counter])] = c;
+        if (d == 0) {
+            const uint32_t qs = warp_reserve32(&a.counters[a.ready_counter]);
+            TR_ASSERT(qs < cn);
+            a.queue[qs] = c;
+        }
     }
 }
 
@@ -690,7 +699,9 @@ __global__ void __launch_bounds__(128) response_flow_kernel(FlowArgs a, const ui
                     next = s1;
                     rec = n1;
                 } else {
-                    vq[atomicAdd(&counters[C_QTAIL], 1u)] = s1;   // second ready successor: to the global queue
+                    const uint32_t qs = atomicAdd(&counters[C_QTAIL], 1u);   // second ready successor: to the global queue
+                    TR_ASSERT(qs < c_n && s1 < c_n);
+                    vq[qs] = s1;
                 }
             }
             cur = next;
@@ -713,6 +724,7 @@ __global__ void __launch_bounds__(128) response_flow_kernel(FlowArgs a, const ui
             }
             if (alive) {
                 const uint32_t c = vq[slot];
+                TR_ASSERT(slot < c_n && (c == EMPTY || c < c_n));
                 if (c != EMPTY) {
                     cur = c;
                     rec = crec[c];

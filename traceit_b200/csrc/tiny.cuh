@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(TINY_MAX) tiny_step_kernel(TinyArgs a, int nst
             uint32_t w = s_off[i];
             for (uint32_t j = i + 1; j < n; ++j)
                 if (tiny_contact(fi, s_flag[j], ci, s_cen[j], hi, s_half[j])) {
+                    TR_ASSERT(w < s_off[i + 1] && w < n * (n - 1u) / 2u);
                     if (w < (uint32_t)TINY_SMEM_PAIRS) s_pairs[w] = (i << 16) | j;
                     a.ckeys[w] = ((unsigned long long)i << 32) | j;
                     ++w;
