@@ -904,3 +904,39 @@ def test_overflow_recovery_survives_a_long_asynchronous_batch(tr):
             assert_bits_equal(a[f], c[f], f"long batch:{f}")
         assert np.array_equal(w1.contacts(), w2.contacts())
         assert w1.stats().steps == 300
+
+
+def test_two_worlds_stepped_concurrently_from_two_host_threads(tr):
+    """Two worlds on one GPU, each driven by its own host thread on its own stream: their collision steps overlap on
+    the device (the K6 prep synchronises its grid by itself - it is a cooperative launch, so two of them cannot end up
+    half resident waiting for each other).  Both must finish and equal a world stepped alone."""
+    import threading
+    b = scenes.dense_lattice(40)          # 64,000 packed spheres, ~190K contacts: the prep uses its whole grid
+    p = tr.default_params(g=(0, 0, 0))
+    steps = 40
+    out, errs = {}, []
+
+    def drive(name):
+        try:
+            with tr.World(p) as w:
+                w.add(b)
+                for _ in range(steps):
+                    w.step(1, sync=False)
+                out[name] = w.read_bodies()
+        except Exception as e:      # surfaced below: an exception in a thread must fail the test
+            errs.append(e)
+
+    ts = [threading.Thread(target=drive, args=(k,)) for k in ("a", "b")]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    assert not any(t.is_alive() for t in ts), "a world did not finish: the two collision steps deadlocked"
+    assert not errs, errs
+    with tr.World(p) as w:
+        w.add(b)
+        w.step(steps)
+        alone = w.read_bodies()
+    for name in ("a", "b"):
+        for f in FIELDS:
+            assert_bits_equal(out[name][f], alone[f], f"world {name}:{f}")

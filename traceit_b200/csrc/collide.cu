@@ -294,8 +294,22 @@ static int launch_response(tr_world* w, cudaStream_t st) {
     PrepArgs pa{c->ckeys, c->cap_contacts, c->counters, w->d_ctl, c->body_cnt, c->seg, c->arank, c->he, c->long_list, c->huge_list, c->dep, c->crec,
                 c->cver, (ContactGeo*)c->cgeo, flow ? (BodyRec*)c->brec : nullptr, c->frontier[0], flow ? C_QTAIL : C_FRONT,
                 w->pos_m[w->cur], w->vel_rest, w->center_r, w->half_ext, w->flags, (uint32_t)w->n};
-    prep_kernel<<<c->prep_blocks, PREP_THREADS, 0, st>>>(pa);
-    TR_CUDA(cudaGetLastError());
+    {
+        // a COOPERATIVE launch: prep_kernel synchronises its grid with a counter barrier, so all its CTAs must be resident
+        // at once - also when another world's kernels (other streams, other host threads) compete for the SMs, where two
+        // half-resident barrier kernels would wait for each other for ever.  Captured into the step's graph like any launch.
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)c->prep_blocks);
+        cfg.blockDim = dim3(PREP_THREADS);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        TR_CUDA(cudaLaunchKernelEx(&cfg, prep_kernel, pa));
+    }
     if (flow) {
         FlowArgs ra{w->pos_m[w->cur], w->vel_rest, w->pos_m[w->cur], w->vel_rest, (BodyRec*)c->brec, c->cver, (const ContactGeo*)c->cgeo};
         if (executor_wide(w, c)) {
