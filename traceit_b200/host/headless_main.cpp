@@ -171,7 +171,7 @@ int main(int argc, char** argv) {
     traceit_b200::options().write_trajectory_file = file;
 
     std::ofstream coords;
-    double timed_ms = 0.0;
+    double timed_ms = 0.0, pack_ms = 0.0, step_ms = 0.0, unpack_ms = 0.0;
     int timed_frames = 0;
     try {
         for (int s = 0; s < steps; ++s) {
@@ -179,6 +179,11 @@ int main(int argc, char** argv) {
             traceit_b200::updatePhysics(w, coords);   // the call of src/main.cpp:1589
             if (s >= 2) {
                 timed_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                double a, b, c;
+                traceit_b200::last_frame_breakdown(a, b, c);
+                pack_ms += a;
+                step_ms += b;
+                unpack_ms += c;
                 ++timed_frames;
             }
             if ((s + 1 == 100 || s + 1 == steps) && trace >= 0 && trace < (int)w.objects.size()) {
@@ -193,9 +198,10 @@ int main(int argc, char** argv) {
     }
     if (timeit && timed_frames > 0)
         std::printf("TIME {\"api\": \"traceit_b200::updatePhysics(world&, ofstream&) on 232-byte reference-shaped objects\", "
-                    "\"n_bodies\": %zu, \"frames\": %d, \"ms_per_frame\": %.4f, \"shape\": \"%s\", \"h2d_bytes_per_frame\": %llu, "
-                    "\"d2h_bytes_per_frame\": %llu}\n",
-                    w.objects.size(), timed_frames, timed_ms / timed_frames, cloud <= 0 ? "default scene" : (pack ? "cfg5 pack" : "sparse cloud"),
+                    "\"n_bodies\": %zu, \"frames\": %d, \"ms_per_frame\": %.4f, \"host_pack_compare_ms\": %.4f, \"step_and_readback_ms\": %.4f, "
+                    "\"host_unpack_history_ms\": %.4f, \"shape\": \"%s\", \"h2d_bytes_per_frame\": %llu, \"d2h_bytes_per_frame\": %llu}\n",
+                    w.objects.size(), timed_frames, timed_ms / timed_frames, pack_ms / timed_frames, step_ms / timed_frames, unpack_ms / timed_frames,
+                    cloud <= 0 ? "default scene" : (pack ? "cfg5 pack" : "sparse cloud"),
                     (unsigned long long)traceit_b200::last_frame_h2d_bytes(), (unsigned long long)traceit_b200::last_frame_d2h_bytes());
     std::printf("bodies %zu steps %d hash 0x%016llx\n", w.objects.size(), steps, (unsigned long long)state_hash(w));
     traceit_b200::release(w);

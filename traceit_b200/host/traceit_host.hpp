@@ -31,6 +31,7 @@
 #pragma once
 
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <fstream>
@@ -67,7 +68,11 @@ struct Session {
     ~Session() { if (w) tr_world_destroy(w); }
 };
 
-struct FrameBytes { unsigned long long h2d = 0, d2h = 0; };
+struct FrameBytes {
+    unsigned long long h2d = 0, d2h = 0;
+    double pack_ms = 0, step_ms = 0, unpack_ms = 0;   // host pack + compare (+ upload of changes) | step + read-back | host unpack + history
+};
+inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 inline FrameBytes& frame_bytes() {
     static FrameBytes b;
     return b;
@@ -184,6 +189,7 @@ void updatePhysics(World& w, std::ofstream& coords) {
     detail::FrameBytes& fb = detail::frame_bytes();
     fb = detail::FrameBytes{};
     if (n) {
+        const double t_pack0 = detail::now_ms();
         if (s.shadow.size() != n) {
             // first frame of this world: create every body on the device
             s.shadow.resize(n);
@@ -223,8 +229,12 @@ void updatePhysics(World& w, std::ofstream& coords) {
                 fb.h2d += (dhi - dlo) * sizeof(tr_body_desc);
             }
         }
+        const double t_step0 = detail::now_ms();
+        fb.pack_ms = t_step0 - t_pack0;
         detail::check(tr_step_frame(s.w, n, nullptr, s.frame.data(), 1), "tr_step_frame");
         fb.d2h += n * sizeof(tr_frame_body);
+        const double t_unpack0 = detail::now_ms();
+        fb.step_ms = t_unpack0 - t_step0;
         std::vector<std::vector<size_t>> dump(17);
         detail::parallel_for(n, [&](size_t lo, size_t hi, unsigned k) {
             for (size_t i = lo; i < hi; ++i) {
@@ -259,6 +269,7 @@ void updatePhysics(World& w, std::ofstream& coords) {
                         for (const auto& pt : w.objects[i].trajectory) coords << pt.x << "(м)\t" << pt.y << "(м)\t" << pt.z << "(м)\n";
                     }
         }
+        fb.unpack_ms = detail::now_ms() - t_unpack0;
     }
     if (opt.write_trajectory_file) coords.close();
 }
@@ -266,6 +277,12 @@ void updatePhysics(World& w, std::ofstream& coords) {
 // bytes the last updatePhysics call moved over PCIe (observability for the harness / bench.py)
 inline unsigned long long last_frame_h2d_bytes() { return detail::frame_bytes().h2d; }
 inline unsigned long long last_frame_d2h_bytes() { return detail::frame_bytes().d2h; }
+// where the last frame's time went: host pack + compare (+ upload of what changed), the step + read-back, host unpack + history
+inline void last_frame_breakdown(double& pack_ms, double& step_ms, double& unpack_ms) {
+    pack_ms = detail::frame_bytes().pack_ms;
+    step_ms = detail::frame_bytes().step_ms;
+    unpack_ms = detail::frame_bytes().unpack_ms;
+}
 
 // toSpherical of the creation form (src/main.cpp:1080-1089), any {x,y,z} aggregate.
 template <class Vec3>
