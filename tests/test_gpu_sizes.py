@@ -79,11 +79,12 @@ def test_gravity_plus_collisions_k20_at_65536_vs_oracle_golden(tr, oracle):
     assert evel <= CONTACT_VEL_REL_TOL
 
 
-def test_step_frame_equals_step(tr, oracle):
+@pytest.mark.parametrize("n", [100, 5000])
+def test_step_frame_equals_step(tr, oracle, n):
     """tr_step_frame (forces up, pos/vel/centre down) == tr_set_force + tr_step + tr_read_bodies, bit for bit,
-    and == the oracle fed the same forces."""
+    and == the oracle fed the same forces.  n = 100 takes the single-CTA path, whose kernel writes the frame into
+    mapped pinned memory itself; n = 5000 the grid pipeline + pack kernel + copy."""
     rs = np.random.RandomState(3)
-    n = 5000
     b = scenes.random_cloud(n, 12, spheres=True, density_l=0.6)
     b["stationary"][::17] = 1
     want = b.copy()

@@ -506,10 +506,13 @@ static int create_common(const tr_world_params* p, int device, int rank, int nra
         memset(w->h_ring, 0, (STEP_RING + 1) * sizeof(StepRecord));
         se = cudaHostGetDevicePointer((void**)&w->d_ring, w->h_ring, 0);
     }
+    if (se == cudaSuccess) se = cudaHostAlloc(&w->h_frame, TINY_FRAME_BODIES * 9 * sizeof(float), cudaHostAllocMapped);
+    if (se == cudaSuccess) se = cudaHostGetDevicePointer((void**)&w->d_frame, w->h_frame, 0);
     if (se != cudaSuccess) {
         if (w->stream) cudaStreamDestroy(w->stream);
         cudaFree(w->d_ctl);
         if (w->h_ring) cudaFreeHost(w->h_ring);
+        if (w->h_frame) cudaFreeHost(w->h_frame);
         delete w;
         return cuda_fail(se, "world creation (stream / control block)", __FILE__, __LINE__);
     }
@@ -709,6 +712,7 @@ int tr_world_destroy(tr_world* w) {
     cudaFree(w->traj_cnt);
     cudaFree(w->d_ctl);
     if (w->h_ring) cudaFreeHost(w->h_ring);
+    if (w->h_frame) cudaFreeHost(w->h_frame);
     if (w->own_stream && w->stream) cudaStreamDestroy(w->stream);
     delete w;
     return TR_OK;
@@ -893,7 +897,18 @@ int tr_step_frame(tr_world* w, uint64_t n, const float* force_xyz, tr_frame_body
         TR_CUDA(cudaGetLastError());
         w->stats.kernel_launches += 1;
     }
-    TR_TRY(tr_step(w, nsteps));
+    w->frame_request = out != nullptr && nsteps > 0;
+    w->frame_ready = false;
+    int step_rc = tr_step(w, nsteps);
+    w->frame_request = false;
+    TR_TRY(step_rc);
+    if (out && w->frame_ready) {
+        // a small world's single-CTA step already left the frame in mapped pinned memory: no pack kernel, no copy
+        w->frame_ready = false;
+        TR_TRY(tr_sync(w));
+        memcpy(out, w->h_frame, (size_t)n * sizeof(tr_frame_body));
+        return TR_OK;
+    }
     if (out) {
         TR_TRY(settle_if_pending(w));
         const size_t bytes = (size_t)n * sizeof(tr_frame_body);

@@ -408,6 +408,8 @@ int tiny_steps(tr_world* w, const StepConsts& sc, int nsteps, bool* taken) {
     a.traj_cnt = w->traj_cnt;
     a.traj_max = w->traj ? w->traj_max : 0;
     a.traj_stride = w->traj_stride;
+    a.frame_out = w->frame_request ? w->d_frame : nullptr;
+    w->frame_ready = w->frame_request;
     tiny_step_kernel<<<1, TINY_MAX, 0, w->stream>>>(a, nsteps);
     TR_CUDA(cudaGetLastError());
     w->stats.kernel_launches += 1;

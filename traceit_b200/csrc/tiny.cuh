@@ -45,7 +45,9 @@ struct TinyArgs {
     uint32_t* traj_cnt;
     uint32_t traj_max;
     unsigned long long traj_stride;
+    float* frame_out;            // optional (mapped pinned host memory): pos, vel, centre of every body after the last step, 9 floats each
 };
+static_assert(TINY_MAX == (int)TINY_FRAME_BODIES, "frame buffer sized for the single-CTA path");
 
 // guards + predicate of one (i<j) visit, main.cpp:695-707
 __device__ __forceinline__ bool tiny_contact(uint8_t fi, uint8_t fj, const float4 ci, const float4 cj, const float4 hi, const float4 hj) {
@@ -157,6 +159,12 @@ __global__ void __launch_bounds__(TINY_MAX) tiny_step_kernel(TinyArgs a, int nst
         a.vel_rest[i] = s_vel[i];
         a.center_r[i] = s_cen[i];
         a.force[i] = frc;
+        if (a.frame_out) {       // tr_step_frame's read-back without a pack kernel and a copy: 36 bytes over PCIe by this thread
+            float* f = a.frame_out + 9 * i;
+            f[0] = s_pos[i].x; f[1] = s_pos[i].y; f[2] = s_pos[i].z;
+            f[3] = s_vel[i].x; f[4] = s_vel[i].y; f[5] = s_vel[i].z;
+            f[6] = s_cen[i].x; f[7] = s_cen[i].y; f[8] = s_cen[i].z;
+        }
     }
     if (i == 0 && a.collide && nsteps > 0) {
         // one record for the launch (the last step's contact count; the stamps bracket the last step)

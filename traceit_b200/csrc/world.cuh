@@ -84,6 +84,7 @@ inline uint32_t grav_chunk_len(uint64_t n) {
 //    STEP_RING records, plus one slot (index STEP_RING) that holds the record of a step that overflowed until the
 //    host has dealt with it.
 enum { CTL_ABORT = 0, CTL_SEQ = 1, CTL_WORDS = 8 };
+constexpr uint32_t TINY_FRAME_BODIES = 256;   // == TINY_MAX (tiny.cuh)
 constexpr uint32_t STEP_RING = 256;
 struct StepRecord {
     uint32_t seq;            // 1 + sequence number (0 = never written)
@@ -187,7 +188,11 @@ struct tr_world {
         int cur_after;                      // pos_m buffer index that is live after the step
     };
     std::vector<PendingStep> pending_steps;
-    bool in_recovery = false;
+    // small worlds: the single-CTA step writes the frame read-back (pos, vel, centre) straight into mapped pinned memory
+    float* h_frame = nullptr;               // TINY_FRAME_BODIES x 9 floats, host view
+    float* d_frame = nullptr;               // device alias
+    bool frame_request = false;             // tr_step_frame asks the step it enqueues to leave the frame there
+    bool frame_ready = false;               // ... and the single-CTA step did
 
     // stats / timing
     tr_stats stats{};
