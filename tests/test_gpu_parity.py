@@ -743,6 +743,12 @@ def test_small_world_single_cta_step_bit_exact(tr, oracle, n, dens, steps):
     b["stationary"][::5] = 1
     b["mass"][::13] = 0
     b["force"] = rs.uniform(-20, 20, size=(n, 3)).astype(np.float32)
+    if n >= 37:      # degenerate bodies: the brute-force step must treat them exactly as the reference does
+        b["pos"][5] = (np.nan, 0, 0)          # never touches anything (every comparison with NaN is false)
+        b["pos"][6] = (1.0e30, -1.0e30, 0)    # far outside any grid domain
+        b["radius"][8] = np.inf               # a sphere that touches every other sphere
+        b["isSphere"][8] = 1
+        b["center"] = b["pos"]
     want = b.copy()
     oracle.step(want, oracle.default_params(), steps)
     got, contacts, st = gpu_run(tr, b, steps)
