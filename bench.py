@@ -427,7 +427,7 @@ def measure(ctx: Ctx, name: str, n: int | None, steps: int, warmup: int, *, shar
               "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": ncu.get("dram_bytes"), "peak_source": src,
               "algorithmic": f"{BROADPHASE_BYTES_PER_BODY} B/body x {n} bodies (SURVEY.md 8d: the budget of a 4-pass radix sort + gather)",
               "kernel_ms": broad_ms,
-              "stopwatch": "CUDA events around the broad-phase kernels inside the step's CUDA graph",
+              "stopwatch": "%globaltimer stamps inside the step's CUDA graph: first CTA of K2 -> first CTA of K5 (launch gaps between the four kernels included)",
               "note": "TIME AGAINST A BYTE BUDGET, not achieved DRAM bandwidth: the shipped one-digit counting sort moves fewer "
                       "bytes than the budget it is scored against (see measured_bytes_per_body)"}
         if ncu:
