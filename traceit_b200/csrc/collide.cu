@@ -376,8 +376,12 @@ void collide_poll_stats(tr_world*) {}
 // Whole steps of a small world in one kernel (tiny.cuh).  integrate: the step's O(N) part runs here too.
 static bool tiny_eligible(const tr_world* w) {
     static const bool off = getenv("TR_NO_TINY") != nullptr;
+    // one thread replays the contacts of a small world sequentially (~80 ns each): fine for the handful of contacts such a
+    // world normally has, slower than the grid pipeline's parallel executor for a dense clump - the last step the host
+    // has seen decides
+    const bool clump = w->col && w->col->last_contacts > 128;
     return !off && !(w->params.debug_flags & TR_DEBUG_NO_TINY) && w->n <= (uint64_t)TINY_MAX && w->nranks == 1 &&
-           (w->params.flags & TR_PAIR_GRAVITY) == 0;
+           (w->params.flags & TR_PAIR_GRAVITY) == 0 && !clump;
 }
 
 int tiny_steps(tr_world* w, const StepConsts& sc, int nsteps, bool* taken) {
