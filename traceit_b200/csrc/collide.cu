@@ -227,13 +227,6 @@ int collide_grow_contacts(tr_world* w, uint64_t found) {
     return alloc_contact_buffers(w, want);
 }
 
-// all-sphere worlds: the id|flags array of the compact record layout lives behind the float4 array, in the same buffer
-static uint32_t* rec_val_of(const Collide* c) {
-    static const bool compact = getenv("TR_COMPACT_RECS") != nullptr;   // measured alternative, see collide_broad.cuh (K3b)
-    if (!compact || c->mixed) return nullptr;
-    return reinterpret_cast<uint32_t*>(reinterpret_cast<float4*>(c->recs) + c->cap_bodies);
-}
-
 // K2-K3b on the stream (used inside the step's graph capture and by the debug entry points).
 static int launch_broad(tr_world* w, cudaStream_t st) {
     Collide* c = state(w);
@@ -247,7 +240,7 @@ static int launch_broad(tr_world* w, cudaStream_t st) {
     tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, ncell, c->tile_sum);
     scan_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, c->tile_sum, c->cell_start, ncell, c->counters, C_GRID);
     scatter_kernel<<<blocks, 256, 0, st>>>(c->keys, ncell, w->flags, w->center_r, c->mixed ? w->half_ext : nullptr, n, c->cell_start,
-                                           c->cell_count, (SlotRec*)c->recs, rec_val_of(c));
+                                           c->cell_count, (SlotRec*)c->recs);
     TR_CUDA(cudaGetLastError());
     return TR_OK;
 }
@@ -262,10 +255,10 @@ static int launch_narrow(tr_world* w, cudaStream_t st, unsigned long long* out, 
     const GridParams g = grid_params(c);
     OutsideArgs oa{c->side_list, c->far_list, c->far_c, c->bnd_list, c->bnd_c, w->center_r, w->half_ext, w->flags, c->klass, (uint32_t)w->n};
     if (c->mixed)
-        narrow_kernel<CANDIDATES, true><<<slot_blocks + outside_blocks, NARROW_THREADS, 0, st>>>((const SlotRec*)c->recs, nullptr, c->cell_start, c->counters,
+        narrow_kernel<CANDIDATES, true><<<slot_blocks + outside_blocks, NARROW_THREADS, 0, st>>>((const SlotRec*)c->recs, c->cell_start, c->counters,
                                                                                                 g, slot_blocks, oa, out, cap, counter);
     else
-        narrow_kernel<CANDIDATES, false><<<slot_blocks + outside_blocks, NARROW_THREADS, 0, st>>>((const SlotRec*)c->recs, rec_val_of(c), c->cell_start, c->counters,
+        narrow_kernel<CANDIDATES, false><<<slot_blocks + outside_blocks, NARROW_THREADS, 0, st>>>((const SlotRec*)c->recs, c->cell_start, c->counters,
                                                                                                  g, slot_blocks, oa, out, cap, counter);
     TR_CUDA(cudaGetLastError());
     return TR_OK;
@@ -359,7 +352,6 @@ static uint64_t step_signature(tr_world* w) {
                           c->ckeys, c->he, c->brec, c->counters, w->d_ctl, w->d_ring, c->frontier[1]};
     for (const void* p : ptrs) h = mix64(h, (uint64_t)(uintptr_t)p);
     h = mix64(h, w->n);
-    h = mix64(h, (uint64_t)(uintptr_t)rec_val_of(c));
     h = mix64(h, c->cap_contacts);
     h = mix64(h, (uint64_t)(c->bx | (c->by << 5) | (c->bz << 10)) | ((uint64_t)(c->mixed ? 1 : 0) << 20) |
                      ((uint64_t)w->params.response_mode << 24) | ((uint64_t)(executor_wide(w, c) ? 1 : 0) << 28));

@@ -87,17 +87,12 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ ce
 }
 
 // K3b: one record per grid body into its cell's segment; counting the histogram back down leaves it
-// zeroed for the next step.  The record carries everything the narrow phase reads about a body, so nothing
-// is gathered by id afterwards.  Two layouts:
-//   mixed worlds (boxes in the grid)  ONE 32-byte sector: centre + radius, id|flags, AABB half extents, written
-//                                     by one 256-bit store (SASS STG.E.ENL2.256) and read back by one 256-bit load;
-//   compact (all-sphere worlds,       20 bytes in two arrays carved out of the same buffer: float4 centre + radius
-//   TR_COMPACT_RECS=1 only)           (all the sphere predicate reads: a candidate costs a 128-bit load, half the LSU
-//                                     wavefronts of the 256-bit one) and the 32-bit id|flags word.  Measured at 1M:
-//                                     narrow phase 45.7 -> 40.4 us (random cloud) / 77.6 -> 74.6 us (pack), but the two
-//                                     partial-sector stores of K3b cost the random cloud's broad phase 34.3 -> 46.2 us
-//                                     (pack: 23.7 -> 22.6 us): a net loss wherever body ids are not spatially coherent,
-//                                     hence off by default.
+// zeroed for the next step.  The record carries everything the narrow phase reads about a body -
+// centre + radius, id|flags, AABB half extents - in ONE 32-byte sector written by one 256-bit store
+// (SASS STG.E.ENL2.256) and read back by one 256-bit load, so nothing is gathered by id afterwards.
+// (Measured and rejected: a compact 20-byte layout for all-sphere worlds - float4 array + id array - halves the
+// narrow phase's load wavefronts, 45.7 -> 40.4 us, but K3b's two partial-sector stores cost the random cloud's
+// broad phase 34.3 -> 46.2 us; pack: 77.6 -> 74.6 and 23.7 -> 22.6.)
 struct __align__(32) SlotRec {
     float4 c;              // collider centre, radius
     uint32_t val;          // id | BOX_BIT | STATIC_BIT
@@ -133,8 +128,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict
                                                       const uint8_t* __restrict__ flags, const float4* __restrict__ center_r,
                                                       const float4* __restrict__ half_ext,   // NULL unless boxes are in the grid
                                                       uint32_t n, const uint32_t* __restrict__ cell_start,
-                                                      uint32_t* __restrict__ cell_count, SlotRec* __restrict__ recs,
-                                                      uint32_t* __restrict__ rec_val /* all-sphere layout: id|flags array; NULL = 32-byte records */) {
+                                                      uint32_t* __restrict__ cell_count, SlotRec* __restrict__ recs) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t key = keys[i];
@@ -144,22 +138,9 @@ __global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict
     const uint32_t old = atomicSub(&cell_count[key], 1u);
     const uint32_t slot = cell_start[key] + old - 1u;
     TR_ASSERT(old >= 1u && old <= n && slot < n && slot < cell_start[key + 1]);
-    if (rec_val) {
-        reinterpret_cast<float4*>(recs)[slot] = c;
-        rec_val[slot] = val;
-    } else {
-        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (half_ext) h = half_ext[i];
-        st_rec(recs + slot, c, val, h);
-    }
-}
-
-// centre + radius / id|flags of the body in slot u, either layout
-__device__ __forceinline__ float4 rec_center(const SlotRec* recs, const uint32_t* rec_val, uint32_t u) {
-    return rec_val ? reinterpret_cast<const float4*>(recs)[u] : recs[u].c;
-}
-__device__ __forceinline__ uint32_t rec_idflags(const SlotRec* recs, const uint32_t* rec_val, uint32_t u) {
-    return rec_val ? rec_val[u] : recs[u].val;
+    float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (half_ext) h = half_ext[i];
+    st_rec(recs + slot, c, val, h);
 }
 
 // K4 (on demand, tr_debug_grid): the stable (key,id) order.  The rank of a body inside its cell is the number of
@@ -317,7 +298,6 @@ __device__ void outside_worker(uint32_t worker, uint32_t nworkers, const Outside
 
 template <bool CANDIDATES, bool MIXED>
 __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* __restrict__ recs,
-                                                                const uint32_t* __restrict__ rec_val,   // all-sphere layout (MIXED = false)
                                                                 const uint32_t* __restrict__ cell_start,
                                                                 uint32_t* counters, GridParams g, uint32_t slot_blocks,
                                                                 OutsideArgs oa, unsigned long long* out, unsigned long long cap,
@@ -342,15 +322,10 @@ __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* _
     for (int r = 0; r < 10; ++r) rs[r] = len[r] = 0;
     const bool big = ngrid > (1u << 27);           // slot << 5 | lane does not fit one word
     if (valid) {
-        float4 ca, ha = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 ca, ha;
         uint32_t va;
-        if (MIXED || !rec_val) {
-            ld_rec(recs + t, ca, va, ha);
-            if (MIXED) sw.own_h[lane] = ha;
-        } else {
-            ca = reinterpret_cast<const float4*>(recs)[t];
-            va = rec_val[t];
-        }
+        ld_rec(recs + t, ca, va, ha);
+        if (MIXED) sw.own_h[lane] = ha;
         sw.own_c[lane] = ca;
         sw.own_v[lane] = va;
         const uint32_t key = cell_key(ca, g);
@@ -432,12 +407,7 @@ __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* _
                         ow[k] = sw.o[p];
                     }
                     TR_ASSERT(u < ngrid && ow[k] < 32u);
-                    if (MIXED || !rec_val) {
-                        ld_rec(recs + u, cb[k], vb[k], hb[k]);
-                    } else {
-                        cb[k] = reinterpret_cast<const float4*>(recs)[u];
-                        vb[k] = rec_val[u];
-                    }
+                    ld_rec(recs + u, cb[k], vb[k], hb[k]);
                 }
             }
 #pragma unroll
@@ -451,7 +421,6 @@ __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* _
                     const uint32_t ov = sw.own_v[o];
                     float4 oh = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (MIXED) oh = sw.own_h[o];
-                    else hb[k] = oh;
                     hit = pair_hit<CANDIDATES, MIXED>(oc, ov, oh, cb[k], vb[k], hb[k]);
                     const uint32_t ida = ov & ID_MASK, idb = vb[k] & ID_MASK;
                     pr = ((unsigned long long)min(ida, idb) << 32) | max(ida, idb);
