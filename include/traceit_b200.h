@@ -84,11 +84,13 @@ typedef struct tr_world_params {
     uint32_t response_mode;
     /* Test / debugging knobs, 0 in production.  TR_DEBUG_NO_TINY: worlds of up to 256 bodies normally
      * run whole steps in ONE single-CTA kernel (the reference's own algorithm, detection spread over the
-     * CTA's threads; see DESIGN.md "small worlds"); the flag sends them through the general grid pipeline. */
+     * CTA's threads; see DESIGN.md "small worlds"); the flag sends them through the general grid pipeline.
+     * TR_DEBUG_BIG_LIST: see below.                                                              */
     uint32_t debug_flags;
     uint32_t reserved;
 } tr_world_params;
 #define TR_DEBUG_NO_TINY 1u
+#define TR_DEBUG_BIG_LIST 2u /* narrow phase: use the list format of worlds with more than 2^27 bodies (so that it can be tested) */
 
 /* Body descriptor = hot fields of the reference's `object` + `collider`
  * (src/main.cpp:79-105), same names and meaning.  The UI-side parameter contract

@@ -946,3 +946,27 @@ def test_two_worlds_stepped_concurrently_from_two_host_threads(tr):
     for name in ("a", "b"):
         for f in FIELDS:
             assert_bits_equal(out[name][f], alone[f], f"world {name}:{f}")
+
+
+def test_narrow_phase_list_format_of_huge_worlds(tr, oracle):
+    """Above 2^27 bodies a (candidate slot, owner lane) pair no longer fits one 32-bit list word and the narrow phase
+    switches to a second instantiation (slot word + owner byte).  Forced on a small dense world here, incl. the
+    candidate-listing debug mode and a mixed world: same contact sets, same state, bit for bit."""
+    b = scenes.random_cloud(20000, 33, spheres=True, density_l=0.6)
+    want = b.copy()
+    oracle.step(want, oracle.default_params(), 2)
+    got, contacts, _ = gpu_run(tr, b, 2, debug_flags=tr.DEBUG_BIG_LIST)
+    check_state(got, want, "big list")
+    assert np.array_equal(contacts, oracle.contacts(want)) and len(contacts) > 1000
+    with tr.World(tr.default_params(debug_flags=tr.DEBUG_BIG_LIST)) as w, tr.World(tr.default_params()) as w0:
+        w.add(b)
+        w0.add(b)
+        n1, c1 = w.debug_candidates()
+        n0, c0 = w0.debug_candidates()
+        assert n1 == n0 and np.array_equal(c1, c0)
+    m = mixed_cloud()
+    want = m.copy()
+    oracle.step(want, oracle.default_params(), 3)
+    got, contacts, _ = gpu_run(tr, m, 3, debug_flags=tr.DEBUG_BIG_LIST)
+    check_state(got, want, "big list, mixed world")
+    assert np.array_equal(contacts, oracle.contacts(want))

@@ -19,7 +19,7 @@ KERNELS = {   # file stem -> regex on the demangled function name
     "gravity_kernel": r"tr::gravity_kernel\(",
     "keys_kernel": r"tr::keys_kernel\(",
     "scatter_kernel": r"tr::scatter_kernel\(",
-    "narrow_kernel_spheres": r"tr::narrow_kernel<\(bool\)0, \(bool\)0>\(",
+    "narrow_kernel_spheres": r"tr::narrow_kernel<\(bool\)0, \(bool\)0, \(bool\)0>\(",
     "response_flow_kernel_1lane": r"tr::response_flow_kernel<\(int\)1>\(",
     "prep_kernel": r"tr::prep_kernel\(",
     "tiny_step_kernel": r"tr::tiny_step_kernel\(",

@@ -28,6 +28,7 @@ ROOT = os.path.dirname(HERE)
 PAIR_GRAVITY = 1
 COLLISIONS = 2
 DEBUG_NO_TINY = 1
+DEBUG_BIG_LIST = 2
 
 ERRORS = {
     0: "TR_OK", 1: "TR_ERR_INVALID_ARG", 2: "TR_ERR_NO_DEVICE", 3: "TR_ERR_CUDA", 4: "TR_ERR_NCCL",

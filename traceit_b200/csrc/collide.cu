@@ -254,12 +254,18 @@ static int launch_narrow(tr_world* w, cudaStream_t st, unsigned long long* out, 
     const uint32_t outside_blocks = CANDIDATES ? 0u : (uint32_t)w->num_sms * 8u;
     const GridParams g = grid_params(c);
     OutsideArgs oa{c->side_list, c->far_list, c->far_c, c->bnd_list, c->bnd_c, w->center_r, w->half_ext, w->flags, c->klass, (uint32_t)w->n};
-    if (c->mixed)
-        narrow_kernel<CANDIDATES, true><<<slot_blocks + outside_blocks, NARROW_THREADS, 0, st>>>((const SlotRec*)c->recs, c->cell_start, c->counters,
-                                                                                                g, slot_blocks, oa, out, cap, counter);
-    else
-        narrow_kernel<CANDIDATES, false><<<slot_blocks + outside_blocks, NARROW_THREADS, 0, st>>>((const SlotRec*)c->recs, c->cell_start, c->counters,
-                                                                                                 g, slot_blocks, oa, out, cap, counter);
+    const SlotRec* recs = (const SlotRec*)c->recs;
+    const unsigned nblk = slot_blocks + outside_blocks;
+    const bool big = w->n > (1ull << 27) || (w->params.debug_flags & TR_DEBUG_BIG_LIST);
+#define TR_NARROW(M, B) narrow_kernel<CANDIDATES, M, B><<<nblk, NARROW_THREADS, 0, st>>>(recs, c->cell_start, c->counters, g, slot_blocks, oa, out, cap, counter)
+    if (c->mixed) {
+        if (big) TR_NARROW(true, true);
+        else TR_NARROW(true, false);
+    } else {
+        if (big) TR_NARROW(false, true);
+        else TR_NARROW(false, false);
+    }
+#undef TR_NARROW
     TR_CUDA(cudaGetLastError());
     return TR_OK;
 }
@@ -354,7 +360,8 @@ static uint64_t step_signature(tr_world* w) {
     h = mix64(h, w->n);
     h = mix64(h, c->cap_contacts);
     h = mix64(h, (uint64_t)(c->bx | (c->by << 5) | (c->bz << 10)) | ((uint64_t)(c->mixed ? 1 : 0) << 20) |
-                     ((uint64_t)w->params.response_mode << 24) | ((uint64_t)(executor_wide(w, c) ? 1 : 0) << 28));
+                     ((uint64_t)w->params.response_mode << 24) | ((uint64_t)(executor_wide(w, c) ? 1 : 0) << 28) |
+                     ((uint64_t)(w->params.debug_flags & 0xFFu) << 32));
     uint32_t f[5];
     memcpy(&f[0], &c->inv_cell, 4);
     memcpy(&f[1], &c->rmax_grid, 4);

@@ -296,7 +296,8 @@ struct OutsideArgs {
 __device__ void outside_worker(uint32_t worker, uint32_t nworkers, const OutsideArgs& oa, const uint32_t* counters,
                                unsigned long long* out, unsigned long long cap, unsigned long long* counter);
 
-template <bool CANDIDATES, bool MIXED>
+// BIG: worlds of more than 2^27 bodies, where slot << 5 | lane does not fit one word (the host picks the instantiation)
+template <bool CANDIDATES, bool MIXED, bool BIG>
 __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* __restrict__ recs,
                                                                 const uint32_t* __restrict__ cell_start,
                                                                 uint32_t* counters, GridParams g, uint32_t slot_blocks,
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* _
     uint32_t rs[10], len[10];
 #pragma unroll
     for (int r = 0; r < 10; ++r) rs[r] = len[r] = 0;
-    const bool big = ngrid > (1u << 27);           // slot << 5 | lane does not fit one word
+    constexpr bool big = BIG;
     if (valid) {
         float4 ca, ha;
         uint32_t va;
@@ -355,6 +356,7 @@ __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* _
             }
         }
     }
+    const bool any_wrap = __any_sync(0xFFFFFFFFu, (len[5] | len[6] | len[7] | len[8] | len[9]) != 0);
     // offsets of every lane's pairs in the warp's flattened list
     const uint32_t mine = (len[0] + len[1] + len[2] + len[3] + len[4]) + (len[5] + len[6] + len[7] + len[8] + len[9]);
     uint32_t incl = mine;
@@ -374,6 +376,7 @@ __global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* _
         uint32_t wo = off;
 #pragma unroll
         for (int r = 0; r < 10; ++r) {
+            if (r == 5 && !any_wrap) break;        // (warp-uniform) the second windows are all empty
             const uint32_t lo = max(wo, base), hi = min(wo + len[r], base + (uint32_t)NARROW_LIST);
             if (!big) {
                 for (uint32_t k = lo; k < hi; ++k) {
