@@ -297,8 +297,11 @@ __device__ void outside_worker(uint32_t worker, uint32_t nworkers, const Outside
                                unsigned long long* out, unsigned long long cap, unsigned long long* counter);
 
 // BIG: worlds of more than 2^27 bodies, where slot << 5 | lane does not fit one word (the host picks the instantiation)
+// (Occupancy is tuned, not left to ptxas: 10 CTAs of 128 threads per SM = 48 registers.  Measured on the 1M cloud / pack:
+// 41.6 / 73 us; 11 or 12 CTAs (46 / 40 registers) 49.6 / 86; unconstrained 47.6 / 82.5; 1, 3 or 4 candidate records in
+// flight per lane instead of 2: 43.5 / 77, 49 / 86, 54.6 / 92.)
 template <bool CANDIDATES, bool MIXED, bool BIG>
-__global__ void __launch_bounds__(NARROW_THREADS) narrow_kernel(const SlotRec* __restrict__ recs,
+__global__ void __launch_bounds__(NARROW_THREADS, MIXED ? 8 : 10) narrow_kernel(const SlotRec* __restrict__ recs,
                                                                 const uint32_t* __restrict__ cell_start,
                                                                 uint32_t* counters, GridParams g, uint32_t slot_blocks,
                                                                 OutsideArgs oa, unsigned long long* out, unsigned long long cap,
