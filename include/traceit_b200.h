@@ -91,6 +91,7 @@ typedef struct tr_world_params {
 } tr_world_params;
 #define TR_DEBUG_NO_TINY 1u
 #define TR_DEBUG_BIG_LIST 2u /* narrow phase: use the list format of worlds with more than 2^27 bodies (so that it can be tested) */
+#define TR_DEBUG_NO_SPARSE 4u /* steps the host expects to have few (<= 3072) contacts normally end in ONE kernel of one thread-block cluster that orders and replays them in distributed shared memory; the flag sends every step through the grid-wide ordering + dataflow executor */
 
 /* Body descriptor = hot fields of the reference's `object` + `collider`
  * (src/main.cpp:79-105), same names and meaning.  The UI-side parameter contract
@@ -130,6 +131,8 @@ typedef struct tr_stats {
     double integrate_ms;         /* standalone integrator (pair gravity off)             */
     double allgather_ms;         /* NCCL all-gather (sharded worlds)                     */
     uint64_t interactions;       /* ordered pair interactions evaluated (N_targets * N)  */
+    uint64_t sparse_steps;       /* collision steps replayed by the one-cluster kernel for sparse steps */
+    uint64_t sparse_bailouts;    /* steps predicted sparse that were not (re-run through the general kernels) */
 } tr_stats;
 
 /* ---- library --------------------------------------------------------------------- */

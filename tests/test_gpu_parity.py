@@ -72,10 +72,11 @@ def test_default_scene_golden_gpu(tr):
     10000x5x10000 slab is oversize and sits in the side list; 1000 steps."""
     g = load_golden("default_scene.npz")
     # through the general pipeline (a 3-body world normally takes the single-CTA path, tested below)
-    got, contacts, st = gpu_run(tr, g["initial"].copy(), 1000, debug_flags=tr.DEBUG_NO_TINY)
-    check_state(got, g["final"], "default scene")
-    assert np.array_equal(contacts, g["contacts"])
-    assert st.side_list_size == 1
+    for extra in (0, tr.DEBUG_NO_SPARSE):
+        got, contacts, st = gpu_run(tr, g["initial"].copy(), 1000, debug_flags=tr.DEBUG_NO_TINY | extra)
+        check_state(got, g["final"], "default scene")
+        assert np.array_equal(contacts, g["contacts"])
+        assert st.side_list_size == 1
 
 
 def test_default_scene_golden_single_cta_path(tr):
@@ -96,9 +97,12 @@ def test_default_scene_golden_single_cta_path(tr):
 
 @pytest.mark.parametrize("name,steps", [("sphere_cloud_2048_s1.npz", 1), ("sphere_cloud_2048_s50.npz", 50),
                                         ("mixed_cloud_1024_s40.npz", 40), ("dense_lattice_12_s20.npz", 20)])
-def test_cloud_goldens_gpu(tr, name, steps):
+@pytest.mark.parametrize("sparse", [True, False])
+def test_cloud_goldens_gpu(tr, name, steps, sparse):
+    """These steps have a few hundred contacts: replayed by the epilogue kernel's single CTA in shared memory
+    (sparse=True, the default) or pushed through the grid-wide ordering + dataflow executor."""
     g = load_golden(name)
-    got, contacts, st = gpu_run(tr, g["initial"].copy(), steps)
+    got, contacts, st = gpu_run(tr, g["initial"].copy(), steps, debug_flags=0 if sparse else tr.DEBUG_NO_SPARSE)
     check_state(got, g["final"], name)
     assert np.array_equal(contacts, g["contacts"]), name
 
@@ -970,3 +974,114 @@ def test_narrow_phase_list_format_of_huge_worlds(tr, oracle):
     got, contacts, _ = gpu_run(tr, m, 3, debug_flags=tr.DEBUG_BIG_LIST)
     check_state(got, want, "big list, mixed world")
     assert np.array_equal(contacts, oracle.contacts(want))
+
+
+# ---------------------------------------------------------------- sparse steps: the one-cluster response kernel
+def _slab_with_boxes(n, seed, static=False):
+    rs = np.random.RandomState(seed)
+    b = scenes.random_cloud(n + 1, 90 + seed, spheres=False)
+    b["pos"][1:, 0] = rs.uniform(-900, 900, n)
+    b["pos"][1:, 1] = rs.uniform(-24.5, -15.5, n)
+    b["pos"][1:, 2] = rs.uniform(-900, 900, n)
+    b["size"][1:] = rs.uniform(0.3, 1.0, size=(n, 3)).astype(np.float32)
+    b["mass"][1:] = rs.uniform(1, 10, n).astype(np.float32)
+    b[0] = scenes.default_scene()[0]
+    b["isStatic"][0] = 1 if static else 0
+    b["center"] = b["pos"]
+    return b
+
+
+@pytest.mark.parametrize("n,static", [(1500, True), (1500, False), (4000, True), (4090, True), (4096, True), (4100, True)])
+def test_sparse_step_hub_and_the_limit(tr, oracle, n, static):
+    """One body with ~n contacts.  A static slab orders nothing: the sparse-step kernel takes it up to its 4096-contact
+    limit (straddled here: the boxes add a few contacts among themselves).  A movable slab is one chain of n contacts,
+    more than the kernel ranks by linear scans: it bails out untouched, the host re-runs the step through the general
+    kernels and stops predicting.  Either way: the sequential sweep's bits, every step."""
+    b = _slab_with_boxes(n, 3, static)
+    want = b.copy()
+    op = oracle.default_params(flags=0)
+    with tr.World(tr.default_params()) as w, tr.World(tr.default_params(debug_flags=tr.DEBUG_NO_SPARSE)) as w2:
+        w.add(b)
+        w2.add(b)
+        for s in range(4):
+            w.step(1)
+            w2.step(1)
+            oracle.step(want, op, 1)
+            c = oracle.contacts(want)
+            oracle.resolve_list(want, c)
+            assert np.array_equal(w.contacts(), c)
+            if s == 0:
+                assert (c[:, 0] == 0).sum() == n
+                st = w.stats()
+                if static and len(c) <= 4096:
+                    assert st.sparse_steps == 1 and st.sparse_bailouts == 0
+                else:
+                    assert st.sparse_steps == 0 and st.sparse_bailouts == 1
+            check_state(w.read_bodies(), want, f"sparse hub step {s}")
+            check_state(w2.read_bodies(), want, f"grid-wide hub step {s}")
+        assert w2.stats().sparse_steps == 0 and w2.stats().sparse_bailouts == 0
+
+
+def _mixed(n, seed, density_l):
+    b = scenes.random_cloud(n, seed, spheres=True, density_l=density_l)
+    b["isSphere"][::3] = 0
+    b["size"][::3] = (0.6, 0.4, 0.5)
+    b["isStatic"][::7] = 1
+    b["stationary"][::11] = 1
+    b["mass"][::13] = 0
+    b["rest"][::5] = 0.9
+    return b
+
+
+def test_sparse_and_dense_steps_alternate_in_one_run(tr, oracle):
+    """A mixed cloud (spheres, boxes, static / stationary / massless bodies) that starts as a clump of 70,000 contacts and
+    thins out to a few hundred.  Synchronous stepping: the first step is predicted sparse (nothing known yet), bails out
+    and is re-run; the host then follows the records - general kernels while the clump lasts, the sparse-step kernel after.
+    The same 200 steps as ONE asynchronous batch (nothing known for the whole batch: one bail-out, then general)."""
+    b = _mixed(4000, 17, 0.25)
+    want = b.copy()
+    op = oracle.default_params()
+    oracle.step(want, op, 1)
+    assert len(oracle.contacts(want)) > 4096 * 4      # (detected after the response: still a clump)
+    oracle.step(want, op, 199)
+    assert len(oracle.contacts(want)) < 2048
+    with tr.World(tr.default_params()) as w:
+        w.add(b.copy())
+        for _ in range(200):
+            w.step(1)
+        st = w.stats()
+        check_state(w.read_bodies(), want, "sparse/dense run")
+        assert st.sparse_steps >= 100 and st.steps == 200   # (step 1 overflows the default contact capacity: grown, re-run)
+    with tr.World(tr.default_params()) as w:
+        w.add(b.copy())
+        w.step(200)
+        st = w.stats()
+        check_state(w.read_bodies(), want, "sparse/dense run, one batch")
+        assert st.steps == 200
+
+
+def test_sparse_prediction_fails_mid_batch(tr, oracle):
+    """A thin cloud stepped a few times (the host now predicts sparse steps), then a clump of 20,000 contacts is dropped
+    in and 30 steps are enqueued without synchronisation: the first of them bails out on the device, the 29 behind it are
+    no-ops, and the host re-runs all 30 through the general kernels at the next synchronisation."""
+    thin = scenes.random_cloud(3000, 5, spheres=True, density_l=0.8)
+    clump = scenes.random_cloud(3000, 6, spheres=True, density_l=0.3)
+    clump["pos"] += np.float32(500.0)
+    clump["center"] = clump["pos"]
+    want = thin.copy()
+    op = oracle.default_params()
+    with tr.World(tr.default_params()) as w:
+        w.add(thin)
+        for _ in range(5):
+            w.step(1)
+        oracle.step(want, op, 5)
+        st = w.stats()
+        assert st.sparse_steps == 5 and st.sparse_bailouts == 0
+        w.add(clump)
+        want = np.concatenate([want, clump])
+        for _ in range(30):
+            w.step(1, sync=False)
+        oracle.step(want, op, 30)
+        check_state(w.read_bodies(), want, "clump dropped in")
+        st = w.stats()
+        assert st.sparse_bailouts == 1 and st.steps == 35

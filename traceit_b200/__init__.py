@@ -29,6 +29,7 @@ PAIR_GRAVITY = 1
 COLLISIONS = 2
 DEBUG_NO_TINY = 1
 DEBUG_BIG_LIST = 2
+DEBUG_NO_SPARSE = 4
 
 ERRORS = {
     0: "TR_OK", 1: "TR_ERR_INVALID_ARG", 2: "TR_ERR_NO_DEVICE", 3: "TR_ERR_CUDA", 4: "TR_ERR_NCCL",
@@ -66,6 +67,7 @@ class Stats(C.Structure):
         ("gravity_ms", C.c_double), ("gravity_launches", C.c_uint64), ("broadphase_ms", C.c_double),
         ("broadphase_launches", C.c_uint64), ("narrowphase_ms", C.c_double), ("response_ms", C.c_double),
         ("integrate_ms", C.c_double), ("allgather_ms", C.c_double), ("interactions", C.c_uint64),
+        ("sparse_steps", C.c_uint64), ("sparse_bailouts", C.c_uint64),
     ]
 
 

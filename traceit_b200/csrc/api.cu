@@ -600,7 +600,8 @@ int settle(tr_world* w) {
         bool overflow = false;
         uint32_t seq = 0;
         uint64_t found = 0;
-        TR_TRY(collide_consume_records(w, &overflow, &seq, &found));
+        bool not_sparse = false;
+        TR_TRY(collide_consume_records(w, &overflow, &seq, &found, &not_sparse));
         if (!overflow) {
             w->pending_steps.clear();
             TR_TRY(collide_headroom(w));
@@ -611,7 +612,7 @@ int settle(tr_world* w) {
         while (k < w->pending_steps.size() && w->pending_steps[k].coll_seq != seq) ++k;
         const std::vector<tr_world::PendingStep> pending = w->pending_steps;
         w->pending_steps.clear();
-        int rc = collide_grow_contacts(w, found);
+        int rc = not_sparse ? TR_OK : collide_grow_contacts(w, found);   // (a step wrongly predicted sparse fits the buffers)
         TR_CUDA(cudaMemsetAsync(w->d_ctl + CTL_ABORT, 0, sizeof(uint32_t), w->stream));
         if (k == pending.size()) {
             set_error("internal: overflowed step %u is not among the %zu pending steps", seq, pending.size());

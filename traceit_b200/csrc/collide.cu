@@ -161,6 +161,11 @@ static int alloc_contact_buffers(tr_world* w, uint64_t want_c) {
 static int ensure_buffers(tr_world* w) {
     Collide* c = state(w);
     const uint64_t n = w->n;
+    if (!c->sparse_smem_set) {   // (not at the launch: that can be inside a stream capture)
+        TR_CUDA(cudaFuncSetAttribute(sparse_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SparseSmem)));
+        if (SPARSE_CLUSTER > 8) TR_CUDA(cudaFuncSetAttribute(sparse_step_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        c->sparse_smem_set = true;
+    }
     if (n > c->cap_bodies) {
         uint64_t cap = w->cap >= n ? w->cap : n;
         TR_TRY(realloc_dev(&c->keys, cap));
@@ -337,12 +342,46 @@ static int launch_response(tr_world* w, cudaStream_t st) {
     return TR_OK;
 }
 
-static int launch_step(tr_world* w, cudaStream_t st) {
+// the tail of a step the host expects to be sparse: ordering + replay + record in one cluster kernel (collide_response.cuh)
+static int launch_sparse_response(tr_world* w, cudaStream_t st) {
+    Collide* c = state(w);
+    SparseArgs sa{c->ckeys, c->cap_contacts, c->counters, w->d_ctl, w->d_ring, w->pos_m[w->cur], w->vel_rest,
+                  w->center_r, w->half_ext, w->flags, (uint32_t)w->n};
+    sparse_step_kernel<<<SPARSE_CLUSTER, SPARSE_THREADS, sizeof(SparseSmem), st>>>(sa);
+    TR_CUDA(cudaGetLastError());
+    return TR_OK;
+}
+
+static int launch_step(tr_world* w, cudaStream_t st, bool sparse) {
     Collide* c = state(w);
     TR_TRY(launch_broad(w, st));
     TR_TRY(launch_narrow<false>(w, st, c->ckeys, c->cap_contacts));
-    TR_TRY(launch_response(w, st));
+    if (sparse) TR_TRY(launch_sparse_response(w, st));
+    else TR_TRY(launch_response(w, st));
     return TR_OK;
+}
+
+// Is the step about to be enqueued a sparse one?  The newest record the device has written so far tells (mapped pinned
+// memory, read without any synchronisation: it is only a hint - the kernel checks).  No record yet: assume it is.
+constexpr uint64_t SPARSE_PREDICT = SPARSE_MAX_CONTACTS * 3 / 4;   // head room for the count to drift before the kernel's own limit
+static bool predict_sparse(tr_world* w, Collide* c) {
+    static const bool off = getenv("TR_NO_SPARSE") != nullptr;
+    // (sharded worlds replicate the collision step: every rank must take the same decisions, and a peek is a matter of timing)
+    if (off || w->params.response_mode != 0 || (w->params.debug_flags & TR_DEBUG_NO_SPARSE) || w->nranks != 1) return false;
+    if (c->sparse_block) {
+        --c->sparse_block;
+        return false;
+    }
+    if (w->h_ring) {
+        if (c->peek_seq < w->ring_consumed) c->peek_seq = w->ring_consumed;
+        while (c->peek_seq < w->coll_seq) {
+            const volatile StepRecord* r = &w->h_ring[c->peek_seq % STEP_RING];
+            if (r->seq != c->peek_seq + 1u) break;
+            if (!(r->flags & 5u)) c->known_contacts = ((uint64_t)r->contacts_hi << 32) | r->contacts_lo;   // (not: overflowed / no-op steps)
+            ++c->peek_seq;
+        }
+    }
+    return c->known_contacts <= SPARSE_PREDICT;
 }
 
 static uint64_t mix64(uint64_t h, uint64_t v) {
@@ -432,17 +471,18 @@ int collide_step(tr_world* w) {
     Collide* c = state(w);
     static const bool no_graph = getenv("TR_NO_GRAPH") != nullptr;
     // the level-synchronous executor is a cooperative launch, and the legacy default stream cannot be captured: plain launches
+    const bool sparse = predict_sparse(w, c);
     if (no_graph || w->stream == nullptr || w->params.response_mode == 1) {
-        TR_TRY(launch_step(w, w->stream));
+        TR_TRY(launch_step(w, w->stream, sparse));
     } else {
-        const int slot = w->cur;
+        const int slot = 2 * w->cur + (sparse ? 1 : 0);
         const uint64_t sig = step_signature(w);
         if (!c->graph[slot] || c->graph_sig[slot] != sig) {
             if (c->graph[slot]) cudaGraphExecDestroy(c->graph[slot]);
             c->graph[slot] = nullptr;
             cudaGraph_t graph = nullptr;
             TR_CUDA(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal));
-            int rc = launch_step(w, w->stream);
+            int rc = launch_step(w, w->stream, sparse);
             cudaError_t e = cudaStreamEndCapture(w->stream, &graph);
             if (rc != TR_OK) return rc;
             if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
@@ -453,7 +493,7 @@ int collide_step(tr_world* w) {
         }
         TR_CUDA(cudaGraphLaunch(c->graph[slot], w->stream));
     }
-    w->stats.kernel_launches += 8;   // keys, tile sums, scan, scatter, narrow (+ side / far workers), prep, executor, epilogue
+    w->stats.kernel_launches += sparse ? 6 : 8;   // keys, tile sums, scan, scatter, narrow (+ side / far workers), then prep, executor, epilogue - or the sparse step's one kernel
     w->coll_seq += 1;
     c->host_contacts_valid = false;
     return TR_OK;
@@ -462,8 +502,9 @@ int collide_step(tr_world* w) {
 // Fold the step records the device has written since the last call into the host-side statistics
 // (after a stream synchronisation).  *overflow_seq = sequence number of a step whose contact list
 // did not fit (its response and every later step were skipped on the device), *found = its count.
-int collide_consume_records(tr_world* w, bool* overflow, uint32_t* overflow_seq, uint64_t* found) {
+int collide_consume_records(tr_world* w, bool* overflow, uint32_t* overflow_seq, uint64_t* found, bool* not_sparse) {
     *overflow = false;
+    *not_sparse = false;
     Collide* c = w->col;
     if (!c || !w->h_ring) return TR_OK;
     const uint32_t upto = w->coll_seq;
@@ -474,6 +515,16 @@ int collide_consume_records(tr_world* w, bool* overflow, uint32_t* overflow_seq,
             *overflow = true;
             *overflow_seq = note.seq - 1u;
             *found = ((uint64_t)note.contacts_hi << 32) | note.contacts_lo;
+            if (note.flags & 8u) {
+                // a step predicted sparse that was not: no capacity problem.  Re-run it through the general kernels and
+                // keep the prediction off for a while, twice as long after every miss in a row
+                *not_sparse = true;
+                if (*found <= SPARSE_MAX_CONTACTS) {   // (too many contacts: the count itself, now known, stops the prediction)
+                    c->sparse_backoff = c->sparse_backoff >= 2048 ? 4096 : c->sparse_backoff * 2;
+                    c->sparse_block = c->sparse_backoff;
+                }
+                w->stats.sparse_bailouts += 1;
+            }
             note.seq = 0;
         }
     }
@@ -489,6 +540,10 @@ int collide_consume_records(tr_world* w, bool* overflow, uint32_t* overflow_seq,
                 w->deferred_error = TR_ERR_CUDA;
                 w->deferred_msg = "ordered response: dataflow watchdog fired (dependency graph did not drain)";
             }
+        }
+        if (r.flags & 16u) {
+            w->stats.sparse_steps += 1;
+            c->sparse_backoff = 32;
         }
         w->stats.last_contacts = cnt;
         w->stats.side_list_size = r.side + r.far;   // everything outside the grid: oversize list + far list
@@ -508,6 +563,8 @@ int collide_consume_records(tr_world* w, bool* overflow, uint32_t* overflow_seq,
         }
     }
     w->ring_consumed = upto;
+    c->peek_seq = upto;
+    c->known_contacts = *overflow ? *found : c->last_contacts;
     return TR_OK;
 }
 
@@ -644,7 +701,7 @@ int collide_free(tr_world* w) {
     cudaFree(c->side_list); cudaFree(c->far_list); cudaFree(c->bnd_list); cudaFree(c->far_c); cudaFree(c->bnd_c); cudaFree(c->klass);
     cudaFree(c->seg); cudaFree(c->long_list); cudaFree(c->huge_list); cudaFree(c->body_cnt); cudaFree(c->counters); cudaFree(c->brec);
     free_contact_buffers(c);
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < 4; ++k)
         if (c->graph[k]) cudaGraphExecDestroy(c->graph[k]);
     delete c;
     w->col = nullptr;

@@ -119,8 +119,15 @@ struct Collide {
 
     // the whole collision step as ONE CUDA graph per live pos_m buffer: launch parameters only change when the
     // buffers, the grid, the body count or the executor choice change, so it is re-captured only then
-    cudaGraphExec_t graph[2] = {nullptr, nullptr};
-    uint64_t graph_sig[2] = {0, 0};
+    // ([2 * buffer + 1]: the variant for sparse steps, which ends in sparse_step_kernel)
+    cudaGraphExec_t graph[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint64_t graph_sig[4] = {0, 0, 0, 0};
+    // sparse steps are PREDICTED by the host (newest step record it can see); a wrong guess is caught on the device and
+    // the step re-run through the general kernels, after which the prediction stays off for sparse_block steps
+    uint32_t sparse_block = 0, sparse_backoff = 32;
+    uint32_t peek_seq = 0;
+    uint64_t known_contacts = 0;       // contact count of the newest step whose record the host has seen (0: none yet - assume sparse)
+    bool sparse_smem_set = false;
 
     // what the host knows from the step records it has consumed so far
     uint64_t last_contacts = 0;

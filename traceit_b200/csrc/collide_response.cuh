@@ -52,8 +52,8 @@ struct __align__(32) ContactGeo {
 };
 static_assert(sizeof(ContactGeo) == 32, "one sector");
 
-__device__ __forceinline__ void contact_normal(uint8_t fi, uint8_t fj, const float4 ci, const float4 cj, const float4* half_ext,
-                                               uint32_t i, uint32_t j, float& nx, float& ny, float& nz) {
+__device__ __forceinline__ void contact_normal_values(uint8_t fi, uint8_t fj, const float4 ci, const float4 cj, const float4 hi, const float4 hj,
+                                                      float& nx, float& ny, float& nz) {
     if ((fi & F_SPHERE) && (fj & F_SPHERE)) {
         // normalize(b.center - a.center), main.cpp:703 + 211-223
         float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
@@ -67,7 +67,6 @@ __device__ __forceinline__ void contact_normal(uint8_t fi, uint8_t fj, const flo
         }
     } else {
         // calculateAABBNormal, main.cpp:622-638
-        const float4 hi = half_ext[i], hj = half_ext[j];
         float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
         float ox = __fsub_rn(__fadd_rn(hi.x, hj.x), fabsf(dx));
         float oy = __fsub_rn(__fadd_rn(hi.y, hj.y), fabsf(dy));
@@ -77,6 +76,16 @@ __device__ __forceinline__ void contact_normal(uint8_t fi, uint8_t fj, const flo
         else if (oy < oz) ny = dy > 0 ? 1.0f : -1.0f;
         else nz = dz > 0 ? 1.0f : -1.0f;
     }
+}
+
+__device__ __forceinline__ void contact_normal(uint8_t fi, uint8_t fj, const float4 ci, const float4 cj, const float4* half_ext,
+                                               uint32_t i, uint32_t j, float& nx, float& ny, float& nz) {
+    float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), hj = hi;
+    if (!((fi & F_SPHERE) && (fj & F_SPHERE))) {
+        hi = half_ext[i];
+        hj = half_ext[j];
+    }
+    contact_normal_values(fi, fj, ci, cj, hi, hj, nx, ny, nz);
 }
 
 // Dataflow executors keep the mutable state of a body that is in contact in ONE 32-byte record
@@ -759,37 +768,436 @@ __global__ void __launch_bounds__(128) response_flow_kernel(FlowArgs a, const ui
     if ((threadIdx.x & 31) == 0) atomicMax(&counters[C_ROUNDS], iters);   // observability: longest warp
 }
 
-// Last kernel of a collision step: the step's record for the host (mapped pinned memory - the host reads it
-// after its next synchronisation, nothing waits for it), then the counters are zeroed for the next step.
+// The step's record for the host (mapped pinned memory - the host reads it after its next synchronisation, nothing
+// waits for it).  One thread.  extra_flags: 8 = a sparse step that has to be re-run through the general kernels,
+// 16 = replayed by sparse_step_kernel.
+__device__ __forceinline__ void write_step_record(uint32_t* counters, uint32_t* ctl, StepRecord* ring, uint32_t extra_flags, uint32_t rounds) {
+    const uint32_t seq = ctl[CTL_SEQ];
+    StepRecord r;
+    r.flags = extra_flags;
+    const unsigned long long found = *reinterpret_cast<const unsigned long long*>(counters + C_CONTACTS);
+    if (ctl[CTL_ABORT] == seq + 1u) r.flags |= 1u;            // this step overflowed the contact buffers (or, with 8: was not sparse after all)
+    else if (ctl[CTL_ABORT] != 0) r.flags |= 4u;              // a step before it did: this one did nothing
+    if (counters[C_ABORT]) r.flags |= 2u;                     // dataflow watchdog
+    r.contacts_lo = (uint32_t)found;
+    r.contacts_hi = (uint32_t)(found >> 32);
+    r.side = counters[C_SIDE];
+    r.far = counters[C_FAR];
+    r.bnd = counters[C_BND];
+    r.grid = counters[C_GRID];
+    r.rounds = rounds;
+    r.long_segments = counters[C_LONG] + counters[C_HUGE];
+    r.pad[0] = r.pad[1] = 0;
+    r.t[0] = *reinterpret_cast<const unsigned long long*>(counters + C_T0);
+    r.t[1] = *reinterpret_cast<const unsigned long long*>(counters + C_T0 + 2);
+    r.t[2] = *reinterpret_cast<const unsigned long long*>(counters + C_T0 + 4);
+    r.t[3] = globaltimer_ns();
+    r.seq = seq + 1u;
+    ring[seq % STEP_RING] = r;
+    if (r.flags & 1u) ring[STEP_RING] = r;   // the overflow notice has a slot of its own: it must survive any number of later (no-op) steps
+    ctl[CTL_SEQ] = seq + 1u;
+}
+
+// Last kernel of a general collision step: the record, then the counters are zeroed for the next step.
 __global__ void __launch_bounds__(128) epilogue_kernel(uint32_t* counters, uint32_t* ctl, StepRecord* ring) {
-    if (threadIdx.x == 0) {
-        const uint32_t seq = ctl[CTL_SEQ];
-        StepRecord r;
-        r.flags = 0;
-        const unsigned long long found = *reinterpret_cast<const unsigned long long*>(counters + C_CONTACTS);
-        if (ctl[CTL_ABORT] == seq + 1u) r.flags |= 1u;            // this step overflowed the contact buffers
-        else if (ctl[CTL_ABORT] != 0) r.flags |= 4u;              // a step before it did: this one did nothing
-        if (counters[C_ABORT]) r.flags |= 2u;                     // dataflow watchdog
-        r.contacts_lo = (uint32_t)found;
-        r.contacts_hi = (uint32_t)(found >> 32);
-        r.side = counters[C_SIDE];
-        r.far = counters[C_FAR];
-        r.bnd = counters[C_BND];
-        r.grid = counters[C_GRID];
-        r.rounds = counters[C_ROUNDS];
-        r.long_segments = counters[C_LONG] + counters[C_HUGE];
-        r.pad[0] = r.pad[1] = 0;
-        r.t[0] = *reinterpret_cast<const unsigned long long*>(counters + C_T0);
-        r.t[1] = *reinterpret_cast<const unsigned long long*>(counters + C_T0 + 2);
-        r.t[2] = *reinterpret_cast<const unsigned long long*>(counters + C_T0 + 4);
-        r.t[3] = globaltimer_ns();
-        r.seq = seq + 1u;
-        ring[seq % STEP_RING] = r;
-        if (r.flags & 1u) ring[STEP_RING] = r;   // the overflow notice has a slot of its own: it must survive any number of later (no-op) steps
-        ctl[CTL_SEQ] = seq + 1u;
-    }
+    if (threadIdx.x == 0) write_step_record(counters, ctl, ring, 0u, counters[C_ROUNDS]);
     __syncthreads();
     for (uint32_t k = threadIdx.x; k < (uint32_t)C_NCOUNTERS; k += blockDim.x) counters[k] = 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Sparse steps: ordering + replay + record in ONE kernel of ONE thread-block cluster
+// ---------------------------------------------------------------------------------------
+// A step with a few thousand contacts (the 1M random cloud: ~2,500; most frames of a real scene) has
+// nothing to spread over a grid: prep_kernel's phases, the dataflow executor and the epilogue are then
+// three launches of pure latency - grid barriers and L2 round trips, 33 us for 2,504 contacts.  When the
+// host expects such a step (the last record it has seen says so) the step's graph ends, after the narrow
+// phase, in this kernel instead: 8 CTAs x 512 threads = one contact per thread, all bookkeeping and the
+// bodies' mutable state in DISTRIBUTED SHARED MEMORY (a hand-off costs ~215 cycles instead of an L2 round
+// trip), cluster barriers (~380 cycles) instead of grid barriers:
+//   gather  the contact's bodies: flags, collider centres, velocity, position (the only DRAM-cold reads; in flight across P0-P2)
+//   P0      a body belongs to the CTA its id hashes to; (remote) atomicCAS into that CTA's hash table,
+//           (remote) atomicAdd on the slot's counter = degree + arrival rank
+//   P1      owners: occupied slots get dense local ids and half-edge segments (warp-aggregated)
+//   P2      half edges (partner id) into the owners' segments; the first arrival deposits the body's velocity + position
+//   P3      rank of the contact among the contacts of both its bodies (= the version it must see)
+//   P5      rounds: a contact whose two bodies are at its versions is applied on the owners' copies; two cluster
+//           barriers per round
+//   P6      owners write the changed bodies back; CTA 0 writes the step's record and re-arms the counters.
+// Same order, same arithmetic (respond_rec's), same bits as the other executors.  One CTA alone cannot do
+// this: shared-memory atomics and scattered stores run at ~1 per cycle per SM, 2,500 contacts x ~20 of them
+// took 45 us on one SM.
+// What the kernel cannot take - more than 4,096 contacts, a movable body with more than SPARSE_MAX_DEGREE
+// contacts (the general path sorts such lists), a lopsided hash partition - it finds out BEFORE it has changed
+// anything; it then raises the same flag as a contact-buffer overflow (CTL_ABORT: every later step is a
+// no-op) plus bit 8 in its record, and the host re-runs the step through the general kernels at its next
+// synchronisation and stops predicting "sparse" for a while (collide.cu: predict_sparse, settle()).
+#ifndef TR_SPARSE_CLUSTER
+#define TR_SPARSE_CLUSTER 16
+#endif
+constexpr int SPARSE_CLUSTER = TR_SPARSE_CLUSTER;            // 16 CTAs: beyond the portable cluster size, allowed per kernel (collide.cu)
+constexpr int SPARSE_CLUSTER_LOG2 = SPARSE_CLUSTER == 16 ? 4 : 3;
+constexpr int SPARSE_THREADS = 4096 / SPARSE_CLUSTER;
+constexpr uint32_t SPARSE_MAX_CONTACTS = SPARSE_CLUSTER * SPARSE_THREADS;   // one contact per thread
+constexpr uint32_t SPARSE_SLOTS = 4 * SPARSE_THREADS;        // hash slots per CTA (16,384 in the cluster for at most 8,192 bodies)
+constexpr uint32_t SPARSE_BODIES = 4 * SPARSE_THREADS;       // bodies one CTA can own (twice the expected number at the limit)
+constexpr uint32_t SPARSE_MAX_DEGREE = 64;     // contacts of one movable body (ranked by a linear scan of remote shared memory)
+constexpr uint32_t SPARSE_DIRTY = 0x80000000u;
+static_assert(SPARSE_CLUSTER == 8 || SPARSE_CLUSTER == 16, "owner = top bits of the hash");
+
+struct SparseSmem {
+    uint32_t key[SPARSE_SLOTS];                // body id per slot
+    uint32_t cnt[SPARSE_SLOTS];                // degree (bit 31: isStatic), after P1: local id
+    uint32_t gid[SPARSE_BODIES];               // local id -> body id
+    uint2 seg[SPARSE_BODIES];                  // the body's half edges: {first, count}
+    uint32_t he[2 * SPARSE_MAX_CONTACTS];      // partner ids, by segment (all half edges fit one CTA: no overflow case)
+    // The mutable state, as in the dataflow executor's BodyRec: {vx, vy, vz, version}, {px, py, pz, version}; version = contacts
+    // applied so far (bit 31: something changed).  Each half is read and written as ONE 128-bit access, so a reader that finds its
+    // version in both halves holds the values stored with it: no fence, no separate flag.  Remote shared memory moves about one
+    // access per cycle per SM whatever its width - 4 accesses per body and hand-off instead of 14.
+    uint4 rec[SPARSE_BODIES][2];
+    uint32_t wsum[2][SPARSE_THREADS / 32];     // P1's CTA scan
+    uint32_t nb, fail, rounds;                 // fail, rounds: CTA 0's copy is the cluster's
+};
+
+struct SparseArgs {
+    const unsigned long long* ckeys;
+    unsigned long long cap;
+    uint32_t* counters;
+    uint32_t* ctl;
+    StepRecord* ring;
+    float4* pos_m;
+    float4* vel_rest;
+    const float4* center_r;
+    const float4* half_ext;
+    const uint8_t* flags;
+    uint32_t n;
+};
+
+constexpr uint32_t SPARSE_SPIN_LIMIT = 1u << 20;
+// record hand-off between threads of the cluster: relaxed, cluster-scope, 128-bit accesses (generic addresses inside the
+// cluster's shared-memory window); PTX .b128 = one access in the memory model
+__device__ __forceinline__ void ld128_relaxed_cluster(const uint4* p, uint4& v) {
+    asm volatile("{\n\t.reg .b128 t;\n\t.reg .b64 lo, hi;\n\tld.relaxed.cluster.b128 t, [%4];\n\tmov.b128 {lo, hi}, t;\n\t"
+                 "mov.b64 {%0,%1}, lo;\n\tmov.b64 {%2,%3}, hi;\n\t}"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ void st128_relaxed_cluster(uint4* p, const uint4 v) {
+    asm volatile("{\n\t.reg .b128 t;\n\t.reg .b64 lo, hi;\n\tmov.b64 lo, {%1,%2};\n\tmov.b64 hi, {%3,%4};\n\tmov.b128 t, {lo, hi};\n\t"
+                 "st.relaxed.cluster.b128 [%0], t;\n\t}" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// slot of body b in the owner's table (EMPTY: table full)
+__device__ __forceinline__ uint32_t sparse_insert(uint32_t* keys, uint32_t b, uint32_t h, bool& fresh) {
+    for (uint32_t probes = 0; probes < SPARSE_SLOTS; ++probes) {
+        const uint32_t old = atomicCAS(&keys[h], EMPTY, b);
+        if (old == EMPTY || old == b) {
+            fresh = old == EMPTY;
+            return h;
+        }
+        h = (h + 1u) & (SPARSE_SLOTS - 1u);
+    }
+    fresh = false;
+    return EMPTY;
+}
+
+// false: not a step for this kernel (nothing has been changed).  The result is the same in every thread of the cluster.
+__device__ __forceinline__ bool sparse_replay(const SparseArgs& a, SparseSmem& s, cg::cluster_group& cluster, const uint32_t cn,
+                                              const unsigned long long key, uint32_t& rounds) {
+    const uint32_t rank = cluster.block_rank(), tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t c = rank * SPARSE_THREADS + tid;
+    const bool have = c < cn;
+    SparseSmem* s0 = cluster.map_shared_rank(&s, 0);
+#ifdef TR_SPARSE_PROF   // instrumented build (make EXTRA=-DTR_SPARSE_PROF TAG=sprof OUT=...): phase boundaries on one thread's clock
+    long long sp_t[16];
+    int sp_n = 0;
+#define SP_STAMP() do { if (rank == 0 && tid == 0 && sp_n < 16) sp_t[sp_n++] = clock64(); } while (0)
+#else
+#define SP_STAMP() do { } while (0)
+#endif
+    SP_STAMP();
+    static_assert(SPARSE_SLOTS == 4 * SPARSE_THREADS, "one 16-byte store per thread and table");
+    reinterpret_cast<uint4*>(s.key)[tid] = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
+    reinterpret_cast<uint4*>(s.cnt)[tid] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) s.nb = s.fail = s.rounds = 0;
+    // ---- gather
+    uint32_t bi = 0, bj = 0;
+    uint8_t fi = 0, fj = 0;
+    float4 ci = make_float4(0.f, 0.f, 0.f, 0.f), cj = ci, hi = ci, hj = ci, vi = ci, vj = ci, pi = ci, pj = ci;
+    if (have) {
+        bi = (uint32_t)(key >> 32);
+        bj = (uint32_t)key;
+        TR_ASSERT(bi < bj && bj < a.n);
+        fi = a.flags[bi];
+        fj = a.flags[bj];
+        ci = a.center_r[bi];
+        cj = a.center_r[bj];
+        vi = a.vel_rest[bi];
+        vj = a.vel_rest[bj];
+        pi = a.pos_m[bi];
+        pj = a.pos_m[bj];
+        hi = a.half_ext[bi];                                 // (only boxes need them - but waiting for the flags to know
+        hj = a.half_ext[bj];                                 //  would put a second DRAM round trip in front of these)
+    }
+    const bool sti = (fi & F_STATIC) != 0, stj = (fj & F_STATIC) != 0;
+    SP_STAMP();
+    cluster.sync();                                          // every CTA's tables are initialised
+    SP_STAMP();
+    // ---- P0: slots, degrees, arrival ranks
+    const uint32_t hhi = bi * 2654435761u, hhj = bj * 2654435761u;
+    SparseSmem* si = cluster.map_shared_rank(&s, hhi >> (32 - SPARSE_CLUSTER_LOG2));
+    SparseSmem* sj = cluster.map_shared_rank(&s, hhj >> (32 - SPARSE_CLUSTER_LOG2));
+    uint32_t sloti = 0, slotj = 0, ri = 0, rj = 0;
+    if (have) {
+        bool fresh_i, fresh_j;
+        sloti = sparse_insert(si->key, bi, (hhi >> 16) & (SPARSE_SLOTS - 1u), fresh_i);
+        slotj = sparse_insert(sj->key, bj, (hhj >> 16) & (SPARSE_SLOTS - 1u), fresh_j);
+        if (sloti == EMPTY || slotj == EMPTY) {
+            s0->fail = 1u;
+        } else {
+            if (fresh_i && sti) atomicOr(&si->cnt[sloti], 0x80000000u);
+            if (fresh_j && stj) atomicOr(&sj->cnt[slotj], 0x80000000u);
+            ri = atomicAdd(&si->cnt[sloti], 1u) & 0x7FFFFFFFu;
+            rj = atomicAdd(&sj->cnt[slotj], 1u) & 0x7FFFFFFFu;
+        }
+    }
+    SP_STAMP();
+    cluster.sync();
+    SP_STAMP();
+    // ---- P1 (owners): dense local ids, half-edge segments for the movable bodies.  A thread owns SPARSE_SLOTS / 512
+    // consecutive slots; one CTA-wide exclusive scan of (occupied slots, half edges needed) places them.
+    {
+        constexpr uint32_t PER = SPARSE_SLOTS / SPARSE_THREADS;
+        static_assert(PER * SPARSE_THREADS == SPARSE_SLOTS, "whole slots per thread");
+        uint32_t nocc = 0, nneed = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < PER; ++q) {
+            const uint32_t k = s.key[tid * PER + q], raw = s.cnt[tid * PER + q];
+            if (k != EMPTY) {
+                ++nocc;
+                if (!(raw >> 31)) nneed += raw;
+            }
+        }
+        uint32_t iocc = nocc, ineed = nneed;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y0 = __shfl_up_sync(0xFFFFFFFFu, iocc, o), y1 = __shfl_up_sync(0xFFFFFFFFu, ineed, o);
+            if (lane >= (uint32_t)o) {
+                iocc += y0;
+                ineed += y1;
+            }
+        }
+        if (lane == 31) {
+            s.wsum[0][tid >> 5] = iocc;
+            s.wsum[1][tid >> 5] = ineed;
+        }
+        __syncthreads();
+        uint32_t l = iocc - nocc, off = ineed - nneed;
+        for (uint32_t wq = 0; wq < (tid >> 5); ++wq) {
+            l += s.wsum[0][wq];
+            off += s.wsum[1][wq];
+        }
+        if (tid == SPARSE_THREADS - 1) s.nb = l + nocc;
+        bool bad = false;
+#pragma unroll
+        for (uint32_t q = 0; q < PER; ++q) {
+            const uint32_t x = tid * PER + q, k = s.key[x], raw = s.cnt[x];
+            if (k == EMPTY) continue;
+            const uint32_t need = (raw >> 31) ? 0u : raw;
+            if (l >= SPARSE_BODIES || need > SPARSE_MAX_DEGREE) {
+                bad = true;
+            } else {
+                TR_ASSERT(off + need <= 2u * SPARSE_MAX_CONTACTS);
+                s.gid[l] = k;
+                s.seg[l] = make_uint2(off, need);
+                s.cnt[x] = l;
+            }
+            ++l;
+            off += need;
+        }
+        if (bad) s0->fail = 1u;
+    }
+    SP_STAMP();
+    cluster.sync();
+    SP_STAMP();
+    {
+        const uint32_t f = s0->fail;
+        if (f) {
+            cluster.sync();                                  // CTA 0's shared memory outlives everybody's read of the flag
+            return false;
+        }
+    }
+    // ---- P2: half edges; the first arrival deposits the body's state
+    uint32_t li = 0, lj = 0, oi = 0, oj = 0, di = 0, dj = 0;
+    if (have) {
+        li = si->cnt[sloti];
+        lj = sj->cnt[slotj];
+        TR_ASSERT(li < SPARSE_BODIES && lj < SPARSE_BODIES);
+        if (!sti) {
+            const uint2 sg = si->seg[li];
+            oi = sg.x;
+            di = sg.y;
+            si->he[oi + ri] = bj;
+        }
+        if (!stj) {
+            const uint2 sg = sj->seg[lj];
+            oj = sg.x;
+            dj = sg.y;
+            sj->he[oj + rj] = bi;
+        }
+        if (ri == 0) {
+            si->rec[li][0] = make_uint4(__float_as_uint(vi.x), __float_as_uint(vi.y), __float_as_uint(vi.z), 0u);
+            si->rec[li][1] = make_uint4(__float_as_uint(pi.x), __float_as_uint(pi.y), __float_as_uint(pi.z), 0u);
+        }
+        if (rj == 0) {
+            sj->rec[lj][0] = make_uint4(__float_as_uint(vj.x), __float_as_uint(vj.y), __float_as_uint(vj.z), 0u);
+            sj->rec[lj][1] = make_uint4(__float_as_uint(pj.x), __float_as_uint(pj.y), __float_as_uint(pj.z), 0u);
+        }
+    }
+    // the contact's constants (registers)
+    float nx = 0.f, ny = 0.f, nz = 0.f, ima = 0.f, imb = 0.f, den = 0.f, e = 0.f;
+    if (have) {
+        contact_normal_values(fi, fj, ci, cj, hi, hj, nx, ny, nz);
+        ima = __fdiv_rn(1.0f, pi.w);
+        imb = __fdiv_rn(1.0f, pj.w);
+        den = __fadd_rn(ima, imb);
+        e = (vj.w < vi.w) ? vj.w : vi.w;                     // std::min(a.rest, b.rest)
+    }
+    SP_STAMP();
+    cluster.sync();
+    SP_STAMP();
+    // ---- P3: versions = rank by partner id among the body's contacts (a static body is never changed: nothing orders its contacts)
+    uint32_t ei = 0, ej = 0;
+    {
+        const uint32_t* p = si->he + oi;                     // (di, dj are 0 for static bodies and idle threads)
+        for (uint32_t x = 0; x < di; ++x) ei += p[x] < bj ? 1u : 0u;
+        const uint32_t* q = sj->he + oj;
+        for (uint32_t x = 0; x < dj; ++x) ej += q[x] < bi ? 1u : 0u;
+    }
+    SP_STAMP();
+    // ---- P5: the replay.  No barrier: a thread polls the records of its contact's two bodies, applies the contact on
+    // the owners' copies when both carry its versions, and stores them back with the next versions - a hand-off costs two
+    // distributed-shared-memory round trips.  Every contact has its thread and all threads are resident, so the earliest
+    // unfinished contact in sweep order can always run.  (P3 only read what the replay never writes.)
+    bool pending = have, stalled = false;
+    uint32_t spins = 0;
+    while (__any_sync(0xFFFFFFFFu, pending)) {               // the warp iterates together: no lane waits inside a divergent branch
+        if (!pending) continue;
+        uint4 ai, bi4, aj, bj4;
+        ld128_relaxed_cluster(&si->rec[li][0], ai);
+        ld128_relaxed_cluster(&sj->rec[lj][0], aj);
+        ld128_relaxed_cluster(&si->rec[li][1], bi4);
+        ld128_relaxed_cluster(&sj->rec[lj][1], bj4);
+        const bool oki = sti || ((ai.w & ~SPARSE_DIRTY) == ei && (bi4.w & ~SPARSE_DIRTY) == ei);
+        const bool okj = stj || ((aj.w & ~SPARSE_DIRTY) == ej && (bj4.w & ~SPARSE_DIRTY) == ej);
+        if (oki && okj) {
+            float vix = __uint_as_float(ai.x), viy = __uint_as_float(ai.y), viz = __uint_as_float(ai.z);
+            float vjx = __uint_as_float(aj.x), vjy = __uint_as_float(aj.y), vjz = __uint_as_float(aj.z);
+            float pix = __uint_as_float(bi4.x), piy = __uint_as_float(bi4.y), piz = __uint_as_float(bi4.z);
+            float pjx = __uint_as_float(bj4.x), pjy = __uint_as_float(bj4.y), pjz = __uint_as_float(bj4.z);
+            const float rvx = __fsub_rn(vix, vjx), rvy = __fsub_rn(viy, vjy), rvz = __fsub_rn(viz, vjz);
+            const float vn = dot3_rn(rvx, rvy, rvz, nx, ny, nz);
+            const bool hit = !(vn > 0);                              // main.cpp:714 (as written)
+            if (hit) {
+                float jimp = __fmul_rn(-__fadd_rn(1.0f, e), vn);     // -(1 + e) * vn
+                jimp = __fdiv_rn(jimp, den);                         // / (1/ma + 1/mb)
+                const float ix = __fmul_rn(nx, jimp), iy = __fmul_rn(ny, jimp), iz = __fmul_rn(nz, jimp);
+                const float kcorr = 0.2f * 0.01f;                    // percent * penetrationSlop (fp32 product)
+                const float cx = __fmul_rn(nx, kcorr), cy = __fmul_rn(ny, kcorr), cz = __fmul_rn(nz, kcorr);
+                vix = __fsub_rn(vix, __fmul_rn(ix, ima));
+                viy = __fsub_rn(viy, __fmul_rn(iy, ima));
+                viz = __fsub_rn(viz, __fmul_rn(iz, ima));
+                pix = __fsub_rn(pix, __fmul_rn(cx, ima));
+                piy = __fsub_rn(piy, __fmul_rn(cy, ima));
+                piz = __fsub_rn(piz, __fmul_rn(cz, ima));
+                vjx = __fadd_rn(vjx, __fmul_rn(ix, imb));
+                vjy = __fadd_rn(vjy, __fmul_rn(iy, imb));
+                vjz = __fadd_rn(vjz, __fmul_rn(iz, imb));
+                pjx = __fadd_rn(pjx, __fmul_rn(cx, imb));
+                pjy = __fadd_rn(pjy, __fmul_rn(cy, imb));
+                pjz = __fadd_rn(pjz, __fmul_rn(cz, imb));
+            }
+            if (!sti) {                                              // (a static body is never written: main.cpp:725-741)
+                const uint32_t nv = (ei + 1u) | (ai.w & SPARSE_DIRTY) | (hit ? SPARSE_DIRTY : 0u);
+                st128_relaxed_cluster(&si->rec[li][0], make_uint4(__float_as_uint(vix), __float_as_uint(viy), __float_as_uint(viz), nv));
+                st128_relaxed_cluster(&si->rec[li][1], make_uint4(__float_as_uint(pix), __float_as_uint(piy), __float_as_uint(piz), nv));
+            }
+            if (!stj) {
+                const uint32_t nv = (ej + 1u) | (aj.w & SPARSE_DIRTY) | (hit ? SPARSE_DIRTY : 0u);
+                st128_relaxed_cluster(&sj->rec[lj][0], make_uint4(__float_as_uint(vjx), __float_as_uint(vjy), __float_as_uint(vjz), nv));
+                st128_relaxed_cluster(&sj->rec[lj][1], make_uint4(__float_as_uint(pjx), __float_as_uint(pjy), __float_as_uint(pjz), nv));
+            }
+            pending = false;
+        } else if (++spins > SPARSE_SPIN_LIMIT) {            // a contact nobody can run - never, with a sound graph
+            stalled = true;
+            pending = false;
+        }
+    }
+    {
+        // for the record: the deepest position any contact has in the list of one of its bodies (= length of the longest chain through one body)
+        const uint32_t depth = __reduce_max_sync(0xFFFFFFFFu, have ? max(ei, ej) + 1u : 0u);
+        if (lane == 0 && depth) atomicMax(&s0->rounds, depth);
+        if (__any_sync(0xFFFFFFFFu, stalled) && lane == 0) a.counters[C_ABORT] = 1u;   // reported like the executors' watchdog
+    }
+    SP_STAMP();
+    cluster.sync();                                          // the replay is complete everywhere
+    rounds = s0->rounds;
+    cluster.sync();                                          // CTA 0 stays until everybody has read it
+    // ---- P6 (owners): changed bodies back to the SoA state
+    const uint32_t nb = s.nb;
+    for (uint32_t l = tid; l < nb; l += SPARSE_THREADS) {
+        const uint4 ra = s.rec[l][0], rb = s.rec[l][1];
+        if (!(ra.w & SPARSE_DIRTY)) continue;
+        const uint32_t b = s.gid[l];
+        store_xyz(a.vel_rest + b, make_float4(__uint_as_float(ra.x), __uint_as_float(ra.y), __uint_as_float(ra.z), 0.f));
+        store_xyz(a.pos_m + b, make_float4(__uint_as_float(rb.x), __uint_as_float(rb.y), __uint_as_float(rb.z), 0.f));
+    }
+    SP_STAMP();
+#ifdef TR_SPARSE_PROF
+    if (rank == 0 && tid == 0) {
+        printf("[TR_SPARSE_PROF] contacts %u rounds %u; cycles init+gather | sync | P0 | sync | P1 | sync | P2+constants | sync | P3 | rounds | write-back:", cn, rounds);
+        for (int k = 1; k < sp_n; ++k) printf(" %lld", sp_t[k] - sp_t[k - 1]);
+        printf("\n");
+    }
+#endif
+#undef SP_STAMP
+    return true;
+}
+
+__global__ void __cluster_dims__(SPARSE_CLUSTER, 1, 1) __launch_bounds__(SPARSE_THREADS) sparse_step_kernel(SparseArgs a) {
+    extern __shared__ __align__(16) unsigned char sparse_raw[];
+    SparseSmem& s = *reinterpret_cast<SparseSmem*>(sparse_raw);
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t rank = cluster.block_rank(), tid = threadIdx.x;
+    if (rank == 0 && tid == 0) *reinterpret_cast<unsigned long long*>(a.counters + C_T0 + 4) = globaltimer_ns();
+    // this thread's contact, if the step has that many: fetched before the count is known (one DRAM round trip instead of two)
+    const uint32_t cidx = rank * SPARSE_THREADS + tid;
+    const unsigned long long key = cidx < a.cap ? a.ckeys[cidx] : 0ull;
+    const bool dead = a.ctl[CTL_ABORT] != 0;                 // an earlier step has to be re-run first
+    const unsigned long long found = *reinterpret_cast<const unsigned long long*>(a.counters + C_CONTACTS);
+    uint32_t rounds = 0, extra = 0;
+    bool bail = false;
+    if (!dead && found != 0) {
+        if (found > a.cap) bail = true;                                      // a real overflow: the buffers must grow
+        else if (found > SPARSE_MAX_CONTACTS || !sparse_replay(a, s, cluster, (uint32_t)found, key, rounds)) {
+            bail = true;
+            extra = 8u;                                                      // not a sparse step: the general kernels must re-run it
+        } else {
+            extra = 16u;
+        }
+    } else if (!dead) {
+        extra = 16u;
+    }
+    if (rank != 0) return;
+    if (tid == 0) {
+        if (bail) a.ctl[CTL_ABORT] = a.ctl[CTL_SEQ] + 1u;
+        write_step_record(a.counters, a.ctl, a.ring, extra, rounds);
+    }
+    __syncthreads();
+    for (uint32_t k = tid; k < (uint32_t)C_NCOUNTERS; k += blockDim.x) a.counters[k] = 0;
 }
 
 }  // namespace tr

@@ -220,7 +220,7 @@ int measure_fma_peak(int device, double* lane_ops_per_s, double* sm_clock_mhz);
 // collide.cu
 int collide_step(tr_world* w);
 int tiny_steps(tr_world* w, const StepConsts& c, int nsteps, bool* taken);
-int collide_consume_records(tr_world* w, bool* overflow, uint32_t* overflow_seq, uint64_t* found);
+int collide_consume_records(tr_world* w, bool* overflow, uint32_t* overflow_seq, uint64_t* found, bool* not_sparse);
 int collide_grow_contacts(tr_world* w, uint64_t found);
 int collide_headroom(tr_world* w);
 int collide_free(tr_world* w);
