@@ -444,14 +444,16 @@ def measure(ctx: Ctx, name: str, n: int | None, steps: int, warmup: int, *, shar
             "kernel_ms": narrow_ms, "peak_source": src}
         rb = RESPONSE_BYTES_PER_CONTACT * contacts
         res["roofline_response"] = {
-            "bound": "hbm", "kernel": "K6: contact ordering + dependency build + ordered dataflow replay", "achieved": rb / (resp_ms * 1e-3) / 1e9 if resp_ms > 0 else None,
+            "bound": "hbm", "kernel": ("K6s sparse_step_kernel: ordering + ordered replay + step record in one 16-CTA cluster (distributed shared memory)"
+                                       if int(st.sparse_steps) > 0 else "K6: contact ordering + dependency build + ordered dataflow replay"), "achieved": rb / (resp_ms * 1e-3) / 1e9 if resp_ms > 0 else None,
             "peak": hbm, "unit": "GB/s", "frac": (rb / (resp_ms * 1e-3) / 1e9 / hbm) if resp_ms > 0 else None, "traffic": None,
             "algorithmic": f"{RESPONSE_BYTES_PER_CONTACT} B/contact x {contacts} (pair 8 + two bodies' pos+vel read 64 and written 64)",
             "kernel_ms": resp_ms, "peak_source": src,
             "note": "latency bound by construction: the reference's Gauss-Seidel order is a dependency chain "
-                    f"({int(st.last_response_rounds)} hand-offs on the longest worker in the last step), so the byte fraction is small"}
+                    f"({int(st.last_response_rounds)} hand-offs on the longest worker / chain through one body in the last step), so the byte fraction is small"}
         res["collision_ms"] = {"broad": broad_ms, "narrow": narrow_ms, "response": resp_ms, "total": broad_ms + narrow_ms + resp_ms,
-                               "contacts_last_step": contacts, "response_rounds_last_step": int(st.last_response_rounds)}
+                               "contacts_last_step": contacts, "response_rounds_last_step": int(st.last_response_rounds),
+                               "sparse_steps": int(st.sparse_steps), "sparse_bailouts": int(st.sparse_bailouts)}
         if "roofline" not in res:
             res["roofline"] = bp
     if nranks > 1:

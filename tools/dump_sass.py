@@ -22,6 +22,7 @@ KERNELS = {   # file stem -> regex on the demangled function name
     "narrow_kernel_spheres": r"tr::narrow_kernel<\(bool\)0, \(bool\)0, \(bool\)0>\(",
     "response_flow_kernel_1lane": r"tr::response_flow_kernel<\(int\)1>\(",
     "prep_kernel": r"tr::prep_kernel\(",
+    "sparse_step_kernel": r"tr::sparse_step_kernel\(",
     "tiny_step_kernel": r"tr::tiny_step_kernel\(",
 }
 

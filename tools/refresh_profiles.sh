@@ -18,7 +18,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:narrow_kernel -s 8 -c 1 -o $O/prof_narrow_cfg3 -f python tools/collide_bench.py cfg3 1048576 6 > $O/ncu_f1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:narrow_kernel -s 8 -c 1 -o $O/prof_narrow_cfg5 -f python tools/collide_bench.py cfg5 1048576 6 > $O/ncu_f2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:prep_kernel -s 8 -c 1 -o $O/prof_prep_cfg5 -f python tools/collide_bench.py cfg5 1048576 6 > $O/ncu_f3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:prep_kernel -s 8 -c 1 -o $O/prof_prep_cfg3 -f python tools/collide_bench.py cfg3 1048576 6 > $O/ncu_f4.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:sparse_step_kernel -s 8 -c 1 -o $O/prof_sparse_cfg3 -f python tools/collide_bench.py cfg3 1048576 6 > $O/ncu_f4.log 2>&1
+TR_NO_SPARSE=1 ncu --set full --clock-control none --import-source on -k regex:prep_kernel -s 8 -c 1 -o $O/prof_prep_cfg3 -f python tools/collide_bench.py cfg3 1048576 6 > $O/ncu_f4b.log 2>&1
 ncu --set full --clock-control none --import-source on -k 'regex:keys_kernel|tile_sums_kernel|scan_kernel|scatter_kernel' -s 32 -c 4 -o $O/prof_broad_cfg3 -f python tools/collide_bench.py cfg3 1048576 6 > $O/ncu_f5.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:response_flow_kernel -s 8 -c 1 -o $O/prof_flow_cfg5 -f python tools/collide_bench.py cfg5 1048576 6 > $O/ncu_f6.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:gravity_kernel -s 1 -c 1 -o $O/prof_gravity_cfg3 -f python bench.py --workload cfg3 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-secondary > $O/ncu_f7.log 2>&1

@@ -44,8 +44,8 @@ for name, cmd in (("collide_cfg3", "python tools/collide_bench.py cfg3 1048576 4
 
 # ---- ncu full captures -> text summaries
 groups = {
-    "collision_kernels_ncu.txt": (["prof_narrow_cfg3", "prof_narrow_cfg5", "prof_prep_cfg3", "prof_prep_cfg5", "prof_flow_cfg5", "prof_tiny"],
-                                  "narrow_kernel / prep_kernel / response_flow_kernel at N = 1,048,576 (python tools/collide_bench.py cfg3|cfg5 1048576 6, "
+    "collision_kernels_ncu.txt": (["prof_narrow_cfg3", "prof_narrow_cfg5", "prof_sparse_cfg3", "prof_prep_cfg3", "prof_prep_cfg5", "prof_flow_cfg5", "prof_tiny"],
+                                  "narrow_kernel / sparse_step_kernel / prep_kernel (cfg3: with TR_NO_SPARSE=1) / response_flow_kernel at N = 1,048,576 (python tools/collide_bench.py cfg3|cfg5 1048576 6, "
                                   "launch 9 of the kernel) and tiny_step_kernel (python tools/small_world_latency.py, default scene)"),
     "broadphase_kernels_cfg3_ncu.txt": (["prof_broad_cfg3"], "the four broad-phase kernels of one timed step, N = 1,048,576 random cloud (python tools/collide_bench.py cfg3 1048576 6)"),
     "gravity_kernel_cfg3_ncu.txt": (["prof_gravity_cfg3"], "gravity_kernel, N = 1,048,576 (python bench.py --workload cfg3 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-secondary, 2nd launch)"),

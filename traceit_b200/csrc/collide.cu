@@ -232,6 +232,24 @@ int collide_grow_contacts(tr_world* w, uint64_t found) {
     return alloc_contact_buffers(w, want);
 }
 
+// A launch that may overlap the tail of the kernel before it on the stream (programmatic dependent launch; the kernel
+// starts with pdl_wait()).  Captured into the step's graph as a programmatic edge.
+static const bool g_no_pdl = getenv("TR_NO_PDL") != nullptr;
+template <typename... KArgs, typename... Args>
+static cudaError_t pdl_launch(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // K2-K3b on the stream (used inside the step's graph capture and by the debug entry points).
 static int launch_broad(tr_world* w, cudaStream_t st) {
     Collide* c = state(w);
@@ -242,10 +260,10 @@ static int launch_broad(tr_world* w, cudaStream_t st) {
     const GridParams g = grid_params(c);
     keys_kernel<<<blocks, 256, 0, st>>>(w->center_r, w->half_ext, w->flags, n, g, c->keys, c->klass, c->side_list, c->far_list, c->far_c,
                                         c->bnd_list, c->bnd_c, c->cell_count, c->counters);
-    tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, ncell, c->tile_sum);
-    scan_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(c->cell_count, c->tile_sum, c->cell_start, ncell, c->counters, C_GRID);
-    scatter_kernel<<<blocks, 256, 0, st>>>(c->keys, ncell, w->flags, w->center_r, c->mixed ? w->half_ext : nullptr, n, c->cell_start,
-                                           c->cell_count, (SlotRec*)c->recs);
+    TR_CUDA(pdl_launch(tile_sums_kernel, ntiles, SCAN_THREADS, 0, st, c->cell_count, ncell, c->tile_sum));
+    TR_CUDA(pdl_launch(scan_kernel, ntiles, SCAN_THREADS, 0, st, c->cell_count, c->tile_sum, c->cell_start, ncell, c->counters, (int)C_GRID));
+    TR_CUDA(pdl_launch(scatter_kernel, blocks, 256, 0, st, c->keys, ncell, w->flags, w->center_r, c->mixed ? w->half_ext : (const float4*)nullptr, n,
+                       c->cell_start, c->cell_count, (SlotRec*)c->recs));
     TR_CUDA(cudaGetLastError());
     return TR_OK;
 }
@@ -262,7 +280,7 @@ static int launch_narrow(tr_world* w, cudaStream_t st, unsigned long long* out, 
     const SlotRec* recs = (const SlotRec*)c->recs;
     const unsigned nblk = slot_blocks + outside_blocks;
     const bool big = w->n > (1ull << 27) || (w->params.debug_flags & TR_DEBUG_BIG_LIST);
-#define TR_NARROW(M, B) narrow_kernel<CANDIDATES, M, B><<<nblk, NARROW_THREADS, 0, st>>>(recs, c->cell_start, c->counters, g, slot_blocks, oa, out, cap, counter)
+#define TR_NARROW(M, B) TR_CUDA(pdl_launch(narrow_kernel<CANDIDATES, M, B>, nblk, NARROW_THREADS, 0, st, recs, c->cell_start, c->counters, g, slot_blocks, oa, out, (unsigned long long)cap, counter))
     if (c->mixed) {
         if (big) TR_NARROW(true, true);
         else TR_NARROW(true, false);
@@ -347,8 +365,7 @@ static int launch_sparse_response(tr_world* w, cudaStream_t st) {
     Collide* c = state(w);
     SparseArgs sa{c->ckeys, c->cap_contacts, c->counters, w->d_ctl, w->d_ring, w->pos_m[w->cur], w->vel_rest,
                   w->center_r, w->half_ext, w->flags, (uint32_t)w->n};
-    sparse_step_kernel<<<SPARSE_CLUSTER, SPARSE_THREADS, sizeof(SparseSmem), st>>>(sa);
-    TR_CUDA(cudaGetLastError());
+    TR_CUDA(pdl_launch(sparse_step_kernel, SPARSE_CLUSTER, SPARSE_THREADS, sizeof(SparseSmem), st, sa));
     return TR_OK;
 }
 

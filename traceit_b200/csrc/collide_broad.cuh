@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ ce
                                                    uint32_t* __restrict__ far_list, float4* __restrict__ far_c,
                                                    uint32_t* __restrict__ bnd_list, float4* __restrict__ bnd_c,
                                                    uint32_t* __restrict__ cell_count, uint32_t* counters) {
+    pdl_trigger();   // (first kernel of the step: an ordinary launch, nothing to wait for)
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) *reinterpret_cast<unsigned long long*>(counters + C_T0) = globaltimer_ns();   // start of the broad phase
     {
@@ -129,6 +130,8 @@ __global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict
                                                       const float4* __restrict__ half_ext,   // NULL unless boxes are in the grid
                                                       uint32_t n, const uint32_t* __restrict__ cell_start,
                                                       uint32_t* __restrict__ cell_count, SlotRec* __restrict__ recs) {
+    pdl_wait();
+    pdl_trigger();
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t key = keys[i];
@@ -307,6 +310,8 @@ __global__ void __launch_bounds__(NARROW_THREADS, MIXED ? 8 : 10) narrow_kernel(
                                                                 OutsideArgs oa, unsigned long long* out, unsigned long long cap,
                                                                 unsigned long long* counter) {
     __shared__ NarrowWarp s_warp[NARROW_WARPS];
+    pdl_wait();
+    pdl_trigger();
     if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<unsigned long long*>(counters + C_T0 + 2) = globaltimer_ns();
     if (blockIdx.x >= slot_blocks) {
         if (!CANDIDATES) outside_worker(blockIdx.x - slot_blocks, gridDim.x - slot_blocks, oa, counters, out, cap, counter);

@@ -268,9 +268,19 @@ __device__ __forceinline__ void load_tile_items(const uint32_t* __restrict__ cel
     }
 }
 
+// Programmatic dependent launch inside the step's graph: a kernel launched with pdl_launch() (collide.cu) may be
+// scheduled while its predecessor drains - its CTAs' launch and prologue overlap the predecessor's tail - and waits
+// in pdl_wait() until the predecessor has completed and flushed.  Every kernel of the chain waits FIRST (every CTA,
+// also the ones that return early: completion is transitive only then) and lets its own dependents go at once.
+// Launched the ordinary way, both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __global__ void __launch_bounds__(SCAN_THREADS) tile_sums_kernel(const uint32_t* __restrict__ cell_count, uint32_t ncell,
                                                                  uint32_t* __restrict__ tile_sum) {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+    pdl_wait();
+    pdl_trigger();
     uint32_t v[SCAN_ITEMS];
     load_tile_items(cell_count, blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS, ncell, v);
     uint32_t tsum = 0;
@@ -293,6 +303,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const uint32_t* __re
                                                             uint32_t* __restrict__ cell_start, uint32_t ncell,
                                                             uint32_t* counters, int total_slot) {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32], s_red[SCAN_THREADS / 32], s_prefix;
+    pdl_wait();
+    pdl_trigger();
     const uint32_t tile = blockIdx.x;
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // prefix of this tile = sum of the tile sums before it

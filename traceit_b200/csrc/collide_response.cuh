@@ -1172,6 +1172,7 @@ __global__ void __cluster_dims__(SPARSE_CLUSTER, 1, 1) __launch_bounds__(SPARSE_
     SparseSmem& s = *reinterpret_cast<SparseSmem*>(sparse_raw);
     cg::cluster_group cluster = cg::this_cluster();
     const uint32_t rank = cluster.block_rank(), tid = threadIdx.x;
+    pdl_wait();
     if (rank == 0 && tid == 0) *reinterpret_cast<unsigned long long*>(a.counters + C_T0 + 4) = globaltimer_ns();
     // this thread's contact, if the step has that many: fetched before the count is known (one DRAM round trip instead of two)
     const uint32_t cidx = rank * SPARSE_THREADS + tid;
