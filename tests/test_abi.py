@@ -38,7 +38,7 @@ def test_struct_layouts_match_header():
     assert tr.BODY_DTYPE.itemsize == 92
     assert C.sizeof(tr.Params) == 72
     assert tr.Params.max_contacts.offset == 48
-    assert C.sizeof(tr.Stats) == 112
+    assert C.sizeof(tr.Stats) == 128   # (+ sparse_steps, sparse_bailouts)
     # same record as the oracle's (tests pass arrays between the two)
     from oracle import pyoracle as po
     assert po.BODY_DTYPE == tr.BODY_DTYPE
