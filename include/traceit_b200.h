@@ -85,13 +85,17 @@ typedef struct tr_world_params {
     /* Test / debugging knobs, 0 in production.  TR_DEBUG_NO_TINY: worlds of up to 256 bodies normally
      * run whole steps in ONE single-CTA kernel (the reference's own algorithm, detection spread over the
      * CTA's threads; see DESIGN.md "small worlds"); the flag sends them through the general grid pipeline.
-     * TR_DEBUG_BIG_LIST: see below.                                                              */
+     * TR_DEBUG_BIG_LIST, TR_DEBUG_NO_SPARSE: see below.                                          */
     uint32_t debug_flags;
     uint32_t reserved;
 } tr_world_params;
 #define TR_DEBUG_NO_TINY 1u
 #define TR_DEBUG_BIG_LIST 2u /* narrow phase: use the list format of worlds with more than 2^27 bodies (so that it can be tested) */
-#define TR_DEBUG_NO_SPARSE 4u /* steps the host expects to have few (<= 3072) contacts normally end in ONE kernel of one thread-block cluster that orders and replays them in distributed shared memory; the flag sends every step through the grid-wide ordering + dataflow executor */
+/* A step the host expects to have few (<= 3072) contacts normally ends in ONE kernel of one thread-block cluster that
+ * orders and replays the contacts in distributed shared memory (response_mode 0 only).  A wrong guess is
+ * caught on the device before anything changes and the step is re-run through the general kernels at the next
+ * synchronisation - invisible to the caller except in tr_stats.sparse_bailouts.  The flag keeps every step general. */
+#define TR_DEBUG_NO_SPARSE 4u
 
 /* Body descriptor = hot fields of the reference's `object` + `collider`
  * (src/main.cpp:79-105), same names and meaning.  The UI-side parameter contract

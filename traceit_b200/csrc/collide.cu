@@ -303,7 +303,7 @@ static bool executor_wide(const tr_world* w, const Collide* c) {
 }
 
 // K6 + epilogue on the stream.
-static int launch_response(tr_world* w, cudaStream_t st) {
+static int launch_response(tr_world* w, cudaStream_t st, bool after_sparse) {
     Collide* c = state(w);
     const bool flow = w->params.response_mode != 1;   // 1 selects the level-synchronous kernel
     if (c->prep_blocks == 0) {
@@ -315,7 +315,7 @@ static int launch_response(tr_world* w, cudaStream_t st) {
     }
     PrepArgs pa{c->ckeys, c->cap_contacts, c->counters, w->d_ctl, c->body_cnt, c->seg, c->arank, c->he, c->long_list, c->huge_list, c->dep, c->crec,
                 c->cver, (ContactGeo*)c->cgeo, flow ? (BodyRec*)c->brec : nullptr, c->frontier[0], flow ? C_QTAIL : C_FRONT,
-                w->pos_m[w->cur], w->vel_rest, w->center_r, w->half_ext, w->flags, (uint32_t)w->n};
+                w->pos_m[w->cur], w->vel_rest, w->center_r, w->half_ext, w->flags, (uint32_t)w->n, after_sparse ? 1u : 0u};
     {
         // a COOPERATIVE launch: prep_kernel synchronises its grid with a counter barrier, so all its CTAs must be resident
         // at once - also when another world's kernels (other streams, other host threads) compete for the SMs, where two
@@ -361,44 +361,58 @@ static int launch_response(tr_world* w, cudaStream_t st) {
 }
 
 // the tail of a step the host expects to be sparse: ordering + replay + record in one cluster kernel (collide_response.cuh)
-static int launch_sparse_response(tr_world* w, cudaStream_t st) {
+static int launch_sparse_response(tr_world* w, cudaStream_t st, bool tail_follows) {
     Collide* c = state(w);
     SparseArgs sa{c->ckeys, c->cap_contacts, c->counters, w->d_ctl, w->d_ring, w->pos_m[w->cur], w->vel_rest,
-                  w->center_r, w->half_ext, w->flags, (uint32_t)w->n};
+                  w->center_r, w->half_ext, w->flags, (uint32_t)w->n, tail_follows ? 1u : 0u};
     TR_CUDA(pdl_launch(sparse_step_kernel, SPARSE_CLUSTER, SPARSE_THREADS, sizeof(SparseSmem), st, sa));
     return TR_OK;
 }
 
-static int launch_step(tr_world* w, cudaStream_t st, bool sparse) {
+// How a step's graph ends after the narrow phase:
+//   STEP_GENERAL  prep_kernel -> executor -> epilogue_kernel                       (any step)
+//   STEP_SPARSE   sparse_step_kernel alone                                         (a step the host is confident is sparse;
+//                 if it is not, the kernel flags it and the host re-runs it: settle() in api.cu)
+//   STEP_TRY      sparse_step_kernel -> prep_kernel -> executor -> epilogue_kernel (nothing recent known: decided on the
+//                 device - the general kernels return at once when the sparse-step kernel has done the step)
+enum StepVariant { STEP_GENERAL = 0, STEP_SPARSE = 1, STEP_TRY = 2 };
+
+static int launch_step(tr_world* w, cudaStream_t st, StepVariant v) {
     Collide* c = state(w);
     TR_TRY(launch_broad(w, st));
     TR_TRY(launch_narrow<false>(w, st, c->ckeys, c->cap_contacts));
-    if (sparse) TR_TRY(launch_sparse_response(w, st));
-    else TR_TRY(launch_response(w, st));
+    if (v != STEP_GENERAL) TR_TRY(launch_sparse_response(w, st, v == STEP_TRY));
+    if (v != STEP_SPARSE) TR_TRY(launch_response(w, st, v == STEP_TRY));
     return TR_OK;
 }
 
-// Is the step about to be enqueued a sparse one?  The newest record the device has written so far tells (mapped pinned
-// memory, read without any synchronisation: it is only a hint - the kernel checks).  No record yet: assume it is.
-constexpr uint64_t SPARSE_PREDICT = SPARSE_MAX_CONTACTS * 3 / 4;   // head room for the count to drift before the kernel's own limit
-static bool predict_sparse(tr_world* w, Collide* c) {
+// Which variant for the step about to be enqueued?  The newest record the device has written so far tells (mapped pinned
+// memory, read without any synchronisation: it is only a hint - the kernels check).
+constexpr uint64_t SPARSE_CONFIDENT = SPARSE_MAX_CONTACTS * 7 / 8;   // head room for the count to drift before the kernel's own limit
+constexpr uint64_t SPARSE_HOPELESS = SPARSE_MAX_CONTACTS * 4;
+static StepVariant predict_variant(tr_world* w, Collide* c) {
     static const bool off = getenv("TR_NO_SPARSE") != nullptr;
     // (sharded worlds replicate the collision step: every rank must take the same decisions, and a peek is a matter of timing)
-    if (off || w->params.response_mode != 0 || (w->params.debug_flags & TR_DEBUG_NO_SPARSE) || w->nranks != 1) return false;
-    if (c->sparse_block) {
-        --c->sparse_block;
-        return false;
-    }
+    if (off || w->params.response_mode != 0 || (w->params.debug_flags & TR_DEBUG_NO_SPARSE) || w->nranks != 1) return STEP_GENERAL;
     if (w->h_ring) {
         if (c->peek_seq < w->ring_consumed) c->peek_seq = w->ring_consumed;
         while (c->peek_seq < w->coll_seq) {
             const volatile StepRecord* r = &w->h_ring[c->peek_seq % STEP_RING];
             if (r->seq != c->peek_seq + 1u) break;
-            if (!(r->flags & 5u)) c->known_contacts = ((uint64_t)r->contacts_hi << 32) | r->contacts_lo;   // (not: overflowed / no-op steps)
+            if (!(r->flags & 5u)) {   // (not: overflowed / no-op steps)
+                c->known_contacts = ((uint64_t)r->contacts_hi << 32) | r->contacts_lo;
+                c->known_valid = true;
+            }
             ++c->peek_seq;
         }
     }
-    return c->known_contacts <= SPARSE_PREDICT;
+    if (!c->known_valid) return STEP_TRY;
+    if (c->known_contacts > SPARSE_HOPELESS) return STEP_GENERAL;
+    if (c->sparse_block) {            // a recent miss the count does not explain (a hub, a lopsided partition): no confidence for a while
+        --c->sparse_block;
+        return STEP_TRY;
+    }
+    return c->known_contacts <= SPARSE_CONFIDENT ? STEP_SPARSE : STEP_TRY;
 }
 
 static uint64_t mix64(uint64_t h, uint64_t v) {
@@ -488,18 +502,18 @@ int collide_step(tr_world* w) {
     Collide* c = state(w);
     static const bool no_graph = getenv("TR_NO_GRAPH") != nullptr;
     // the level-synchronous executor is a cooperative launch, and the legacy default stream cannot be captured: plain launches
-    const bool sparse = predict_sparse(w, c);
+    const StepVariant variant = predict_variant(w, c);
     if (no_graph || w->stream == nullptr || w->params.response_mode == 1) {
-        TR_TRY(launch_step(w, w->stream, sparse));
+        TR_TRY(launch_step(w, w->stream, variant));
     } else {
-        const int slot = 2 * w->cur + (sparse ? 1 : 0);
+        const int slot = 3 * w->cur + (int)variant;
         const uint64_t sig = step_signature(w);
         if (!c->graph[slot] || c->graph_sig[slot] != sig) {
             if (c->graph[slot]) cudaGraphExecDestroy(c->graph[slot]);
             c->graph[slot] = nullptr;
             cudaGraph_t graph = nullptr;
             TR_CUDA(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal));
-            int rc = launch_step(w, w->stream, sparse);
+            int rc = launch_step(w, w->stream, variant);
             cudaError_t e = cudaStreamEndCapture(w->stream, &graph);
             if (rc != TR_OK) return rc;
             if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
@@ -510,7 +524,7 @@ int collide_step(tr_world* w) {
         }
         TR_CUDA(cudaGraphLaunch(c->graph[slot], w->stream));
     }
-    w->stats.kernel_launches += sparse ? 6 : 8;   // keys, tile sums, scan, scatter, narrow (+ side / far workers), then prep, executor, epilogue - or the sparse step's one kernel
+    w->stats.kernel_launches += variant == STEP_SPARSE ? 6 : variant == STEP_TRY ? 9 : 8;   // keys, tile sums, scan, scatter, narrow (+ side / far workers), then prep, executor, epilogue - or the sparse step's one kernel
     w->coll_seq += 1;
     c->host_contacts_valid = false;
     return TR_OK;
@@ -545,6 +559,7 @@ int collide_consume_records(tr_world* w, bool* overflow, uint32_t* overflow_seq,
             note.seq = 0;
         }
     }
+    bool fresh = false;
     if (upto - w->ring_consumed > STEP_RING) w->ring_consumed = upto - STEP_RING;   // older records were overwritten
     for (uint32_t s = w->ring_consumed; s < upto; ++s) {
         const StepRecord r = w->h_ring[s % STEP_RING];
@@ -558,6 +573,7 @@ int collide_consume_records(tr_world* w, bool* overflow, uint32_t* overflow_seq,
                 w->deferred_msg = "ordered response: dataflow watchdog fired (dependency graph did not drain)";
             }
         }
+        fresh = true;
         if (r.flags & 16u) {
             w->stats.sparse_steps += 1;
             c->sparse_backoff = 32;
@@ -581,7 +597,13 @@ int collide_consume_records(tr_world* w, bool* overflow, uint32_t* overflow_seq,
     }
     w->ring_consumed = upto;
     c->peek_seq = upto;
-    c->known_contacts = *overflow ? *found : c->last_contacts;
+    if (*overflow) {
+        c->known_contacts = *found;
+        c->known_valid = true;
+    } else if (fresh) {
+        c->known_contacts = c->last_contacts;
+        c->known_valid = true;
+    }
     return TR_OK;
 }
 
@@ -718,7 +740,7 @@ int collide_free(tr_world* w) {
     cudaFree(c->side_list); cudaFree(c->far_list); cudaFree(c->bnd_list); cudaFree(c->far_c); cudaFree(c->bnd_c); cudaFree(c->klass);
     cudaFree(c->seg); cudaFree(c->long_list); cudaFree(c->huge_list); cudaFree(c->body_cnt); cudaFree(c->counters); cudaFree(c->brec);
     free_contact_buffers(c);
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < 6; ++k)
         if (c->graph[k]) cudaGraphExecDestroy(c->graph[k]);
     delete c;
     w->col = nullptr;

@@ -42,7 +42,7 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 enum { C_SIDE = 0, C_GRID = 1, C_CONTACTS = 2 /*u64*/, C_CAND = 4 /*u64*/, C_HE = 6 /* half-edge slots handed out */,
        C_LONG = 7 /* bodies with a long contact list */, C_FRONT = 8 /*3*/, C_ROUNDS = 11, C_ABORT = 12, C_FIN = 13, C_BAR = 14 /* grid barrier of prep_kernel */, C_HUGE = 15 /* bodies whose contact list the whole grid sorts */,
        C_FAR = 16, C_BND = 17, C_T0 = 18 /* 3 x u64 globaltimer stamps: broad, narrow, prep */,
-       C_NHOST = 24,
+       C_NHOST = 24, C_SPARSE = 25 /* sparse_step_kernel replayed this step (1 + its rounds): the general kernels behind it in the graph return */,
        C_QHEAD = 32, C_QTAIL = 64, C_DONE = 96, C_NCOUNTERS = 128 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -119,14 +119,15 @@ struct Collide {
 
     // the whole collision step as ONE CUDA graph per live pos_m buffer: launch parameters only change when the
     // buffers, the grid, the body count or the executor choice change, so it is re-captured only then
-    // ([2 * buffer + 1]: the variant for sparse steps, which ends in sparse_step_kernel)
-    cudaGraphExec_t graph[4] = {nullptr, nullptr, nullptr, nullptr};
-    uint64_t graph_sig[4] = {0, 0, 0, 0};
+    // three variants per buffer ([3 * buffer + variant], collide.cu: StepVariant)
+    cudaGraphExec_t graph[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint64_t graph_sig[6] = {0, 0, 0, 0, 0, 0};
     // sparse steps are PREDICTED by the host (newest step record it can see); a wrong guess is caught on the device and
     // the step re-run through the general kernels, after which the prediction stays off for sparse_block steps
     uint32_t sparse_block = 0, sparse_backoff = 32;
     uint32_t peek_seq = 0;
-    uint64_t known_contacts = 0;       // contact count of the newest step whose record the host has seen (0: none yet - assume sparse)
+    uint64_t known_contacts = 0;       // contact count of the newest step whose record the host has seen
+    bool known_valid = false;
     bool sparse_smem_set = false;
 
     // what the host knows from the step records it has consumed so far

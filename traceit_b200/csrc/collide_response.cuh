@@ -171,6 +171,7 @@ struct PrepArgs {
     const float4* half_ext;
     const uint8_t* flags;
     uint32_t n;             // bodies (index checks of the checked build)
+    uint32_t after_sparse;  // sparse_step_kernel ran before this kernel in the step's graph (it stamped the phase, and may have done the step)
 };
 
 // all CTAs of prep_kernel are resident (the host sizes the grid from the occupancy API): a counter barrier
@@ -218,7 +219,8 @@ __device__ __forceinline__ void segment_lookup(const uint2* __restrict__ he, con
 
 __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs a) {
     __shared__ uint2 s_sort[PREP_SMEM_SORT];
-    if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<unsigned long long*>(a.counters + C_T0 + 4) = globaltimer_ns();
+    if (!a.after_sparse && blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<unsigned long long*>(a.counters + C_T0 + 4) = globaltimer_ns();
+    if (a.after_sparse && a.counters[C_SPARSE] != 0) return;   // the sparse-step kernel has replayed this step
     if (a.ctl[CTL_ABORT] != 0) return;                     // an earlier step overflowed: the host has to re-run from there
     const unsigned long long found = *reinterpret_cast<const unsigned long long*>(a.counters + C_CONTACTS);
     if (found > a.cap) {
@@ -616,6 +618,7 @@ __global__ void __launch_bounds__(128) response_flow_kernel(FlowArgs a, const ui
                                                             uint32_t* q, const uint32_t* ctl, uint32_t* counters, uint32_t idle_ns) {
     if ((threadIdx.x & 31) >= LANES) return;
     if (ctl[CTL_ABORT] != 0) return;               // contact buffer overflow in this or an earlier step: no response
+    if (counters[C_SPARSE] != 0) return;           // replayed by sparse_step_kernel earlier in the step's graph
     const uint32_t c_n = counters[C_CONTACTS];     // <= capacity < 2^32 here (prep_kernel checked)
     if ((unsigned long long)blockIdx.x * (blockDim.x / 32) * LANES >= c_n) return;   // no more workers than contacts (also: none for none)
     constexpr uint32_t LMASK = LANES == 32 ? 0xFFFFFFFFu : ((1u << LANES) - 1u);
@@ -800,7 +803,10 @@ __device__ __forceinline__ void write_step_record(uint32_t* counters, uint32_t* 
 
 // Last kernel of a general collision step: the record, then the counters are zeroed for the next step.
 __global__ void __launch_bounds__(128) epilogue_kernel(uint32_t* counters, uint32_t* ctl, StepRecord* ring) {
-    if (threadIdx.x == 0) write_step_record(counters, ctl, ring, 0u, counters[C_ROUNDS]);
+    if (threadIdx.x == 0) {
+        const uint32_t sparse = counters[C_SPARSE];
+        write_step_record(counters, ctl, ring, sparse ? 16u : 0u, sparse ? sparse - 1u : counters[C_ROUNDS]);
+    }
     __syncthreads();
     for (uint32_t k = threadIdx.x; k < (uint32_t)C_NCOUNTERS; k += blockDim.x) counters[k] = 0;
 }
@@ -831,7 +837,7 @@ __global__ void __launch_bounds__(128) epilogue_kernel(uint32_t* counters, uint3
 // contacts (the general path sorts such lists), a lopsided hash partition - it finds out BEFORE it has changed
 // anything; it then raises the same flag as a contact-buffer overflow (CTL_ABORT: every later step is a
 // no-op) plus bit 8 in its record, and the host re-runs the step through the general kernels at its next
-// synchronisation and stops predicting "sparse" for a while (collide.cu: predict_sparse, settle()).
+// synchronisation and stops predicting "sparse" for a while (collide.cu: predict_variant, settle()).
 #ifndef TR_SPARSE_CLUSTER
 #define TR_SPARSE_CLUSTER 16
 #endif
@@ -872,6 +878,7 @@ struct SparseArgs {
     const float4* half_ext;
     const uint8_t* flags;
     uint32_t n;
+    uint32_t tail_follows;   // prep_kernel, the executor and epilogue_kernel follow in the step's graph: what this kernel cannot take is theirs
 };
 
 constexpr uint32_t SPARSE_SPIN_LIMIT = 1u << 20;
@@ -1185,7 +1192,7 @@ __global__ void __cluster_dims__(SPARSE_CLUSTER, 1, 1) __launch_bounds__(SPARSE_
         if (found > a.cap) bail = true;                                      // a real overflow: the buffers must grow
         else if (found > SPARSE_MAX_CONTACTS || !sparse_replay(a, s, cluster, (uint32_t)found, key, rounds)) {
             bail = true;
-            extra = 8u;                                                      // not a sparse step: the general kernels must re-run it
+            extra = 8u;                                                      // not a sparse step: the general kernels must (re-)run it
         } else {
             extra = 16u;
         }
@@ -1193,6 +1200,11 @@ __global__ void __cluster_dims__(SPARSE_CLUSTER, 1, 1) __launch_bounds__(SPARSE_
         extra = 16u;
     }
     if (rank != 0) return;
+    if (a.tail_follows) {
+        // the general kernels come next in this graph: they take what this kernel left alone, and the epilogue writes the record
+        if (tid == 0 && extra == 16u) a.counters[C_SPARSE] = 1u + rounds;
+        return;
+    }
     if (tid == 0) {
         if (bail) a.ctl[CTL_ABORT] = a.ctl[CTL_SEQ] + 1u;
         write_step_record(a.counters, a.ctl, a.ring, extra, rounds);
