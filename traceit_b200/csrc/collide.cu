@@ -164,6 +164,23 @@ static int ensure_buffers(tr_world* w) {
     if (!c->sparse_smem_set) {   // (not at the launch: that can be inside a stream capture)
         TR_CUDA(cudaFuncSetAttribute(sparse_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SparseSmem)));
         if (SPARSE_CLUSTER > 8) TR_CUDA(cudaFuncSetAttribute(sparse_step_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        // can this device place one such cluster at all (a partitioned GPU, a GPC with fewer SMs)?  If not, every step is general.
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(SPARSE_CLUSTER);
+        cfg.blockDim = dim3(SPARSE_THREADS);
+        cfg.dynamicSmemBytes = sizeof(SparseSmem);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = SPARSE_CLUSTER;
+        attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&clusters, sparse_step_kernel, &cfg) != cudaSuccess) {
+            cudaGetLastError();
+            clusters = 0;
+        }
+        c->sparse_ok = clusters >= 1;
         c->sparse_smem_set = true;
     }
     if (n > c->cap_bodies) {
@@ -393,7 +410,7 @@ constexpr uint64_t SPARSE_HOPELESS = SPARSE_MAX_CONTACTS * 4;
 static StepVariant predict_variant(tr_world* w, Collide* c) {
     static const bool off = getenv("TR_NO_SPARSE") != nullptr;
     // (sharded worlds replicate the collision step: every rank must take the same decisions, and a peek is a matter of timing)
-    if (off || w->params.response_mode != 0 || (w->params.debug_flags & TR_DEBUG_NO_SPARSE) || w->nranks != 1) return STEP_GENERAL;
+    if (off || !c->sparse_ok || w->params.response_mode != 0 || (w->params.debug_flags & TR_DEBUG_NO_SPARSE) || w->nranks != 1) return STEP_GENERAL;
     if (w->h_ring) {
         if (c->peek_seq < w->ring_consumed) c->peek_seq = w->ring_consumed;
         while (c->peek_seq < w->coll_seq) {

@@ -128,7 +128,7 @@ struct Collide {
     uint32_t peek_seq = 0;
     uint64_t known_contacts = 0;       // contact count of the newest step whose record the host has seen
     bool known_valid = false;
-    bool sparse_smem_set = false;
+    bool sparse_smem_set = false, sparse_ok = false;   // kernel attributes set; the device can place the sparse-step kernel's cluster
 
     // what the host knows from the step records it has consumed so far
     uint64_t last_contacts = 0;

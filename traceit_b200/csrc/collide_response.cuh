@@ -849,13 +849,20 @@ constexpr uint32_t SPARSE_SLOTS = 4 * SPARSE_THREADS;        // hash slots per C
 constexpr uint32_t SPARSE_BODIES = 4 * SPARSE_THREADS;       // bodies one CTA can own (twice the expected number at the limit)
 constexpr uint32_t SPARSE_MAX_DEGREE = 64;     // contacts of one movable body (ranked by a linear scan of remote shared memory)
 constexpr uint32_t SPARSE_DIRTY = 0x80000000u;
+constexpr uint32_t SPARSE_BODIES_LOG2 = SPARSE_CLUSTER == 16 ? 10 : 11;
+static_assert((1u << SPARSE_BODIES_LOG2) == SPARSE_BODIES && 2u * SPARSE_MAX_CONTACTS == (1u << 13), "packing of a hash slot after P1");
+constexpr uint32_t SPARSE_DEG_SAT = (1u << (32 - SPARSE_BODIES_LOG2 - 13)) - 1u;
+static_assert(SPARSE_DEG_SAT > SPARSE_MAX_DEGREE, "a saturated degree must still read as too long");
+// hash slot after P1: local id | first half-edge slot | degree (saturating)
+__host__ __device__ constexpr uint32_t sparse_pack(uint32_t l, uint32_t off, uint32_t deg) {
+    return l | (off << SPARSE_BODIES_LOG2) | ((deg < SPARSE_DEG_SAT ? deg : SPARSE_DEG_SAT) << (SPARSE_BODIES_LOG2 + 13));
+}
 static_assert(SPARSE_CLUSTER == 8 || SPARSE_CLUSTER == 16, "owner = top bits of the hash");
 
 struct SparseSmem {
     uint32_t key[SPARSE_SLOTS];                // body id per slot
     uint32_t cnt[SPARSE_SLOTS];                // degree (bit 31: isStatic), after P1: local id
     uint32_t gid[SPARSE_BODIES];               // local id -> body id
-    uint2 seg[SPARSE_BODIES];                  // the body's half edges: {first, count}
     uint32_t he[2 * SPARSE_MAX_CONTACTS];      // partner ids, by segment (all half edges fit one CTA: no overflow case)
     // The mutable state, as in the dataflow executor's BodyRec: {vx, vy, vz, version}, {px, py, pz, version}; version = contacts
     // applied so far (bit 31: something changed).  Each half is read and written as ONE 128-bit access, so a reader that finds its
@@ -863,6 +870,8 @@ struct SparseSmem {
     // access per cycle per SM whatever its width - 4 accesses per body and hand-off instead of 14.
     uint4 rec[SPARSE_BODIES][2];
     uint32_t wsum[2][SPARSE_THREADS / 32];     // P1's CTA scan
+    uint4 stage[8][SPARSE_THREADS];            // the thread's gather, landing asynchronously: centre, velocity, position, half extents of i and j
+    uint32_t fstage[2][SPARSE_THREADS];        // ... and the aligned words that hold their flag bytes
     uint32_t nb, fail, rounds;                 // fail, rounds: CTA 0's copy is the cluster's
 };
 
@@ -898,16 +907,12 @@ __device__ __forceinline__ void st128_relaxed_cluster(uint4* p, const uint4 v) {
 }
 
 // slot of body b in the owner's table (EMPTY: table full)
-__device__ __forceinline__ uint32_t sparse_insert(uint32_t* keys, uint32_t b, uint32_t h, bool& fresh) {
+__device__ __forceinline__ uint32_t sparse_insert(uint32_t* keys, uint32_t b, uint32_t h) {
     for (uint32_t probes = 0; probes < SPARSE_SLOTS; ++probes) {
         const uint32_t old = atomicCAS(&keys[h], EMPTY, b);
-        if (old == EMPTY || old == b) {
-            fresh = old == EMPTY;
-            return h;
-        }
+        if (old == EMPTY || old == b) return h;
         h = (h + 1u) & (SPARSE_SLOTS - 1u);
     }
-    fresh = false;
     return EMPTY;
 }
 
@@ -930,26 +935,13 @@ __device__ __forceinline__ bool sparse_replay(const SparseArgs& a, SparseSmem& s
     reinterpret_cast<uint4*>(s.key)[tid] = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
     reinterpret_cast<uint4*>(s.cnt)[tid] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) s.nb = s.fail = s.rounds = 0;
-    // ---- gather
+    // (the bodies of this contact are on their way into s.stage - asynchronous copies issued by the caller; read after P1)
     uint32_t bi = 0, bj = 0;
-    uint8_t fi = 0, fj = 0;
-    float4 ci = make_float4(0.f, 0.f, 0.f, 0.f), cj = ci, hi = ci, hj = ci, vi = ci, vj = ci, pi = ci, pj = ci;
     if (have) {
         bi = (uint32_t)(key >> 32);
         bj = (uint32_t)key;
         TR_ASSERT(bi < bj && bj < a.n);
-        fi = a.flags[bi];
-        fj = a.flags[bj];
-        ci = a.center_r[bi];
-        cj = a.center_r[bj];
-        vi = a.vel_rest[bi];
-        vj = a.vel_rest[bj];
-        pi = a.pos_m[bi];
-        pj = a.pos_m[bj];
-        hi = a.half_ext[bi];                                 // (only boxes need them - but waiting for the flags to know
-        hj = a.half_ext[bj];                                 //  would put a second DRAM round trip in front of these)
     }
-    const bool sti = (fi & F_STATIC) != 0, stj = (fj & F_STATIC) != 0;
     SP_STAMP();
     cluster.sync();                                          // every CTA's tables are initialised
     SP_STAMP();
@@ -959,22 +951,19 @@ __device__ __forceinline__ bool sparse_replay(const SparseArgs& a, SparseSmem& s
     SparseSmem* sj = cluster.map_shared_rank(&s, hhj >> (32 - SPARSE_CLUSTER_LOG2));
     uint32_t sloti = 0, slotj = 0, ri = 0, rj = 0;
     if (have) {
-        bool fresh_i, fresh_j;
-        sloti = sparse_insert(si->key, bi, (hhi >> 16) & (SPARSE_SLOTS - 1u), fresh_i);
-        slotj = sparse_insert(sj->key, bj, (hhj >> 16) & (SPARSE_SLOTS - 1u), fresh_j);
+        sloti = sparse_insert(si->key, bi, (hhi >> 16) & (SPARSE_SLOTS - 1u));
+        slotj = sparse_insert(sj->key, bj, (hhj >> 16) & (SPARSE_SLOTS - 1u));
         if (sloti == EMPTY || slotj == EMPTY) {
             s0->fail = 1u;
         } else {
-            if (fresh_i && sti) atomicOr(&si->cnt[sloti], 0x80000000u);
-            if (fresh_j && stj) atomicOr(&sj->cnt[slotj], 0x80000000u);
-            ri = atomicAdd(&si->cnt[sloti], 1u) & 0x7FFFFFFFu;
-            rj = atomicAdd(&sj->cnt[slotj], 1u) & 0x7FFFFFFFu;
+            ri = atomicAdd(&si->cnt[sloti], 1u);
+            rj = atomicAdd(&sj->cnt[slotj], 1u);
         }
     }
     SP_STAMP();
     cluster.sync();
     SP_STAMP();
-    // ---- P1 (owners): dense local ids, half-edge segments for the movable bodies.  A thread owns SPARSE_SLOTS / 512
+    // ---- P1 (owners): dense local ids, half-edge segments.  A thread owns SPARSE_SLOTS / SPARSE_THREADS
     // consecutive slots; one CTA-wide exclusive scan of (occupied slots, half edges needed) places them.
     {
         constexpr uint32_t PER = SPARSE_SLOTS / SPARSE_THREADS;
@@ -985,7 +974,7 @@ __device__ __forceinline__ bool sparse_replay(const SparseArgs& a, SparseSmem& s
             const uint32_t k = s.key[tid * PER + q], raw = s.cnt[tid * PER + q];
             if (k != EMPTY) {
                 ++nocc;
-                if (!(raw >> 31)) nneed += raw;
+                nneed += raw;
             }
         }
         uint32_t iocc = nocc, ineed = nneed;
@@ -1013,14 +1002,13 @@ __device__ __forceinline__ bool sparse_replay(const SparseArgs& a, SparseSmem& s
         for (uint32_t q = 0; q < PER; ++q) {
             const uint32_t x = tid * PER + q, k = s.key[x], raw = s.cnt[x];
             if (k == EMPTY) continue;
-            const uint32_t need = (raw >> 31) ? 0u : raw;
-            if (l >= SPARSE_BODIES || need > SPARSE_MAX_DEGREE) {
+            const uint32_t need = raw;
+            if (l >= SPARSE_BODIES) {
                 bad = true;
             } else {
                 TR_ASSERT(off + need <= 2u * SPARSE_MAX_CONTACTS);
                 s.gid[l] = k;
-                s.seg[l] = make_uint2(off, need);
-                s.cnt[x] = l;
+                s.cnt[x] = sparse_pack(l, off, need);         // what a contact of this body needs in P2-P3, in one word
             }
             ++l;
             off += need;
@@ -1037,24 +1025,46 @@ __device__ __forceinline__ bool sparse_replay(const SparseArgs& a, SparseSmem& s
             return false;
         }
     }
-    // ---- P2: half edges; the first arrival deposits the body's state
-    uint32_t li = 0, lj = 0, oi = 0, oj = 0, di = 0, dj = 0;
+    // ---- the gather has landed (or nearly); then P2: half edges; the first arrival deposits the body's state
+    uint8_t fi = 0, fj = 0;
+    float4 ci = make_float4(0.f, 0.f, 0.f, 0.f), cj = ci, hi = ci, hj = ci, vi = ci, vj = ci, pi = ci, pj = ci;
+    asm volatile("cp.async.wait_all;" ::: "memory");           // this thread's own copies: no barrier needed to read them
     if (have) {
-        li = si->cnt[sloti];
-        lj = sj->cnt[slotj];
-        TR_ASSERT(li < SPARSE_BODIES && lj < SPARSE_BODIES);
+        fi = (uint8_t)(s.fstage[0][tid] >> (8u * (bi & 3u)));
+        fj = (uint8_t)(s.fstage[1][tid] >> (8u * (bj & 3u)));
+        const float4* st = reinterpret_cast<const float4*>(&s.stage[0][0]);
+        ci = st[0 * SPARSE_THREADS + tid];
+        cj = st[1 * SPARSE_THREADS + tid];
+        vi = st[2 * SPARSE_THREADS + tid];
+        vj = st[3 * SPARSE_THREADS + tid];
+        pi = st[4 * SPARSE_THREADS + tid];
+        pj = st[5 * SPARSE_THREADS + tid];
+        hi = st[6 * SPARSE_THREADS + tid];
+        hj = st[7 * SPARSE_THREADS + tid];
+    }
+    uint32_t li = 0, lj = 0, oi = 0, oj = 0, di = 0, dj = 0;
+    uint2 sgi = make_uint2(0u, 0u), sgj = sgi;
+    if (have) {
+        const uint32_t wi = si->cnt[sloti], wj = sj->cnt[slotj];
+        li = wi & (SPARSE_BODIES - 1u);
+        lj = wj & (SPARSE_BODIES - 1u);
+        sgi = make_uint2((wi >> SPARSE_BODIES_LOG2) & (2u * SPARSE_MAX_CONTACTS - 1u), wi >> (SPARSE_BODIES_LOG2 + 13));
+        sgj = make_uint2((wj >> SPARSE_BODIES_LOG2) & (2u * SPARSE_MAX_CONTACTS - 1u), wj >> (SPARSE_BODIES_LOG2 + 13));
+    }
+    const bool sti = (fi & F_STATIC) != 0, stj = (fj & F_STATIC) != 0;
+    if (have) {
+        // a static body is never changed, so nothing orders its contacts: its list is neither filled nor ranked, however long
         if (!sti) {
-            const uint2 sg = si->seg[li];
-            oi = sg.x;
-            di = sg.y;
+            oi = sgi.x;
+            di = sgi.y;
             si->he[oi + ri] = bj;
         }
         if (!stj) {
-            const uint2 sg = sj->seg[lj];
-            oj = sg.x;
-            dj = sg.y;
+            oj = sgj.x;
+            dj = sgj.y;
             sj->he[oj + rj] = bi;
         }
+        if (di > SPARSE_MAX_DEGREE || dj > SPARSE_MAX_DEGREE) s0->fail = 1u;   // a movable hub: the general path sorts such lists
         if (ri == 0) {
             si->rec[li][0] = make_uint4(__float_as_uint(vi.x), __float_as_uint(vi.y), __float_as_uint(vi.z), 0u);
             si->rec[li][1] = make_uint4(__float_as_uint(pi.x), __float_as_uint(pi.y), __float_as_uint(pi.z), 0u);
@@ -1076,6 +1086,13 @@ __device__ __forceinline__ bool sparse_replay(const SparseArgs& a, SparseSmem& s
     SP_STAMP();
     cluster.sync();
     SP_STAMP();
+    {
+        const uint32_t f = s0->fail;                         // (nothing has been written outside shared memory yet)
+        if (f) {
+            cluster.sync();
+            return false;
+        }
+    }
     // ---- P3: versions = rank by partner id among the body's contacts (a static body is never changed: nothing orders its contacts)
     uint32_t ei = 0, ej = 0;
     {
@@ -1181,11 +1198,27 @@ __global__ void __cluster_dims__(SPARSE_CLUSTER, 1, 1) __launch_bounds__(SPARSE_
     const uint32_t rank = cluster.block_rank(), tid = threadIdx.x;
     pdl_wait();
     if (rank == 0 && tid == 0) *reinterpret_cast<unsigned long long*>(a.counters + C_T0 + 4) = globaltimer_ns();
-    // this thread's contact, if the step has that many: fetched before the count is known (one DRAM round trip instead of two)
+    // this thread's contact, if the step has that many: fetched together with the count (one round trip instead of two)
     const uint32_t cidx = rank * SPARSE_THREADS + tid;
     const unsigned long long key = cidx < a.cap ? a.ckeys[cidx] : 0ull;
     const bool dead = a.ctl[CTL_ABORT] != 0;                 // an earlier step has to be re-run first
     const unsigned long long found = *reinterpret_cast<const unsigned long long*>(a.counters + C_CONTACTS);
+    if (!dead && cidx < found && found <= SPARSE_MAX_CONTACTS && found <= a.cap) {
+        // ... and its bodies straight behind it, as ASYNCHRONOUS copies into this thread's staging slots: after an L2 flush they
+        // cost ~3 us of DRAM + page-walk latency, which now runs under P0 and P1 - an ordinary load in flight would be waited for
+        // by the first cluster barrier (its release is a GPU-scope MEMBAR), and a prefetch is dropped on the TLB miss (both measured)
+        const uint32_t gi = (uint32_t)(key >> 32), gj = (uint32_t)key;
+        TR_ASSERT(gi < gj && gj < a.n);
+        {
+            const void* src[8] = {a.center_r + gi, a.center_r + gj, a.vel_rest + gi, a.vel_rest + gj, a.pos_m + gi, a.pos_m + gj, a.half_ext + gi, a.half_ext + gj};
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(&s.stage[k][tid])), "l"(src[k]) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(&s.fstage[0][tid])), "l"(a.flags + (gi & ~3u)) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(&s.fstage[1][tid])), "l"(a.flags + (gj & ~3u)) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     uint32_t rounds = 0, extra = 0;
     bool bail = false;
     if (!dead && found != 0) {
