@@ -951,8 +951,11 @@ __device__ __forceinline__ bool sparse_replay(const SparseArgs& a, SparseSmem& s
     SparseSmem* sj = cluster.map_shared_rank(&s, hhj >> (32 - SPARSE_CLUSTER_LOG2));
     uint32_t sloti = 0, slotj = 0, ri = 0, rj = 0;
     if (have) {
-        sloti = sparse_insert(si->key, bi, (hhi >> 16) & (SPARSE_SLOTS - 1u));
-        slotj = sparse_insert(sj->key, bj, (hhj >> 16) & (SPARSE_SLOTS - 1u));
+        // (first probes of both bodies in flight together, then both counts: two remote round trips instead of four)
+        const uint32_t h0i = (hhi >> 16) & (SPARSE_SLOTS - 1u), h0j = (hhj >> 16) & (SPARSE_SLOTS - 1u);
+        const uint32_t oldi = atomicCAS(&si->key[h0i], EMPTY, bi), oldj = atomicCAS(&sj->key[h0j], EMPTY, bj);
+        sloti = (oldi == EMPTY || oldi == bi) ? h0i : sparse_insert(si->key, bi, (h0i + 1u) & (SPARSE_SLOTS - 1u));
+        slotj = (oldj == EMPTY || oldj == bj) ? h0j : sparse_insert(sj->key, bj, (h0j + 1u) & (SPARSE_SLOTS - 1u));
         if (sloti == EMPTY || slotj == EMPTY) {
             s0->fail = 1u;
         } else {
@@ -1167,9 +1170,8 @@ __device__ __forceinline__ bool sparse_replay(const SparseArgs& a, SparseSmem& s
         if (__any_sync(0xFFFFFFFFu, stalled) && lane == 0) a.counters[C_ABORT] = 1u;   // reported like the executors' watchdog
     }
     SP_STAMP();
-    cluster.sync();                                          // the replay is complete everywhere
-    rounds = s0->rounds;
-    cluster.sync();                                          // CTA 0 stays until everybody has read it
+    cluster.sync();                                          // the replay is complete everywhere; nobody touches remote shared memory any more
+    rounds = s.rounds;                                       // (CTA 0's is the cluster's; only CTA 0 uses it)
     // ---- P6 (owners): changed bodies back to the SoA state
     const uint32_t nb = s.nb;
     for (uint32_t l = tid; l < nb; l += SPARSE_THREADS) {
