@@ -24,6 +24,10 @@
 //       response_flow_kernel the ordered replay: a contact runs when the previous contact of BOTH its
 //                            bodies has run, so results are bit-identical to the sequential sweep.
 //       epilogue_kernel      the step's record for the host (mapped pinned ring), counters re-armed.
+//   K6s sparse_step_kernel   a step with few contacts: ordering + ordered replay + record in ONE kernel of one
+//                            16-CTA cluster, in distributed shared memory - instead of, or in front of, the three
+//                            K6 kernels (StepVariant below).
+//   K3a, K3b, K5, K6s are programmatic dependent launches: scheduled while their predecessor drains.
 // Worlds of up to TINY_MAX bodies skip all of that: tiny_step_kernel (tiny.cuh) runs whole steps in one CTA.
 //
 // The contact SET is a pure function of collider centres/radii (the sweep never writes

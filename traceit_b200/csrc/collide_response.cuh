@@ -817,27 +817,36 @@ __global__ void __launch_bounds__(128) epilogue_kernel(uint32_t* counters, uint3
 // A step with a few thousand contacts (the 1M random cloud: ~2,500; most frames of a real scene) has
 // nothing to spread over a grid: prep_kernel's phases, the dataflow executor and the epilogue are then
 // three launches of pure latency - grid barriers and L2 round trips, 33 us for 2,504 contacts.  When the
-// host expects such a step (the last record it has seen says so) the step's graph ends, after the narrow
-// phase, in this kernel instead: 8 CTAs x 512 threads = one contact per thread, all bookkeeping and the
-// bodies' mutable state in DISTRIBUTED SHARED MEMORY (a hand-off costs ~215 cycles instead of an L2 round
-// trip), cluster barriers (~380 cycles) instead of grid barriers:
-//   gather  the contact's bodies: flags, collider centres, velocity, position (the only DRAM-cold reads; in flight across P0-P2)
+// host expects such a step (the newest record it has seen says so), or does not know (then the general
+// kernels follow in the graph and return at once if this one has done the step), the narrow phase is followed
+// by this kernel: 16 CTAs x 256 threads = one contact per thread, all bookkeeping and the bodies' mutable
+// state in DISTRIBUTED SHARED MEMORY (a hand-off costs a few hundred cycles instead of an L2 round trip),
+// cluster barriers instead of grid barriers:
+//   gather  the contact's bodies (collider centres, velocity, position, half extents, flags): the step's only
+//           DRAM-cold reads, issued by the kernel as asynchronous copies into per-thread staging slots so that
+//           they run under P0-P1 (a cluster barrier's release is a GPU-scope MEMBAR: it waits for ordinary loads)
 //   P0      a body belongs to the CTA its id hashes to; (remote) atomicCAS into that CTA's hash table,
 //           (remote) atomicAdd on the slot's counter = degree + arrival rank
-//   P1      owners: occupied slots get dense local ids and half-edge segments (warp-aggregated)
-//   P2      half edges (partner id) into the owners' segments; the first arrival deposits the body's velocity + position
+//   P1      owners: occupied slots get dense local ids and half-edge segments (one CTA scan); local id, segment
+//           and degree go back into the slot word
+//   P2      half edges (partner id) into the owners' segments - not for static bodies, which order nothing;
+//           a movable body with more than SPARSE_MAX_DEGREE contacts fails the step here; the first arrival
+//           deposits the body's velocity + position record
 //   P3      rank of the contact among the contacts of both its bodies (= the version it must see)
-//   P5      rounds: a contact whose two bodies are at its versions is applied on the owners' copies; two cluster
-//           barriers per round
-//   P6      owners write the changed bodies back; CTA 0 writes the step's record and re-arms the counters.
+//   P5      the replay, without barriers: poll both bodies' records, apply when both carry the contact's
+//           versions, store them back with the next versions
+//   P6      owners write the changed bodies back; CTA 0 writes the step's record and re-arms the counters
+//           (or, with the general kernels behind it, only tells them that the step is done).
 // Same order, same arithmetic (respond_rec's), same bits as the other executors.  One CTA alone cannot do
 // this: shared-memory atomics and scattered stores run at ~1 per cycle per SM, 2,500 contacts x ~20 of them
-// took 45 us on one SM.
+// took 45 us on one SM; remote shared memory, too, moves ~1 access per cycle per SM - hence 128-bit records
+// and 16 CTAs rather than 8.
 // What the kernel cannot take - more than 4,096 contacts, a movable body with more than SPARSE_MAX_DEGREE
 // contacts (the general path sorts such lists), a lopsided hash partition - it finds out BEFORE it has changed
-// anything; it then raises the same flag as a contact-buffer overflow (CTL_ABORT: every later step is a
-// no-op) plus bit 8 in its record, and the host re-runs the step through the general kernels at its next
-// synchronisation and stops predicting "sparse" for a while (collide.cu: predict_variant, settle()).
+// anything.  With the general kernels behind it in the graph it simply leaves the step to them; alone, it raises
+// the same flag as a contact-buffer overflow (CTL_ABORT: every later step is a no-op) plus bit 8 in its record,
+// and the host re-runs the step through the general kernels at its next synchronisation and is less confident
+// for a while (collide.cu: predict_variant; api.cu: settle()).
 #ifndef TR_SPARSE_CLUSTER
 #define TR_SPARSE_CLUSTER 16
 #endif
@@ -861,7 +870,7 @@ static_assert(SPARSE_CLUSTER == 8 || SPARSE_CLUSTER == 16, "owner = top bits of 
 
 struct SparseSmem {
     uint32_t key[SPARSE_SLOTS];                // body id per slot
-    uint32_t cnt[SPARSE_SLOTS];                // degree (bit 31: isStatic), after P1: local id
+    uint32_t cnt[SPARSE_SLOTS];                // degree; after P1: sparse_pack(local id, first half-edge slot, degree)
     uint32_t gid[SPARSE_BODIES];               // local id -> body id
     uint32_t he[2 * SPARSE_MAX_CONTACTS];      // partner ids, by segment (all half edges fit one CTA: no overflow case)
     // The mutable state, as in the dataflow executor's BodyRec: {vx, vy, vz, version}, {px, py, pz, version}; version = contacts
@@ -1184,7 +1193,7 @@ __device__ __forceinline__ bool sparse_replay(const SparseArgs& a, SparseSmem& s
     SP_STAMP();
 #ifdef TR_SPARSE_PROF
     if (rank == 0 && tid == 0) {
-        printf("[TR_SPARSE_PROF] contacts %u rounds %u; cycles init+gather | sync | P0 | sync | P1 | sync | P2+constants | sync | P3 | rounds | write-back:", cn, rounds);
+        printf("[TR_SPARSE_PROF] contacts %u rounds %u; cycles init | sync | P0 | sync | P1 | sync | gather wait + P2 + constants | sync | P3 | replay | sync + write-back:", cn, rounds);
         for (int k = 1; k < sp_n; ++k) printf(" %lld", sp_t[k] - sp_t[k - 1]);
         printf("\n");
     }
